@@ -1,0 +1,375 @@
+// conv_tc.cu - 3x3 / 1x1 stride-1 convolution as an implicit GEMM on the Blackwell 5th-gen tensor cores.
+//
+// Stands in for every nn.Conv2d(k=3,pad=1) / Conv2d(k=1) / Conv1d(k=1) of the UNet
+// (reference guided_diffusion/unet.py:185, 211, 222, 286, 294, 482, 615) in the fp16-operand / fp32-accumulate mode.
+//
+//   D[m][n] = sum_{tap} sum_{c} A_tap[m][c] * Wt[tap][n][c]        m = output pixel, n = output channel
+//
+// * A operand: activations NHWC fp16.  One M tile = 128 output pixels = a (TN x TH x TW) box of the image
+//   (TW*TH*TN = 128).  For tap (dy,dx) the A tile is the SAME box shifted by (dy-1, dx-1); it is fetched by ONE 4-D TMA
+//   (cp.async.bulk.tensor.4d) whose out-of-bounds rows/cols/images are zero-filled by the hardware - that is the conv's
+//   zero padding, so no im2col buffer, no halo logic and no predication exists anywhere.
+// * B operand: weights fp16 packed [tap][CoutPad][Cin] (K-major), fetched by a 3-D TMA.
+// * Both land in shared memory in the canonical K-major SWIZZLE_128B layout (64 fp16 = 128 B per row), consumed directly
+//   by tcgen05.mma (kind::f16, M=128, N=BN, K=16) through shared-memory matrix descriptors; fp32 accumulators live in
+//   TMEM (128 lanes x BN columns).
+// * Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+//   warps 2-5 = epilogue (tcgen05.ld 32x32b -> registers -> bias / residual / NCHW / eps->x0 -> global).
+// * STAGES-deep smem ring with full/empty mbarriers; MMA completion releases a stage via tcgen05.commit.
+//   Two CTAs fit per SM (3 x 32 KB stages, 128 TMEM columns each) so one CTA's epilogue overlaps the other's main loop.
+#include "unet_kernels.cuh"
+
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+namespace dpir {
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok;
+}
+// bounded spin: a broken pipeline traps after ~2 s instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *m) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *m, uint64_t *bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *m, uint64_t *bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+template <int COLS> __device__ __forceinline__ void tmem_alloc(uint32_t *slot) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "n"(COLS) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int COLS> __device__ __forceinline__ void tmem_dealloc(uint32_t addr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "n"(COLS) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, kind::f16 (fp16 in, fp32 accumulate), issued by ONE thread
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t *r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t *r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (sm_100 format): start address >> 4 in bits [0,14),
+// LBO (ignored for swizzled K-major) = 1 in [16,30), SBO = 1024 B (8 rows x 128 B) >> 4 in [32,46), version 1 in [46,48),
+// layout type SWIZZLE_128B = 2 in [61,64).
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// ------------------------------------------------------------------------------------------------ kernel
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;                       // fp16 elements per K chunk = 128 bytes = one swizzle row
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;   // 16 KB
+constexpr int TC_THREADS = 192;
+
+struct ConvTcGeom {
+  int B, H, W, Cin, Cout, taps, ksize;
+  int TW, TH, TN;             // M-tile box (TW*TH*TN == 128)
+  int tiles_w, tiles_h, tiles_n;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS) k_conv_tc(const __grid_constant__ CUtensorMap tmA,
+                                                         const __grid_constant__ CUtensorMap tmB, ConvTcGeom g, ConvEpi epi) {
+  constexpr int B_BYTES = BN * TC_BK * 2;
+  constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
+  constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  // instruction descriptor: D=f32 (bit 4), A=B=f16 (0), K-major both, N>>3 at bit 17, M>>4 at bit 24
+  constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
+  uint64_t *empty = full + STAGES;
+  uint64_t *tmem_full = empty + STAGES;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mt = blockIdx.x;
+  const int w0 = (mt % g.tiles_w) * g.TW;
+  const int h0 = ((mt / g.tiles_w) % g.tiles_h) * g.TH;
+  const int n0 = (mt / (g.tiles_w * g.tiles_h)) * g.TN;
+  const int co0 = blockIdx.y * BN;
+  const int chunks = g.Cin / TC_BK;
+  const int num_k = g.taps * chunks;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int pad = g.ksize / 2;
+      for (int k = 0; k < num_k; ++k) {
+        const int s = k % STAGES;
+        const uint32_t ph = (uint32_t)(k / STAGES) & 1u;
+        mbar_wait(&empty[s], ph ^ 1u);
+        const int tap = k / chunks, ch = k - tap * chunks;
+        const int dy = tap / g.ksize - pad, dx = tap % g.ksize - pad;
+        uint8_t *sa = smem + s * STAGE_BYTES;
+        mbar_expect_tx(&full[s], STAGE_BYTES);
+        tma_load_4d(sa, &tmA, &full[s], ch * TC_BK, w0 + dx, h0 + dy, n0);
+        tma_load_3d(sa + TC_A_BYTES, &tmB, &full[s], ch * TC_BK, co0, tap);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      for (int k = 0; k < num_k; ++k) {
+        const int s = k % STAGES;
+        const uint32_t ph = (uint32_t)(k / STAGES) & 1u;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+        const uint64_t adesc = make_sw128_desc(sa);
+        const uint64_t bdesc = make_sw128_desc(sa + TC_A_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < TC_BK / 16; ++kk) {
+          // advance 16 fp16 = 32 bytes along K inside the 128 B swizzle row: +2 in the (>>4) address field
+          umma_f16(tmem_base, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), IDESC, (k | kk) ? 1u : 0u);
+        }
+        umma_commit(&empty[s]);   // stage reusable once these MMAs have read it
+      }
+      umma_commit(tmem_full);     // accumulator complete
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue: 4 warps x 32 TMEM lanes
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;          // M index inside the tile
+    const int xw = w0 + row % g.TW;
+    const int yh = h0 + (row / g.TW) % g.TH;
+    const int n = n0 + row / (g.TW * g.TH);
+    const bool valid = (n < g.B) && (yh < g.H) && (xw < g.W);
+    const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16);
+    if (BN >= 32) {
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t r[32];
+        tmem_ld32(tbase + (uint32_t)c, r);
+        tmem_ld_wait();
+        if (valid) {
+          const int co = co0 + c;
+          if (epi.mode == EPI_NHWC) {
+            const int64_t pix = ((int64_t)n * g.H + yh) * g.W + xw;
+            float *o = epi.out + pix * g.Cout + co;
+            const float *rs = epi.residual ? epi.residual + pix * g.Cout + co : nullptr;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (co + j < g.Cout) {
+                float4 b4 = __ldg(reinterpret_cast<const float4 *>(epi.bias + co + j));
+                float4 v = make_float4(__uint_as_float(r[j]) + b4.x, __uint_as_float(r[j + 1]) + b4.y,
+                                       __uint_as_float(r[j + 2]) + b4.z, __uint_as_float(r[j + 3]) + b4.w);
+                if (rs) {
+                  float4 rv = *reinterpret_cast<const float4 *>(rs + j);
+                  v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
+                }
+                *reinterpret_cast<float4 *>(o + j) = v;
+              }
+            }
+          } else {
+            float acc[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(r[j]);
+            int ncols = g.Cout - co;
+            if (ncols > 32) ncols = 32;
+            if (ncols > 0) conv_epilogue_store(epi, n, yh, xw, g.H, g.W, g.Cout, co, acc, ncols);
+          }
+        }
+      }
+    } else {
+      uint32_t r[16];
+      tmem_ld16(tbase, r);
+      tmem_ld_wait();
+      if (valid) {
+        float acc[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(r[j]);
+        int ncols = g.Cout - co0;
+        if (ncols > 16) ncols = 16;
+        if (ncols > 0) conv_epilogue_store(epi, n, yh, xw, g.H, g.W, g.Cout, co0, acc, ncols);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+struct ConvTcPlan {
+  CUtensorMap tmA, tmB;
+  ConvTcGeom g;
+  int BN, CoutPad;
+};
+
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }
+  return fn;
+}
+
+static int pow2_ge(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+int conv_tc_plan_create(const void *act_half, const void *w_half, int B, int H, int W, int Cin, int CoutPad, int ksize,
+                        ConvTcPlan **out) {
+  DPIR_REQUIRE(Cin % TC_BK == 0, "conv_tc: Cin must be a multiple of 64 (got %d)", Cin);
+  DPIR_REQUIRE(ksize == 1 || ksize == 3, "conv_tc: ksize must be 1 or 3");
+  DPIR_REQUIRE(CoutPad == 16 || CoutPad % 128 == 0, "conv_tc: padded Cout must be 16 or a multiple of 128 (got %d)", CoutPad);
+  DPIR_REQUIRE((((uintptr_t)act_half | (uintptr_t)w_half) & 15) == 0, "conv_tc: operands must be 16-byte aligned");
+  auto encode = get_encode_fn();
+  if (!encode) { set_error("conv_tc: cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)"); return DPIR_E_CUDA; }
+  ConvTcPlan *p = new ConvTcPlan();
+  ConvTcGeom &g = p->g;
+  g.B = B; g.H = H; g.W = W; g.Cin = Cin; g.Cout = 0; g.ksize = ksize; g.taps = ksize * ksize;
+  g.TW = W >= 128 ? 128 : pow2_ge(W);
+  int th = 128 / g.TW;
+  g.TH = th < pow2_ge(H) ? th : pow2_ge(H);
+  g.TN = 128 / (g.TW * g.TH);
+  g.tiles_w = cdiv(W, g.TW); g.tiles_h = cdiv(H, g.TH); g.tiles_n = cdiv(B, g.TN);
+  p->BN = CoutPad == 16 ? 16 : 128;
+  p->CoutPad = CoutPad;
+  {
+    cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t gstr[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
+    cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)g.TW, (cuuint32_t)g.TH, (cuuint32_t)g.TN};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = encode(&p->tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(act_half), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled(A) failed: %d", (int)r); delete p; return DPIR_E_CUDA; }
+  }
+  {
+    cuuint64_t gdim[3] = {(cuuint64_t)Cin, (cuuint64_t)CoutPad, (cuuint64_t)g.taps};
+    cuuint64_t gstr[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)CoutPad * Cin * 2};
+    cuuint32_t box[3] = {(cuuint32_t)TC_BK, (cuuint32_t)p->BN, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode(&p->tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void *>(w_half), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled(B) failed: %d", (int)r); delete p; return DPIR_E_CUDA; }
+  }
+  *out = p;
+  return DPIR_OK;
+}
+
+void conv_tc_plan_destroy(ConvTcPlan *p) { delete p; }
+
+template <int BN, int STAGES>
+static int launch_tc_impl(const ConvTcPlan *p, const ConvTcGeom &g, const ConvEpi &epi, cudaStream_t st) {
+  constexpr int smem = STAGES * (TC_A_BYTES + BN * TC_BK * 2) + 1024 + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DPIR_CUDA_CHECK(cudaFuncSetAttribute(k_conv_tc<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  dim3 grid(g.tiles_w * g.tiles_h * g.tiles_n, p->CoutPad / BN);
+  k_conv_tc<BN, STAGES><<<grid, TC_THREADS, smem, st>>>(p->tmA, p->tmB, g, epi);
+  DPIR_LAUNCH_CHECK();
+  return DPIR_OK;
+}
+
+int launch_conv_tc(const ConvTcPlan *p, const ConvEpi &epi, int Cout, cudaStream_t st) {
+  DPIR_REQUIRE(Cout <= p->CoutPad, "conv_tc: Cout exceeds padded weight rows");
+  DPIR_REQUIRE(epi.mode != EPI_NHWC || Cout % 4 == 0, "conv_tc: NHWC epilogue needs Cout %% 4 == 0");
+  ConvTcGeom g = p->g;
+  g.Cout = Cout;
+  if (p->BN == 16) return launch_tc_impl<16, 4>(p, g, epi, st);
+  return launch_tc_impl<128, 3>(p, g, epi, st);
+}
+
+}  // namespace dpir

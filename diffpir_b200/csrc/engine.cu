@@ -1,0 +1,856 @@
+// engine.cu - the UNet denoiser engine behind dpir_create / dpir_load_weight / dpir_unet_forward / dpir_unet_x0.
+//
+// Replays guided_diffusion/unet.py:479-618 (UNetModel.__init__) from dpir_unet_config to get the block structure, packs
+// the checkpoint tensors into kernel-native layouts inside one device arena (so a single NCCL broadcast moves the
+// model), and turns UNetModel.forward (unet.py:634-663) into a flat "tape" of kernel launches per
+// batch shape: activations live in one workspace carved by a lifetime-aware pool at plan time; no allocation,
+// synchronisation or host-device copy happens inside a forward.
+#include "unet_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+using namespace dpir;
+
+namespace {
+
+constexpr size_t ALIGN = 256;
+static inline size_t align_up(size_t v, size_t a = ALIGN) { return (v + a - 1) / a * a; }
+
+// ---------------------------------------------------------------------------------------------- structure
+struct LayerDesc {
+  int kind;  // 0 conv(stem), 1 res, 2 attn
+  std::string prefix;
+  int cin = 0, cout = 0, updown = 0 /*RS_*/, heads = 0;
+};
+
+// how a checkpoint tensor is repacked
+enum PackKind { PK_COPY, PK_CONV_STEM, PK_CONV, PK_FILM_W, PK_FILM_B };
+struct ParamSlot {
+  PackKind kind;
+  std::vector<int64_t> shape;
+  size_t off = 0;      // byte offset in the arena
+  size_t bytes = 0;    // packed bytes
+  int ldw = 0;         // padded Cout (fp32: %4, fp16: 16 or %128)
+  int film_row = 0;    // PK_FILM_*: first row in the concatenated FiLM matrix
+  bool loaded = false;
+};
+
+struct ConvW { size_t w_off = 0, b_off = 0; int cin = 0, cout = 0, ldw = 0, ksize = 3; };
+struct NormW { size_t g_off = 0, b_off = 0; };
+struct ResW { NormW n1, n2; ConvW c1, c2, skip; bool has_skip = false; int film_row = 0; };
+struct AttnW { NormW n; ConvW qkv, proj; };
+
+struct Buf {   // workspace tensor
+  size_t off = 0, bytes = 0;
+  int B = 0, H = 0, W = 0, C = 0;
+  bool half = false;
+  int refs = 0;
+  int id = -1;
+};
+
+enum OpKind { OP_MEMSET, OP_TIME_EMBED, OP_FILM, OP_CONV_IN, OP_GN_STATS, OP_GN_APPLY, OP_CONV, OP_ATTN };
+struct Op {
+  OpKind kind;
+  // generic pointers / ints, interpreted per kind
+  GnApplyArgs gn{};
+  ConvEpi epi{};
+  const void *p0 = nullptr, *p1 = nullptr, *p2 = nullptr;   // workspace tensors (offset-encoded until the plan is rebased)
+  void *q0 = nullptr;                                        // workspace tensor (output)
+  const void *w = nullptr;                                   // absolute pointer into the weight arena
+  size_t bytes = 0;
+  int B = 0, H = 0, W = 0, C1 = 0, C2 = 0, Cin = 0, Cout = 0, ldw = 0, ksize = 0, heads = 0, HW = 0, out_half = 0;
+  ConvTcPlan *tc = nullptr;
+  bool bind_x = false, bind_t = false, bind_out = false;   // patched with call arguments at launch
+};
+
+struct Plan {
+  int B = 0, H = 0, W = 0;
+  std::vector<Op> ops;
+  std::vector<ConvTcPlan *> tc_plans;
+  size_t ws_bytes = 0;
+  int final_conv = -1;
+  cudaGraphExec_t graph_nchw = nullptr, graph_x0 = nullptr;
+  ~Plan() {
+    for (auto *p : tc_plans) conv_tc_plan_destroy(p);
+    if (graph_nchw) cudaGraphExecDestroy(graph_nchw);
+    if (graph_x0) cudaGraphExecDestroy(graph_x0);
+  }
+};
+
+// first-fit offset pool with coalescing; used only at plan time
+struct Pool {
+  struct Blk { size_t off, size; bool free; };
+  std::vector<Blk> blks;
+  size_t peak = 0;
+  size_t alloc(size_t n) {
+    n = align_up(n, 1024);
+    for (size_t i = 0; i < blks.size(); ++i) {
+      if (blks[i].free && blks[i].size >= n) {
+        if (blks[i].size > n) {
+          Blk rest{blks[i].off + n, blks[i].size - n, true};
+          blks[i].size = n;
+          blks.insert(blks.begin() + i + 1, rest);
+        }
+        blks[i].free = false;
+        return blks[i].off;
+      }
+    }
+    size_t off = blks.empty() ? 0 : blks.back().off + blks.back().size;
+    if (!blks.empty() && blks.back().free) {   // grow the trailing free block
+      off = blks.back().off;
+      blks.back().size = n;
+      blks.back().free = false;
+    } else {
+      blks.push_back(Blk{off, n, false});
+    }
+    peak = std::max(peak, off + n);
+    return off;
+  }
+  void release(size_t off) {
+    for (size_t i = 0; i < blks.size(); ++i) {
+      if (blks[i].off == off && !blks[i].free) {
+        blks[i].free = true;
+        if (i + 1 < blks.size() && blks[i + 1].free) { blks[i].size += blks[i + 1].size; blks.erase(blks.begin() + i + 1); }
+        if (i > 0 && blks[i - 1].free) { blks[i - 1].size += blks[i].size; blks.erase(blks.begin() + i); }
+        return;
+      }
+    }
+  }
+};
+
+}  // namespace
+
+struct dpir_engine {
+  dpir_unet_config cfg{};
+  bool half = false;
+  int ted = 0, ch0 = 0;
+  std::vector<std::vector<LayerDesc>> inputs, middle, outputs;
+  std::map<std::string, ParamSlot> slots;
+  std::map<std::string, ResW> resw;
+  std::map<std::string, AttnW> attnw;
+  ConvW stem, outconv;
+  NormW outnorm;
+  size_t te_w0 = 0, te_b0 = 0, te_w2 = 0, te_b2 = 0, film_w = 0, film_b = 0, freqs_off = 0, coef_off = 0;
+  int film_rows = 0;
+  uint8_t *arena = nullptr;
+  size_t arena_bytes = 0;
+  uint8_t *ws = nullptr;
+  size_t ws_bytes = 0;
+  std::map<std::tuple<int, int, int>, std::unique_ptr<Plan>> plans;
+  int graph_mode = 0;
+  // staging buffers for graph mode (fixed addresses baked into the graph)
+  float *g_x = nullptr, *g_out = nullptr;
+  int64_t *g_t = nullptr;
+  size_t g_cap = 0;
+
+  template <typename T> T *ap(size_t off) const { return reinterpret_cast<T *>(arena + off); }
+};
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------- construction
+int build_structure(dpir_engine *e) {
+  const dpir_unet_config &c = e->cfg;
+  DPIR_REQUIRE(c.model_channels > 0 && c.model_channels % 128 == 0, "model_channels must be a positive multiple of 128");
+  DPIR_REQUIRE(c.n_channel_mult >= 1 && c.n_channel_mult <= 8, "bad channel_mult");
+  DPIR_REQUIRE(c.in_channels >= 1 && c.in_channels <= 4, "in_channels must be 1..4");
+  DPIR_REQUIRE(c.out_channels >= 3 && c.out_channels <= 16, "out_channels must be 3..16");
+  auto has_att = [&](int ds) {
+    for (int i = 0; i < c.n_attention_ds; ++i) if (c.attention_ds[i] == ds) return true;
+    return false;
+  };
+  int nh_up = c.num_heads_upsample == -1 ? c.num_heads : c.num_heads_upsample;
+  auto heads = [&](int ch, int nh) { return c.num_head_channels == -1 ? nh : ch / c.num_head_channels; };
+  int mc = c.model_channels;
+  int ch = c.channel_mult[0] * mc;
+  e->ch0 = ch;
+  e->ted = mc * 4;
+  std::vector<int> chans;
+  auto mk = [](int kind, std::string p, int cin, int cout, int ud = 0, int hd = 0) {
+    LayerDesc l; l.kind = kind; l.prefix = std::move(p); l.cin = cin; l.cout = cout; l.updown = ud; l.heads = hd; return l;
+  };
+  e->inputs.push_back({mk(0, "input_blocks.0.0.", c.in_channels, ch)});
+  chans.push_back(ch);
+  int ds = 1;
+  for (int level = 0; level < c.n_channel_mult; ++level) {
+    int mult = c.channel_mult[level];
+    for (int r = 0; r < c.num_res_blocks; ++r) {
+      int i = (int)e->inputs.size();
+      std::vector<LayerDesc> blk;
+      blk.push_back(mk(1, "input_blocks." + std::to_string(i) + ".0.", ch, mult * mc));
+      ch = mult * mc;
+      if (has_att(ds)) blk.push_back(mk(2, "input_blocks." + std::to_string(i) + ".1.", ch, ch, 0, heads(ch, c.num_heads)));
+      e->inputs.push_back(blk);
+      chans.push_back(ch);
+    }
+    if (level != c.n_channel_mult - 1) {
+      int i = (int)e->inputs.size();
+      e->inputs.push_back({mk(1, "input_blocks." + std::to_string(i) + ".0.", ch, ch, RS_DOWN)});
+      chans.push_back(ch);
+      ds *= 2;
+    }
+  }
+  e->middle.push_back({mk(1, "middle_block.0.", ch, ch), mk(2, "middle_block.1.", ch, ch, 0, heads(ch, c.num_heads)),
+                       mk(1, "middle_block.2.", ch, ch)});
+  for (int level = c.n_channel_mult - 1; level >= 0; --level) {
+    int mult = c.channel_mult[level];
+    for (int i = 0; i <= c.num_res_blocks; ++i) {
+      int ich = chans.back();
+      chans.pop_back();
+      int o = (int)e->outputs.size();
+      std::string pre = "output_blocks." + std::to_string(o) + ".";
+      std::vector<LayerDesc> blk;
+      blk.push_back(mk(1, pre + "0.", ch + ich, mc * mult));
+      ch = mc * mult;
+      if (has_att(ds)) blk.push_back(mk(2, pre + std::to_string(blk.size()) + ".", ch, ch, 0, heads(ch, nh_up)));
+      if (level && i == c.num_res_blocks) {
+        blk.push_back(mk(1, pre + std::to_string(blk.size()) + ".", ch, ch, RS_UP));
+        ds /= 2;
+      }
+      e->outputs.push_back(blk);
+    }
+  }
+  return DPIR_OK;
+}
+
+struct ArenaBuilder {
+  size_t cur = 0;
+  size_t take(size_t bytes) { size_t o = cur; cur = align_up(cur + bytes); return o; }
+};
+
+int conv_ldw(bool half, int cout) {
+  if (half) return cout < 16 ? 16 : cout;
+  return (cout + 3) / 4 * 4;
+}
+
+int build_params(dpir_engine *e) {
+  ArenaBuilder ab;
+  const bool half = e->half;
+  auto add = [&](const std::string &name, PackKind kind, std::vector<int64_t> shape, size_t bytes, int ldw = 0) -> ParamSlot & {
+    ParamSlot s;
+    s.kind = kind; s.shape = std::move(shape); s.bytes = bytes; s.ldw = ldw;
+    if (kind != PK_FILM_W && kind != PK_FILM_B) s.off = ab.take(bytes);
+    e->slots[name] = s;
+    return e->slots[name];
+  };
+  auto add_vec = [&](const std::string &name, int n) { return add(name, PK_COPY, {n}, (size_t)n * 4).off; };
+  auto add_conv = [&](const std::string &pre, int cin, int cout, int ksize, bool conv1d) {
+    ConvW w;
+    w.cin = cin; w.cout = cout; w.ksize = ksize; w.ldw = conv_ldw(half, cout);
+    size_t bytes = (size_t)ksize * ksize * cin * w.ldw * (half ? 2 : 4);
+    std::vector<int64_t> shape = conv1d ? std::vector<int64_t>{cout, cin, 1} : std::vector<int64_t>{cout, cin, ksize, ksize};
+    w.w_off = add(pre + "weight", PK_CONV, shape, bytes, w.ldw).off;
+    w.b_off = add(pre + "bias", PK_COPY, {cout}, (size_t)conv_ldw(false, cout) * 4).off;
+    return w;
+  };
+  int ted = e->ted, mc = e->cfg.model_channels;
+  e->te_w0 = add("time_embed.0.weight", PK_COPY, {ted, mc}, (size_t)ted * mc * 4).off;
+  e->te_b0 = add_vec("time_embed.0.bias", ted);
+  e->te_w2 = add("time_embed.2.weight", PK_COPY, {ted, ted}, (size_t)ted * ted * 4).off;
+  e->te_b2 = add_vec("time_embed.2.bias", ted);
+  // first pass: count FiLM rows
+  int film_rows = 0;
+  auto each_layer = [&](auto fn) {
+    for (auto *grp : {&e->inputs, &e->middle, &e->outputs})
+      for (auto &blk : *grp)
+        for (auto &l : blk) fn(l);
+  };
+  each_layer([&](LayerDesc &l) { if (l.kind == 1) film_rows += 2 * l.cout; });
+  e->film_rows = film_rows;
+  e->film_w = ab.take((size_t)film_rows * ted * 4);
+  e->film_b = ab.take((size_t)film_rows * 4);
+  int row = 0;
+  int rc = DPIR_OK;
+  each_layer([&](LayerDesc &l) {
+    const std::string &p = l.prefix;
+    if (l.kind == 0) {
+      ConvW w;
+      w.cin = l.cin; w.cout = l.cout; w.ksize = 3; w.ldw = l.cout;
+      w.w_off = add(p + "weight", PK_CONV_STEM, {l.cout, l.cin, 3, 3}, (size_t)9 * l.cin * l.cout * 4, l.cout).off;
+      w.b_off = add_vec(p + "bias", l.cout);
+      e->stem = w;
+    } else if (l.kind == 1) {
+      if (l.cin % 128 || l.cout % 128) { set_error("channel counts must be multiples of 128 (%s)", p.c_str()); rc = DPIR_E_ARG; return; }
+      ResW r;
+      r.n1.g_off = add_vec(p + "in_layers.0.weight", l.cin);
+      r.n1.b_off = add_vec(p + "in_layers.0.bias", l.cin);
+      r.c1 = add_conv(p + "in_layers.2.", l.cin, l.cout, 3, false);
+      r.film_row = row;
+      ParamSlot &fw = add(p + "emb_layers.1.weight", PK_FILM_W, {2 * l.cout, ted}, (size_t)2 * l.cout * ted * 4);
+      fw.film_row = row; fw.off = e->film_w + (size_t)row * ted * 4;
+      ParamSlot &fb = add(p + "emb_layers.1.bias", PK_FILM_B, {2 * l.cout}, (size_t)2 * l.cout * 4);
+      fb.film_row = row; fb.off = e->film_b + (size_t)row * 4;
+      row += 2 * l.cout;
+      r.n2.g_off = add_vec(p + "out_layers.0.weight", l.cout);
+      r.n2.b_off = add_vec(p + "out_layers.0.bias", l.cout);
+      r.c2 = add_conv(p + "out_layers.3.", l.cout, l.cout, 3, false);
+      r.has_skip = l.cin != l.cout;
+      if (r.has_skip) r.skip = add_conv(p + "skip_connection.", l.cin, l.cout, 1, false);
+      e->resw[p] = r;
+    } else {
+      if (l.cin % 128 || l.cin != l.heads * 64) { set_error("attention needs C %% 128 == 0 and head dim 64 (%s)", p.c_str()); rc = DPIR_E_ARG; return; }
+      AttnW a;
+      a.n.g_off = add_vec(p + "norm.weight", l.cin);
+      a.n.b_off = add_vec(p + "norm.bias", l.cin);
+      a.qkv = add_conv(p + "qkv.", l.cin, 3 * l.cin, 1, true);
+      a.proj = add_conv(p + "proj_out.", l.cin, l.cin, 1, true);
+      e->attnw[p] = a;
+    }
+  });
+  if (rc) return rc;
+  e->outnorm.g_off = add_vec("out.0.weight", e->ch0);
+  e->outnorm.b_off = add_vec("out.0.bias", e->ch0);
+  e->outconv = add_conv("out.2.", e->ch0, e->cfg.out_channels, 3, false);
+  e->freqs_off = ab.take((size_t)(mc / 2) * 4);
+  e->coef_off = ab.take((size_t)e->cfg.diffusion_steps * 2 * 4);
+  e->arena_bytes = ab.cur;
+  return DPIR_OK;
+}
+
+int init_tables(dpir_engine *e) {
+  // nn.py:112-114 frequencies and gaussian_diffusion.py:133-151 eps->x0 coefficients (float64 tables -> float)
+  int half = e->cfg.model_channels / 2;
+  std::vector<float> fr(half);
+  for (int i = 0; i < half; ++i) fr[i] = expf(-logf(10000.0f) * (float)i / (float)half);
+  DPIR_CUDA_CHECK(cudaMemcpy(e->arena + e->freqs_off, fr.data(), fr.size() * 4, cudaMemcpyHostToDevice));
+  int T = e->cfg.diffusion_steps;
+  std::vector<float> coef((size_t)T * 2);
+  double scale = 1000.0 / T, b0 = scale * 0.0001, b1 = scale * 0.02, ac = 1.0;
+  for (int i = 0; i < T; ++i) {
+    double beta = T > 1 ? b0 + (b1 - b0) * (double)i / (double)(T - 1) : b0;
+    ac *= (1.0 - beta);
+    coef[2 * i] = (float)std::sqrt(1.0 / ac);
+    coef[2 * i + 1] = (float)std::sqrt(1.0 / ac - 1.0);
+  }
+  DPIR_CUDA_CHECK(cudaMemcpy(e->arena + e->coef_off, coef.data(), coef.size() * 4, cudaMemcpyHostToDevice));
+  return DPIR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- plan building
+struct PlanBuilder {
+  dpir_engine *e;
+  Plan *plan;
+  Pool pool;
+  std::vector<Buf> bufs;
+  size_t stats_off = 0;      // inside the workspace: [n_norms][B][64] doubles
+  int n_norms = 0;
+  size_t film_off = 0, hidden_off = 0, emb_off = 0;
+  int B, H, W;
+  int err = DPIR_OK;
+
+  int new_buf(int B_, int H_, int W_, int C_, bool half) {
+    Buf b;
+    b.B = B_; b.H = H_; b.W = W_; b.C = C_; b.half = half;
+    b.bytes = (size_t)B_ * H_ * W_ * C_ * (half ? 2 : 4);
+    b.off = pool.alloc(b.bytes);
+    b.refs = 1;
+    b.id = (int)bufs.size();
+    bufs.push_back(b);
+    return b.id;
+  }
+  void retain(int id) { bufs[id].refs++; }
+  void release(int id) {
+    if (id < 0) return;
+    if (--bufs[id].refs == 0) pool.release(bufs[id].off);
+  }
+  // pointers are stored as workspace offsets (+1 so that 0 stays "null") and rebased after the workspace is allocated
+  template <typename T> T *wp(size_t off) { return reinterpret_cast<T *>(off + 1); }
+  template <typename T> T *bp(int id) { return wp<T>(bufs[id].off); }
+  double *stats_ptr(int norm_idx) { return wp<double>(stats_off + (size_t)norm_idx * B * 64 * sizeof(double)); }
+
+  int gn(int src1, int src2, const NormW &nw, int film_row /*-1: none*/, int silu, int resample, bool want_raw32,
+         bool want_rawact, int *act_id, int *raw32_id, int *rawact_id) {
+    const Buf &s1 = bufs[src1];
+    int C1 = s1.C, C2 = src2 >= 0 ? bufs[src2].C : 0, C = C1 + C2;
+    int Hin = s1.H, Win = s1.W;
+    int Ho = resample == RS_DOWN ? Hin / 2 : (resample == RS_UP ? Hin * 2 : Hin);
+    int Wo = resample == RS_DOWN ? Win / 2 : (resample == RS_UP ? Win * 2 : Win);
+    int ni = n_norms++;
+    Op st;
+    st.kind = OP_GN_STATS;
+    st.p0 = bp<float>(src1); st.C1 = C1;
+    st.p1 = src2 >= 0 ? bp<float>(src2) : nullptr; st.C2 = C2;
+    st.q0 = stats_ptr(ni); st.B = B; st.HW = Hin * Win;
+    plan->ops.push_back(st);
+    *act_id = new_buf(B, Ho, Wo, C, e->half);
+    *raw32_id = want_raw32 ? new_buf(B, Ho, Wo, C, false) : -1;
+    *rawact_id = want_rawact ? new_buf(B, Ho, Wo, C, e->half) : -1;
+    Op ap;
+    ap.kind = OP_GN_APPLY;
+    GnApplyArgs &a = ap.gn;
+    a.src1 = bp<float>(src1); a.C1 = C1;
+    a.src2 = src2 >= 0 ? bp<float>(src2) : nullptr; a.C2 = C2;
+    a.stats = stats_ptr(ni);
+    a.gamma = e->ap<float>(nw.g_off); a.beta = e->ap<float>(nw.b_off);
+    a.film = film_row >= 0 ? wp<float>(film_off + (size_t)film_row * 4) : nullptr;
+    a.film_stride = e->film_rows;
+    a.silu = silu; a.resample = resample; a.B = B; a.H = Hin; a.W = Win; a.out_half = e->half;
+    a.act = bp<void>(*act_id);
+    a.raw32 = want_raw32 ? bp<float>(*raw32_id) : nullptr;
+    a.rawact = want_rawact ? bp<void>(*rawact_id) : nullptr;
+    plan->ops.push_back(ap);
+    return DPIR_OK;
+  }
+
+  // conv on a workspace activation -> new fp32 NHWC buffer (residual optional)
+  int conv(int act, const ConvW &cw, int residual, int *out_id) {
+    const Buf &a = bufs[act];
+    *out_id = new_buf(B, a.H, a.W, cw.cout, false);
+    Op op;
+    op.kind = OP_CONV;
+    op.p0 = bp<void>(act);
+    op.w = e->arena + cw.w_off;
+    op.B = B; op.H = a.H; op.W = a.W; op.Cin = cw.cin; op.Cout = cw.cout; op.ldw = cw.ldw; op.ksize = cw.ksize;
+    op.epi.mode = EPI_NHWC;
+    op.epi.bias = e->ap<float>(cw.b_off);
+    op.epi.residual = residual >= 0 ? bp<float>(residual) : nullptr;
+    op.epi.out = bp<float>(*out_id);
+    plan->ops.push_back(op);
+    return DPIR_OK;
+  }
+
+  int resblock(const LayerDesc &l, int x, int skip, int *out) {
+    const ResW &rw = e->resw[l.prefix];
+    bool concat = skip >= 0;
+    bool need_raw32 = !rw.has_skip && (l.updown != RS_NONE || concat);
+    int a1, xr, xraw;
+    gn(x, skip, rw.n1, -1, 1, l.updown, need_raw32, rw.has_skip, &a1, &xr, &xraw);
+    int residual = -1;
+    if (!rw.has_skip) {
+      if (need_raw32) { residual = xr; release(x); }
+      else residual = x;   // keep x alive until conv2
+    } else {
+      release(x);
+    }
+    if (concat) release(skip);
+    int h1;
+    conv(a1, rw.c1, -1, &h1);
+    release(a1);
+    int a2, d0, d1;
+    gn(h1, -1, rw.n2, rw.film_row, 1, RS_NONE, false, false, &a2, &d0, &d1);
+    release(h1);
+    if (rw.has_skip) {
+      conv(xraw, rw.skip, -1, &residual);
+      release(xraw);
+    }
+    conv(a2, rw.c2, residual, out);
+    release(a2);
+    release(residual);
+    return DPIR_OK;
+  }
+
+  int attnblock(const LayerDesc &l, int x, int *out) {
+    const AttnW &aw = e->attnw[l.prefix];
+    int xn, d0, d1;
+    gn(x, -1, aw.n, -1, 0, RS_NONE, false, false, &xn, &d0, &d1);
+    int qkv;
+    conv(xn, aw.qkv, -1, &qkv);
+    release(xn);
+    const Buf &xb = bufs[x];
+    int a = new_buf(B, xb.H, xb.W, l.cin, e->half);
+    Op op;
+    op.kind = OP_ATTN;
+    op.p0 = bp<float>(qkv); op.q0 = bp<void>(a);
+    op.B = B; op.HW = xb.H * xb.W; op.Cin = l.cin; op.heads = l.heads; op.out_half = e->half;
+    plan->ops.push_back(op);
+    release(qkv);
+    conv(a, aw.proj, x, out);
+    release(a);
+    release(x);
+    return DPIR_OK;
+  }
+
+  int run_block(const std::vector<LayerDesc> &blk, int h, int skip, int *out) {
+    for (size_t j = 0; j < blk.size(); ++j) {
+      const LayerDesc &l = blk[j];
+      int o;
+      if (l.kind == 1) resblock(l, h, j == 0 ? skip : -1, &o);
+      else attnblock(l, h, &o);
+      h = o;
+    }
+    *out = h;
+    return DPIR_OK;
+  }
+
+  int build() {
+    int ted = e->ted;
+    // persistent small buffers first (never released)
+    hidden_off = pool.alloc((size_t)B * ted * 4);
+    emb_off = pool.alloc((size_t)B * ted * 4);
+    film_off = pool.alloc((size_t)B * e->film_rows * 4);
+    int total_norms = 1;
+    for (auto *grp : {&e->inputs, &e->middle, &e->outputs})
+      for (auto &blk : *grp)
+        for (auto &l : blk) total_norms += l.kind == 1 ? 2 : (l.kind == 2 ? 1 : 0);
+    size_t stats_bytes = (size_t)total_norms * B * 64 * sizeof(double);
+    stats_off = pool.alloc(stats_bytes);
+
+    Op ms; ms.kind = OP_MEMSET; ms.q0 = wp<void>(stats_off); ms.bytes = stats_bytes;
+    plan->ops.push_back(ms);
+    Op te; te.kind = OP_TIME_EMBED; te.bind_t = true; te.q0 = wp<void>(hidden_off); te.p1 = wp<void>(emb_off); te.B = B;
+    plan->ops.push_back(te);
+    Op fl; fl.kind = OP_FILM; fl.p0 = wp<void>(emb_off); fl.q0 = wp<void>(film_off); fl.B = B;
+    plan->ops.push_back(fl);
+
+    std::vector<int> hs;
+    int h = new_buf(B, H, W, e->ch0, false);
+    Op ci; ci.kind = OP_CONV_IN; ci.bind_x = true; ci.q0 = bp<void>(h); ci.B = B; ci.H = H; ci.W = W;
+    plan->ops.push_back(ci);
+    retain(h); hs.push_back(h);
+    for (size_t i = 1; i < e->inputs.size(); ++i) {
+      int o;
+      run_block(e->inputs[i], h, -1, &o);
+      h = o;
+      retain(h); hs.push_back(h);
+    }
+    { int o; run_block(e->middle[0], h, -1, &o); h = o; }
+    for (size_t i = 0; i < e->outputs.size(); ++i) {
+      int skip = hs.back(); hs.pop_back();
+      int o;
+      run_block(e->outputs[i], h, skip, &o);
+      h = o;
+    }
+    int a, d0, d1;
+    gn(h, -1, e->outnorm, -1, 1, RS_NONE, false, false, &a, &d0, &d1);
+    release(h);
+    Op fc;
+    fc.kind = OP_CONV;
+    fc.p0 = bp<void>(a); fc.w = e->arena + e->outconv.w_off;
+    fc.B = B; fc.H = H; fc.W = W; fc.Cin = e->outconv.cin; fc.Cout = e->outconv.cout; fc.ldw = e->outconv.ldw; fc.ksize = 3;
+    fc.epi.mode = EPI_NCHW; fc.epi.bias = e->ap<float>(e->outconv.b_off);
+    fc.epi.coef = e->ap<float>(e->coef_off);
+    fc.bind_out = true;
+    plan->final_conv = (int)plan->ops.size();
+    plan->ops.push_back(fc);
+    release(a);
+    if (n_norms != total_norms) { set_error("internal: norm count mismatch %d vs %d", n_norms, total_norms); return DPIR_E_STATE; }
+    plan->ws_bytes = pool.peak;
+    return err;
+  }
+};
+
+template <typename T> void rebase(T *&p, uint8_t *base) {
+  if (p) p = reinterpret_cast<T *>(base + (reinterpret_cast<uintptr_t>(p) - 1));
+}
+void rebase_c(const void *&p, uint8_t *base) {
+  if (p) p = base + (reinterpret_cast<uintptr_t>(p) - 1);
+}
+
+int get_plan(dpir_engine *e, int B, int H, int W, Plan **out) {
+  auto key = std::make_tuple(B, H, W);
+  auto it = e->plans.find(key);
+  if (it != e->plans.end()) { *out = it->second.get(); return DPIR_OK; }
+  int nlev = e->cfg.n_channel_mult;
+  DPIR_REQUIRE(B >= 1 && H >= 1 && W >= 1, "bad batch shape");
+  DPIR_REQUIRE(H % (1 << (nlev - 1)) == 0 && W % (1 << (nlev - 1)) == 0, "H and W must be divisible by %d", 1 << (nlev - 1));
+  std::unique_ptr<Plan> plan(new Plan());
+  plan->B = B; plan->H = H; plan->W = W;
+  PlanBuilder pb;
+  pb.e = e; pb.plan = plan.get(); pb.B = B; pb.H = H; pb.W = W;
+  int rc = pb.build();
+  if (rc) return rc;
+  if (plan->ws_bytes > e->ws_bytes) {
+    // grow the workspace: cached plans hold absolute addresses (and TMA descriptors), so drop them
+    e->plans.clear();
+    if (e->ws) { cudaDeviceSynchronize(); cudaFree(e->ws); e->ws = nullptr; e->ws_bytes = 0; }
+    cudaError_t ce = cudaMalloc(&e->ws, plan->ws_bytes);
+    if (ce != cudaSuccess) { set_error("workspace cudaMalloc(%zu) failed: %s", plan->ws_bytes, cudaGetErrorString(ce)); return DPIR_E_NOMEM; }
+    e->ws_bytes = plan->ws_bytes;
+  }
+  uint8_t *base = e->ws;
+  for (Op &op : plan->ops) {
+    rebase_c(op.p0, base); rebase_c(op.p1, base); rebase_c(op.p2, base); rebase(op.q0, base);
+    if (op.kind == OP_GN_APPLY) {
+      rebase(op.gn.src1, base); rebase(op.gn.src2, base); rebase(op.gn.stats, base); rebase(op.gn.film, base);
+      rebase(op.gn.act, base); rebase(op.gn.raw32, base); rebase(op.gn.rawact, base);
+    }
+    if (op.kind == OP_CONV) { rebase(op.epi.residual, base); rebase(op.epi.out, base); }
+  }
+  if (e->half) {
+    for (Op &op : plan->ops) {
+      if (op.kind != OP_CONV) continue;
+      ConvTcPlan *tp = nullptr;
+      rc = conv_tc_plan_create(op.p0, op.w, op.B, op.H, op.W, op.Cin, op.ldw, op.ksize, &tp);
+      if (rc) return rc;
+      op.tc = tp;
+      plan->tc_plans.push_back(tp);
+    }
+  }
+  *out = plan.get();
+  e->plans[key] = std::move(plan);
+  return DPIR_OK;
+}
+
+int run_plan(dpir_engine *e, Plan *plan, const float *x, const int64_t *t, float *out, int mode, cudaStream_t st) {
+  for (Op &op : plan->ops) {
+    int rc = DPIR_OK;
+    switch (op.kind) {
+      case OP_MEMSET:
+        DPIR_CUDA_CHECK(cudaMemsetAsync(op.q0, 0, op.bytes, st));
+        break;
+      case OP_TIME_EMBED:
+        rc = launch_time_embed(t, e->ap<float>(e->freqs_off), e->ap<float>(e->te_w0), e->ap<float>(e->te_b0),
+                               e->ap<float>(e->te_w2), e->ap<float>(e->te_b2), (float *)op.q0, (float *)const_cast<void *>(op.p1),
+                               op.B, e->cfg.model_channels, e->ted, st);
+        break;
+      case OP_FILM:
+        rc = launch_linear_rows((const float *)op.p0, e->ap<float>(e->film_w), e->ap<float>(e->film_b), (float *)op.q0, op.B,
+                                e->ted, e->film_rows, 0, 0, st);
+        break;
+      case OP_CONV_IN:
+        rc = launch_conv_in(x, e->ap<float>(e->stem.w_off), e->ap<float>(e->stem.b_off), (float *)op.q0, op.B, op.H, op.W,
+                            e->stem.cin, e->stem.cout, st);
+        break;
+      case OP_GN_STATS:
+        rc = launch_gn_stats((const float *)op.p0, op.C1, (const float *)op.p1, op.C2, (double *)op.q0, op.B, op.HW, st);
+        break;
+      case OP_GN_APPLY:
+        rc = launch_gn_apply(op.gn, st);
+        break;
+      case OP_CONV: {
+        ConvEpi epi = op.epi;
+        if (op.bind_out) {
+          epi.mode = mode;
+          epi.out = out;
+          epi.x_nchw = x;
+          epi.t = t;
+        }
+        if (e->half) rc = launch_conv_tc(op.tc, epi, op.Cout, st);
+        else rc = launch_conv_simt((const float *)op.p0, (const float *)op.w, op.ldw, epi, op.B, op.H, op.W, op.Cin, op.Cout,
+                                   op.ksize, st);
+        break;
+      }
+      case OP_ATTN:
+        rc = launch_attention((const float *)op.p0, op.q0, op.out_half, op.B, op.HW, op.Cin, op.heads,
+                              e->cfg.use_new_attention_order, st);
+        break;
+    }
+    if (rc) return rc;
+  }
+  return DPIR_OK;
+}
+
+int ensure_graph_staging(dpir_engine *e, int B, int H, int W) {
+  size_t need = (size_t)B * 3 * H * W;
+  if (need <= e->g_cap) return DPIR_OK;
+  if (e->g_x) { cudaFree(e->g_x); cudaFree(e->g_out); cudaFree(e->g_t); }
+  // a new staging area invalidates captured graphs
+  for (auto &kv : e->plans) {
+    if (kv.second->graph_nchw) { cudaGraphExecDestroy(kv.second->graph_nchw); kv.second->graph_nchw = nullptr; }
+    if (kv.second->graph_x0) { cudaGraphExecDestroy(kv.second->graph_x0); kv.second->graph_x0 = nullptr; }
+  }
+  DPIR_CUDA_CHECK(cudaMalloc(&e->g_x, need * 4));
+  DPIR_CUDA_CHECK(cudaMalloc(&e->g_out, (size_t)B * e->cfg.out_channels * H * W * 4));
+  DPIR_CUDA_CHECK(cudaMalloc(&e->g_t, (size_t)B * 8 + 256));
+  e->g_cap = need;
+  return DPIR_OK;
+}
+
+int forward_impl(dpir_engine *e, const float *x, const int64_t *t, float *out, int B, int H, int W, int mode, void *stream) {
+  DPIR_REQUIRE(e && x && t && out, "unet forward: null pointer");
+  if (dpir_missing_weights(e) != 0) { set_error("unet forward: %d checkpoint tensors not loaded", dpir_missing_weights(e)); return DPIR_E_STATE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  Plan *plan = nullptr;
+  int rc = get_plan(e, B, H, W, &plan);
+  if (rc) return rc;
+  if (!e->graph_mode) return run_plan(e, plan, x, t, out, mode, st);
+
+  // graph mode: fixed staging buffers, one captured graph per (shape, output mode)
+  rc = ensure_graph_staging(e, B, H, W);
+  if (rc) return rc;
+  size_t xin = (size_t)B * 3 * H * W * 4;
+  size_t xout = (size_t)B * (mode == EPI_X0 ? 3 : e->cfg.out_channels) * H * W * 4;
+  cudaGraphExec_t &gexec = mode == EPI_X0 ? plan->graph_x0 : plan->graph_nchw;
+  DPIR_CUDA_CHECK(cudaMemcpyAsync(e->g_x, x, xin, cudaMemcpyDeviceToDevice, st));
+  DPIR_CUDA_CHECK(cudaMemcpyAsync(e->g_t, t, (size_t)B * 8, cudaMemcpyDeviceToDevice, st));
+  if (!gexec) {
+    // warm-up run outside capture (sets function attributes, validates the tape), then capture
+    rc = run_plan(e, plan, e->g_x, e->g_t, e->g_out, mode, st);
+    if (rc) return rc;
+    DPIR_CUDA_CHECK(cudaStreamSynchronize(st));
+    cudaGraph_t graph;
+    DPIR_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    int64_t before = g_launch_count;
+    rc = run_plan(e, plan, e->g_x, e->g_t, e->g_out, mode, st);
+    g_launch_count = before;
+    cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    if (rc) return rc;
+    if (ce != cudaSuccess) { set_error("graph capture failed: %s", cudaGetErrorString(ce)); return DPIR_E_CUDA; }
+    DPIR_CUDA_CHECK(cudaGraphInstantiate(&gexec, graph, 0));
+    cudaGraphDestroy(graph);
+  }
+  DPIR_CUDA_CHECK(cudaGraphLaunch(gexec, st));
+  // count the kernels the graph replays (same tape)
+  for (Op &op : plan->ops) g_launch_count += (op.kind == OP_MEMSET ? 0 : (op.kind == OP_TIME_EMBED ? 2 : 1));
+  DPIR_CUDA_CHECK(cudaMemcpyAsync(out, e->g_out, xout, cudaMemcpyDeviceToDevice, st));
+  return DPIR_OK;
+}
+
+}  // namespace
+
+// =============================================================================================== C-ABI
+extern "C" {
+
+int dpir_create(const dpir_unet_config *cfg, dpir_engine **out) {
+  DPIR_REQUIRE(cfg && out, "dpir_create: null pointer");
+  DPIR_REQUIRE(cfg->precision == DPIR_PRECISION_FP32 || cfg->precision == DPIR_PRECISION_FP16, "dpir_create: bad precision");
+  DPIR_REQUIRE(cfg->diffusion_steps >= 1, "dpir_create: diffusion_steps must be >= 1");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_error("dpir_create: no CUDA device available (this library has no CPU fallback)");
+    return DPIR_E_CUDA;
+  }
+  std::unique_ptr<dpir_engine> e(new dpir_engine());
+  e->cfg = *cfg;
+  e->half = cfg->precision == DPIR_PRECISION_FP16;
+  int rc = build_structure(e.get());
+  if (rc) return rc;
+  rc = build_params(e.get());
+  if (rc) return rc;
+  cudaError_t ce = cudaMalloc(&e->arena, e->arena_bytes);
+  if (ce != cudaSuccess) { set_error("weight arena cudaMalloc(%zu) failed: %s", e->arena_bytes, cudaGetErrorString(ce)); return DPIR_E_NOMEM; }
+  DPIR_CUDA_CHECK(cudaMemset(e->arena, 0, e->arena_bytes));
+  rc = init_tables(e.get());
+  if (rc) { cudaFree(e->arena); return rc; }
+  *out = e.release();
+  return DPIR_OK;
+}
+
+int dpir_destroy(dpir_engine *e) {
+  if (!e) return DPIR_OK;
+  cudaDeviceSynchronize();
+  e->plans.clear();
+  if (e->arena) cudaFree(e->arena);
+  if (e->ws) cudaFree(e->ws);
+  if (e->g_x) { cudaFree(e->g_x); cudaFree(e->g_out); cudaFree(e->g_t); }
+  delete e;
+  return DPIR_OK;
+}
+
+int dpir_load_weight(dpir_engine *e, const char *name, const float *data, const int64_t *shape, int32_t ndim) {
+  DPIR_REQUIRE(e && name && data && shape, "dpir_load_weight: null pointer");
+  auto it = e->slots.find(name);
+  if (it == e->slots.end()) { set_error("dpir_load_weight: unexpected tensor '%s'", name); return DPIR_E_ARG; }
+  ParamSlot &s = it->second;
+  bool ok = (int)s.shape.size() == ndim;
+  for (int i = 0; ok && i < ndim; ++i) ok = s.shape[i] == shape[i];
+  // conv1d checkpoints may come as (O,I,1) or (O,I,1,1); 1x1 convs as (O,I,1,1)
+  if (!ok) {
+    int64_t n_exp = 1, n_got = 1;
+    for (auto v : s.shape) n_exp *= v;
+    for (int i = 0; i < ndim; ++i) n_got *= shape[i];
+    ok = n_exp == n_got && ndim >= 2 && s.shape.size() >= 2 && shape[0] == s.shape[0] && shape[1] == s.shape[1];
+  }
+  if (!ok) { set_error("dpir_load_weight: shape mismatch for '%s'", name); return DPIR_E_ARG; }
+  if (s.kind == PK_COPY || s.kind == PK_FILM_W || s.kind == PK_FILM_B) {
+    int64_t n = 1;
+    for (auto v : s.shape) n *= v;
+    DPIR_CUDA_CHECK(cudaMemcpy(e->arena + s.off, data, (size_t)n * 4, cudaMemcpyHostToDevice));
+  } else if (s.kind == PK_CONV_STEM) {
+    int O = (int)s.shape[0], I = (int)s.shape[1];
+    std::vector<float> pk((size_t)9 * I * O);
+    for (int o = 0; o < O; ++o)
+      for (int i = 0; i < I; ++i)
+        for (int tp = 0; tp < 9; ++tp) pk[((size_t)tp * I + i) * O + o] = data[((size_t)o * I + i) * 9 + tp];
+    DPIR_CUDA_CHECK(cudaMemcpy(e->arena + s.off, pk.data(), pk.size() * 4, cudaMemcpyHostToDevice));
+  } else {  // PK_CONV
+    int O = (int)s.shape[0], I = (int)s.shape[1];
+    int taps = s.shape.size() == 4 ? (int)(s.shape[2] * s.shape[3]) : 1;
+    int ldw = s.ldw;
+    if (e->half) {   // [tap][ldw][I] fp16
+      std::vector<__half> pk((size_t)taps * ldw * I, __float2half(0.f));
+      for (int o = 0; o < O; ++o)
+        for (int i = 0; i < I; ++i)
+          for (int tp = 0; tp < taps; ++tp)
+            pk[((size_t)tp * ldw + o) * I + i] = __float2half_rn(data[((size_t)o * I + i) * taps + tp]);
+      DPIR_CUDA_CHECK(cudaMemcpy(e->arena + s.off, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
+    } else {         // [tap][I][ldw] fp32
+      std::vector<float> pk((size_t)taps * I * ldw, 0.f);
+      for (int o = 0; o < O; ++o)
+        for (int i = 0; i < I; ++i)
+          for (int tp = 0; tp < taps; ++tp) pk[((size_t)tp * I + i) * ldw + o] = data[((size_t)o * I + i) * taps + tp];
+      DPIR_CUDA_CHECK(cudaMemcpy(e->arena + s.off, pk.data(), pk.size() * 4, cudaMemcpyHostToDevice));
+    }
+  }
+  s.loaded = true;
+  return DPIR_OK;
+}
+
+int dpir_missing_weights(dpir_engine *e) {
+  if (!e) return -1;
+  int n = 0;
+  for (auto &kv : e->slots) n += kv.second.loaded ? 0 : 1;
+  return n;
+}
+
+int dpir_weight_arena(dpir_engine *e, void **dev_ptr, size_t *bytes) {
+  DPIR_REQUIRE(e && dev_ptr && bytes, "dpir_weight_arena: null pointer");
+  *dev_ptr = e->arena;
+  *bytes = e->arena_bytes;
+  return DPIR_OK;
+}
+
+int dpir_mark_weights_loaded(dpir_engine *e) {
+  DPIR_REQUIRE(e, "dpir_mark_weights_loaded: null engine");
+  for (auto &kv : e->slots) kv.second.loaded = true;
+  return DPIR_OK;
+}
+
+int dpir_set_tables(dpir_engine *e, const float *freqs, int32_t n_freqs, const float *coef, int32_t T) {
+  DPIR_REQUIRE(e, "dpir_set_tables: null engine");
+  if (freqs) {
+    DPIR_REQUIRE(n_freqs == e->cfg.model_channels / 2, "dpir_set_tables: need model_channels/2 frequencies");
+    DPIR_CUDA_CHECK(cudaMemcpy(e->arena + e->freqs_off, freqs, (size_t)n_freqs * 4, cudaMemcpyHostToDevice));
+  }
+  if (coef) {
+    DPIR_REQUIRE(T == e->cfg.diffusion_steps, "dpir_set_tables: coefficient table must have diffusion_steps rows");
+    DPIR_CUDA_CHECK(cudaMemcpy(e->arena + e->coef_off, coef, (size_t)T * 2 * 4, cudaMemcpyHostToDevice));
+  }
+  return DPIR_OK;
+}
+
+int dpir_unet_forward(dpir_engine *e, const float *x, const int64_t *t, float *out, int32_t B, int32_t H, int32_t W, void *stream) {
+  return forward_impl(e, x, t, out, B, H, W, EPI_NCHW, stream);
+}
+
+int dpir_unet_x0(dpir_engine *e, const float *x, const int64_t *t, float *x0, int32_t B, int32_t H, int32_t W, void *stream) {
+  DPIR_REQUIRE(e && e->cfg.in_channels == 3, "dpir_unet_x0: needs a 3-channel model");
+  return forward_impl(e, x, t, x0, B, H, W, EPI_X0, stream);
+}
+
+int64_t dpir_workspace_bytes(dpir_engine *e) { return e ? (int64_t)e->ws_bytes : 0; }
+
+int dpir_set_graph_mode(dpir_engine *e, int32_t enable) {
+  DPIR_REQUIRE(e, "dpir_set_graph_mode: null engine");
+  e->graph_mode = enable ? 1 : 0;
+  return DPIR_OK;
+}
+
+// ---- per-kernel entry points for tests / benchmarks
+int dpir_conv_tc(const void *act, const void *w, const float *bias, const float *residual, float *out, int32_t B, int32_t H,
+                 int32_t W, int32_t Cin, int32_t Cout, int32_t CoutPad, int32_t ksize, void *stream) {
+  DPIR_REQUIRE(act && w && bias && out, "dpir_conv_tc: null pointer");
+  ConvTcPlan *p = nullptr;
+  int rc = conv_tc_plan_create(act, w, B, H, W, Cin, CoutPad, ksize, &p);
+  if (rc) return rc;
+  ConvEpi epi{};
+  epi.mode = EPI_NHWC; epi.bias = bias; epi.residual = residual; epi.out = out;
+  rc = launch_conv_tc(p, epi, Cout, (cudaStream_t)stream);
+  conv_tc_plan_destroy(p);   // the tensor maps were copied into the launch parameters
+  return rc;
+}
+
+int dpir_conv_simt(const float *act, const float *w, const float *bias, const float *residual, float *out, int32_t B, int32_t H,
+                   int32_t W, int32_t Cin, int32_t Cout, int32_t ksize, void *stream) {
+  DPIR_REQUIRE(act && w && bias && out, "dpir_conv_simt: null pointer");
+  ConvEpi epi{};
+  epi.mode = EPI_NHWC; epi.bias = bias; epi.residual = residual; epi.out = out;
+  return launch_conv_simt(act, w, (Cout + 3) / 4 * 4, epi, B, H, W, Cin, Cout, ksize, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,533 @@
+// unet_kernels.cu - GroupNorm/SiLU/FiLM/resample passes, input stem, fp32 CUDA-core implicit-GEMM convolution,
+// fused QKV attention and the timestep-embedding MLPs of the guided-diffusion UNet.
+//
+// Reference behaviour (paths relative to the reference root):
+//   guided_diffusion/nn.py:17-19, 93-100  GroupNorm32(32, C), eps 1e-5
+//   guided_diffusion/unet.py:236-256      ResBlock._forward (GN+SiLU -> up/down -> conv; FiLM: GN(h)*(1+scale)+shift)
+//   guided_diffusion/unet.py:81-140       Upsample (nearest x2) / Downsample (avg-pool 2)
+//   guided_diffusion/unet.py:337-354      QKVAttentionLegacy ([head][q,k,v][ch] channel order), :371-389 new order
+//   guided_diffusion/nn.py:103-121        timestep_embedding;  unet.py:471-475 time_embed; :199-205 emb_layers
+// Layout: activations NHWC so that channels are the contiguous (coalesced, float4) dimension and so that the same
+// buffers feed the tcgen05 implicit-GEMM convolution (conv_tc.cu) as K-major operands.
+#include "unet_kernels.cuh"
+
+namespace dpir {
+
+// =========================================================================================== input stem
+// input_blocks.0.0: Conv2d(3, C, 3, padding=1) reading the caller's NCHW image and writing NHWC fp32.
+// w packed [tap*Cin + ci][Cout].  One thread = one pixel x 4 output channels.
+__global__ void k_conv_in(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ bias,
+                          float *__restrict__ out, int B, int H, int W, int Cin, int Cout) {
+  extern __shared__ float sw[];  // [9*Cin][Cout]
+  int K = 9 * Cin;
+  for (int i = threadIdx.x; i < K * Cout; i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
+  int C4 = Cout / 4;
+  int ppb = blockDim.x / C4;
+  int lane_p = threadIdx.x / C4, c4 = threadIdx.x % C4;
+  if (lane_p >= ppb) return;
+  int64_t npix = (int64_t)B * H * W;
+  float4 bv = reinterpret_cast<const float4 *>(bias)[c4];
+  for (int64_t p = (int64_t)blockIdx.x * ppb + lane_p; p < npix; p += (int64_t)gridDim.x * ppb) {
+    int xw = (int)(p % W);
+    int yh = (int)((p / W) % H);
+    int n = (int)(p / ((int64_t)W * H));
+    float4 acc = bv;
+    for (int dy = 0; dy < 3; ++dy) {
+      int yy = yh + dy - 1;
+      if (yy < 0 || yy >= H) continue;
+      for (int dx = 0; dx < 3; ++dx) {
+        int xx = xw + dx - 1;
+        if (xx < 0 || xx >= W) continue;
+        for (int ci = 0; ci < Cin; ++ci) {
+          float v = __ldg(&x[(((int64_t)n * Cin + ci) * H + yy) * W + xx]);
+          float4 wv = reinterpret_cast<const float4 *>(sw + ((dy * 3 + dx) * Cin + ci) * Cout)[c4];
+          acc.x += v * wv.x; acc.y += v * wv.y; acc.z += v * wv.z; acc.w += v * wv.w;
+        }
+      }
+    }
+    reinterpret_cast<float4 *>(out + p * Cout)[c4] = acc;
+  }
+}
+
+int launch_conv_in(const float *x, const float *w, const float *bias, float *out, int B, int H, int W, int Cin, int Cout,
+                   cudaStream_t st) {
+  DPIR_REQUIRE(Cout % 4 == 0 && Cout / 4 <= 256, "conv_in: Cout must be a multiple of 4 and <= 1024");
+  int C4 = Cout / 4;
+  int threads = C4 * (256 / C4 > 0 ? 256 / C4 : 1);
+  size_t smem = (size_t)9 * Cin * Cout * sizeof(float);
+  DPIR_REQUIRE(smem <= 200 * 1024, "conv_in: weights do not fit in shared memory");
+  static size_t attr_smem = 48 * 1024;
+  if (smem > attr_smem) {
+    DPIR_CUDA_CHECK(cudaFuncSetAttribute(k_conv_in, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem = smem;
+  }
+  int64_t npix = (int64_t)B * H * W;
+  int ppb = threads / C4;
+  int64_t want = (npix + ppb * 8 - 1) / (ppb * 8);
+  int grid = (int)(want < 1 ? 1 : (want > 148 * 8 ? 148 * 8 : want));
+  k_conv_in<<<grid, threads, smem, st>>>(x, w, bias, out, B, H, W, Cin, Cout);
+  DPIR_LAUNCH_CHECK();
+  return DPIR_OK;
+}
+
+// =========================================================================================== GroupNorm statistics
+// sums over (C/32 channels x HW) per (sample, group), accumulated in fp64: stats[b][g] = (sum, sumsq).
+// Thread = one float4 channel lane (a float4 never straddles a group because C % 128 == 0), loops over pixels.
+constexpr int GN_PIX_PER_BLOCK = 256;
+
+__global__ void k_gn_stats(const float *__restrict__ s1, int C1, const float *__restrict__ s2, int C2,
+                           double *__restrict__ stats, int HW) {
+  __shared__ double sh[64];
+  int C = C1 + C2, C4 = C / 4;
+  int ppb = blockDim.x / C4;
+  int lane_p = threadIdx.x / C4, c4 = threadIdx.x % C4;
+  int b = blockIdx.y;
+  if (threadIdx.x < 64) sh[threadIdx.x] = 0.0;
+  __syncthreads();
+  int p0 = blockIdx.x * GN_PIX_PER_BLOCK;
+  int p1 = min(p0 + GN_PIX_PER_BLOCK, HW);
+  const float *src; int Cs, cc;
+  if (c4 * 4 < C1) { src = s1 + (int64_t)b * HW * C1; Cs = C1; cc = c4 * 4; }
+  else             { src = s2 + (int64_t)b * HW * C2; Cs = C2; cc = c4 * 4 - C1; }
+  float s = 0.f, ss = 0.f;
+  for (int p = p0 + lane_p; p < p1; p += ppb) {
+    float4 v = *reinterpret_cast<const float4 *>(src + (int64_t)p * Cs + cc);
+    s += (v.x + v.y) + (v.z + v.w);
+    ss += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+  }
+  int g = c4 / (C4 / 32);
+  atomicAdd(&sh[2 * g], (double)s);
+  atomicAdd(&sh[2 * g + 1], (double)ss);
+  __syncthreads();
+  if (threadIdx.x < 64) atomicAdd(&stats[(int64_t)b * 64 + threadIdx.x], sh[threadIdx.x]);
+}
+
+static inline int gn_threads(int C) {
+  int C4 = C / 4;
+  int ppb = 256 / C4;
+  if (ppb < 1) ppb = 1;
+  return C4 * ppb;
+}
+
+int launch_gn_stats(const float *s1, int C1, const float *s2, int C2, double *stats, int B, int HW, cudaStream_t st) {
+  int C = C1 + C2;
+  DPIR_REQUIRE(C % 128 == 0 && C1 % 4 == 0 && C <= 4096, "gn_stats: channels must be a multiple of 128 (got %d)", C);
+  dim3 grid(cdiv(HW, GN_PIX_PER_BLOCK), B);
+  k_gn_stats<<<grid, gn_threads(C), 0, st>>>(s1, C1, s2, C2, stats, HW);
+  DPIR_LAUNCH_CHECK();
+  return DPIR_OK;
+}
+
+// =========================================================================================== GroupNorm apply
+template <typename T> struct Store4;
+template <> struct Store4<float> {
+  static __device__ __forceinline__ void st(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
+};
+template <> struct Store4<__half> {
+  static __device__ __forceinline__ void st(__half *p, float4 v) {
+    __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t *>(&a);
+    u.y = *reinterpret_cast<uint32_t *>(&b);
+    *reinterpret_cast<uint2 *>(p) = u;
+  }
+};
+
+struct GnDev {
+  const float *s1; int C1; const float *s2; int C2;
+  const double *stats; const float *gamma, *beta; const float *film; int film_stride;
+  int silu, H, W;
+  float *raw32;
+};
+
+__device__ __forceinline__ float4 gn_act(float4 v, float mean, float rstd, float4 g, float4 be, bool has_film, float4 sc,
+                                         float4 sh, int silu) {
+  float4 o;
+  o.x = (v.x - mean) * rstd * g.x + be.x;
+  o.y = (v.y - mean) * rstd * g.y + be.y;
+  o.z = (v.z - mean) * rstd * g.z + be.z;
+  o.w = (v.w - mean) * rstd * g.w + be.w;
+  if (has_film) {
+    o.x = o.x * (1.f + sc.x) + sh.x; o.y = o.y * (1.f + sc.y) + sh.y;
+    o.z = o.z * (1.f + sc.z) + sh.z; o.w = o.w * (1.f + sc.w) + sh.w;
+  }
+  if (silu) {
+    o.x = o.x / (1.f + expf(-o.x)); o.y = o.y / (1.f + expf(-o.y));
+    o.z = o.z / (1.f + expf(-o.z)); o.w = o.w / (1.f + expf(-o.w));
+  }
+  return o;
+}
+
+constexpr int GN_APPLY_PIX = 64;  // work pixels per block
+
+// MODE none: one work pixel = one pixel.  MODE down: work pixel = output pixel (reads 2x2 inputs, averages the
+// ACTIVATED values as unet.py:238-241 does: in_rest(x) then h_upd).  MODE up: work pixel = input pixel, written 2x2.
+template <typename T, int MODE>
+__global__ void k_gn_apply(GnDev a, T *__restrict__ act, T *__restrict__ rawact) {
+  __shared__ float s_mean[32], s_rstd[32];
+  int C = a.C1 + a.C2, C4 = C / 4;
+  int b = blockIdx.y;
+  int H = a.H, W = a.W, HW = H * W;
+  if (threadIdx.x < 32) {
+    double n = (double)HW * (double)(C / 32);
+    double su = a.stats[(int64_t)b * 64 + 2 * threadIdx.x], sq = a.stats[(int64_t)b * 64 + 2 * threadIdx.x + 1];
+    double mean = su / n;
+    double var = sq / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_mean[threadIdx.x] = (float)mean;
+    s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + 1e-5));
+  }
+  __syncthreads();
+  int ppb = blockDim.x / C4;
+  int lane_p = threadIdx.x / C4, c4 = threadIdx.x % C4;
+  int g = c4 / (C4 / 32);
+  float mean = s_mean[g], rstd = s_rstd[g];
+  float4 ga = reinterpret_cast<const float4 *>(a.gamma)[c4];
+  float4 be = reinterpret_cast<const float4 *>(a.beta)[c4];
+  bool has_film = a.film != nullptr;
+  float4 sc = make_float4(0, 0, 0, 0), sh = sc;
+  if (has_film) {
+    const float *f = a.film + (int64_t)b * a.film_stride;
+    sc = reinterpret_cast<const float4 *>(f)[c4];
+    sh = reinterpret_cast<const float4 *>(f + C)[c4];
+  }
+  const float *src; int Cs, cc;
+  if (c4 * 4 < a.C1) { src = a.s1 + (int64_t)b * HW * a.C1; Cs = a.C1; cc = c4 * 4; }
+  else               { src = a.s2 + (int64_t)b * HW * a.C2; Cs = a.C2; cc = c4 * 4 - a.C1; }
+  int Hw = (MODE == RS_DOWN) ? H / 2 : H, Ww = (MODE == RS_DOWN) ? W / 2 : W;   // work grid
+  int Ho = (MODE == RS_UP) ? H * 2 : Hw, Wo = (MODE == RS_UP) ? W * 2 : Ww;     // output grid
+  int nwork = Hw * Ww;
+  int p0 = blockIdx.x * GN_APPLY_PIX;
+  int p1 = min(p0 + GN_APPLY_PIX, nwork);
+  int64_t obase = (int64_t)b * Ho * Wo;
+  for (int p = p0 + lane_p; p < p1; p += ppb) {
+    if (MODE == RS_NONE) {
+      float4 v = *reinterpret_cast<const float4 *>(src + (int64_t)p * Cs + cc);
+      float4 o = gn_act(v, mean, rstd, ga, be, has_film, sc, sh, a.silu);
+      Store4<T>::st(act + (obase + p) * C + c4 * 4, o);
+      if (a.raw32) *reinterpret_cast<float4 *>(a.raw32 + (obase + p) * C + c4 * 4) = v;
+      if (rawact) Store4<T>::st(rawact + (obase + p) * C + c4 * 4, v);
+    } else if (MODE == RS_DOWN) {
+      int yo = p / Ww, xo = p % Ww;
+      float4 accA = make_float4(0, 0, 0, 0), accR = accA;
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {
+        int yi = 2 * yo + (d >> 1), xi = 2 * xo + (d & 1);
+        float4 v = *reinterpret_cast<const float4 *>(src + ((int64_t)yi * W + xi) * Cs + cc);
+        float4 o = gn_act(v, mean, rstd, ga, be, has_film, sc, sh, a.silu);
+        accA.x += o.x; accA.y += o.y; accA.z += o.z; accA.w += o.w;
+        accR.x += v.x; accR.y += v.y; accR.z += v.z; accR.w += v.w;
+      }
+      accA.x *= 0.25f; accA.y *= 0.25f; accA.z *= 0.25f; accA.w *= 0.25f;
+      accR.x *= 0.25f; accR.y *= 0.25f; accR.z *= 0.25f; accR.w *= 0.25f;
+      Store4<T>::st(act + (obase + p) * C + c4 * 4, accA);
+      if (a.raw32) *reinterpret_cast<float4 *>(a.raw32 + (obase + p) * C + c4 * 4) = accR;
+      if (rawact) Store4<T>::st(rawact + (obase + p) * C + c4 * 4, accR);
+    } else {
+      int yi = p / W, xi = p % W;
+      float4 v = *reinterpret_cast<const float4 *>(src + (int64_t)p * Cs + cc);
+      float4 o = gn_act(v, mean, rstd, ga, be, has_film, sc, sh, a.silu);
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {
+        int64_t q = obase + (int64_t)(2 * yi + (d >> 1)) * Wo + 2 * xi + (d & 1);
+        Store4<T>::st(act + q * C + c4 * 4, o);
+        if (a.raw32) *reinterpret_cast<float4 *>(a.raw32 + q * C + c4 * 4) = v;
+        if (rawact) Store4<T>::st(rawact + q * C + c4 * 4, v);
+      }
+    }
+  }
+}
+
+int launch_gn_apply(const GnApplyArgs &a, cudaStream_t st) {
+  int C = a.C1 + a.C2;
+  DPIR_REQUIRE(C % 128 == 0 && a.C1 % 4 == 0 && C <= 4096, "gn_apply: channels must be a multiple of 128 (got %d)", C);
+  DPIR_REQUIRE(a.resample != RS_DOWN || (a.H % 2 == 0 && a.W % 2 == 0), "gn_apply: downsample needs even H, W");
+  GnDev d{a.src1, a.C1, a.src2, a.C2, a.stats, a.gamma, a.beta, a.film, a.film_stride, a.silu, a.H, a.W, a.raw32};
+  int nwork = (a.resample == RS_DOWN) ? (a.H / 2) * (a.W / 2) : a.H * a.W;
+  dim3 grid(cdiv(nwork, GN_APPLY_PIX), a.B);
+  int threads = gn_threads(C);
+#define GN_LAUNCH(T, M) k_gn_apply<T, M><<<grid, threads, 0, st>>>(d, (T *)a.act, (T *)a.rawact)
+  if (a.out_half) {
+    if (a.resample == RS_NONE) GN_LAUNCH(__half, RS_NONE);
+    else if (a.resample == RS_DOWN) GN_LAUNCH(__half, RS_DOWN);
+    else GN_LAUNCH(__half, RS_UP);
+  } else {
+    if (a.resample == RS_NONE) GN_LAUNCH(float, RS_NONE);
+    else if (a.resample == RS_DOWN) GN_LAUNCH(float, RS_DOWN);
+    else GN_LAUNCH(float, RS_UP);
+  }
+#undef GN_LAUNCH
+  DPIR_LAUNCH_CHECK();
+  return DPIR_OK;
+}
+
+// =========================================================================================== fp32 implicit-GEMM conv
+// D[pixel][co] = sum_{tap, ci} act[pixel + tap][ci] * w[tap][ci][co]  on CUDA cores (parity mode / debugging aid).
+// Tile 64 pixels x 64 couts x 16 channels, 256 threads, 4x4 register micro-tile.
+constexpr int SB_M = 64, SB_N = 64, SB_K = 16, SB_PAD = 4;
+
+__global__ void __launch_bounds__(256) k_conv_simt(const float *__restrict__ act, const float *__restrict__ w, int ldw,
+                                                   ConvEpi epi, int B, int H, int W, int Cin, int Cout, int ksize) {
+  __shared__ __align__(16) float As[SB_K][SB_M + SB_PAD];
+  __shared__ __align__(16) float Bs[SB_K][SB_N];
+  int tid = threadIdx.x;
+  int64_t npix = (int64_t)B * H * W;
+  int64_t m0 = (int64_t)blockIdx.x * SB_M;
+  int n0 = blockIdx.y * SB_N;
+  // A-load role: pixel row = tid/4, channel quad = tid%4
+  int ar = tid >> 2, aq = tid & 3;
+  int64_t ap = m0 + ar;
+  bool apv = ap < npix;
+  int ax = 0, ay = 0, an = 0;
+  if (apv) { ax = (int)(ap % W); ay = (int)((ap / W) % H); an = (int)(ap / ((int64_t)W * H)); }
+  // B-load role: k row = tid/16, col quad = tid%16
+  int br = tid >> 4, bq = tid & 15;
+  int ty = tid >> 4, tx = tid & 15;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  int taps = ksize * ksize, pad = ksize / 2;
+  for (int tap = 0; tap < taps; ++tap) {
+    int dy = tap / ksize - pad, dx = tap % ksize - pad;
+    int yy = ay + dy, xx = ax + dx;
+    bool v = apv && yy >= 0 && yy < H && xx >= 0 && xx < W;
+    const float *arow = act + (((int64_t)an * H + yy) * W + xx) * Cin;
+    const float *wt = w + (int64_t)tap * Cin * ldw;
+    for (int c0 = 0; c0 < Cin; c0 += SB_K) {
+      float4 av = v ? *reinterpret_cast<const float4 *>(arow + c0 + aq * 4) : make_float4(0, 0, 0, 0);
+      float4 bv = make_float4(0, 0, 0, 0);
+      if (n0 + bq * 4 < ldw) bv = *reinterpret_cast<const float4 *>(wt + (int64_t)(c0 + br) * ldw + n0 + bq * 4);
+      __syncthreads();
+      As[aq * 4 + 0][ar] = av.x; As[aq * 4 + 1][ar] = av.y; As[aq * 4 + 2][ar] = av.z; As[aq * 4 + 3][ar] = av.w;
+      *reinterpret_cast<float4 *>(&Bs[br][bq * 4]) = bv;
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < SB_K; ++k) {
+        float4 a4 = *reinterpret_cast<const float4 *>(&As[k][ty * 4]);
+        float4 b4 = *reinterpret_cast<const float4 *>(&Bs[k][tx * 4]);
+        float a_[4] = {a4.x, a4.y, a4.z, a4.w}, b_[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] += a_[i] * b_[j];
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int64_t p = m0 + ty * 4 + i;
+    if (p >= npix) continue;
+    int x = (int)(p % W), y = (int)((p / W) % H), n = (int)(p / ((int64_t)W * H));
+    int co = n0 + tx * 4;
+    int ncols = Cout - co;
+    if (ncols <= 0) continue;
+    if (ncols > 4) ncols = 4;
+    conv_epilogue_store(epi, n, y, x, H, W, Cout, co, acc[i], ncols);
+  }
+}
+
+int launch_conv_simt(const float *act, const float *w, int ldw, const ConvEpi &epi, int B, int H, int W, int Cin, int Cout,
+                     int ksize, cudaStream_t st) {
+  DPIR_REQUIRE(Cin % SB_K == 0 && ldw % 4 == 0 && ldw >= Cout, "conv_simt: Cin %% 16 == 0 and padded Cout %% 4 == 0 required");
+  DPIR_REQUIRE(ksize == 1 || ksize == 3, "conv_simt: ksize must be 1 or 3");
+  int64_t npix = (int64_t)B * H * W;
+  dim3 grid(cdiv(npix, SB_M), cdiv(Cout, SB_N));
+  k_conv_simt<<<grid, 256, 0, st>>>(act, w, ldw, epi, B, H, W, Cin, Cout, ksize);
+  DPIR_LAUNCH_CHECK();
+  return DPIR_OK;
+}
+
+// =========================================================================================== attention
+// softmax((q*s)^T (k*s)) v per (sample, head), s = ch^-1/4, ch = 64  [unet.py:337-354].  Flash-style: 64-query tile per
+// CTA, streams 64-key tiles, online softmax in fp32; nothing of size T x T is materialised.
+constexpr int AT_D = 64, AT_Q = 64, AT_K = 64, AT_LD = 68;
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_attention(const float *__restrict__ qkv, T *__restrict__ out, int Tn, int C, int heads,
+                                                   int new_order) {
+  extern __shared__ __align__(16) float sm[];
+  float *Qt = sm;                       // [D][AT_LD]  (d-major: Qt[d][q])
+  float *Kt = Qt + AT_D * AT_LD;        // [D][AT_LD]
+  float *Vs = Kt + AT_D * AT_LD;        // [K][AT_LD]  (Vs[k][c])
+  float *Pt = Vs + AT_K * AT_LD;        // [K][AT_LD]  (Pt[k][q])
+  int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  int q0 = blockIdx.x * AT_Q;
+  int h = blockIdx.y, b = blockIdx.z;
+  int C3 = 3 * C;
+  int qoff, koff, voff;
+  if (new_order) { qoff = h * AT_D; koff = C + h * AT_D; voff = 2 * C + h * AT_D; }
+  else           { qoff = h * 3 * AT_D; koff = qoff + AT_D; voff = qoff + 2 * AT_D; }
+  const float *base = qkv + (int64_t)b * Tn * C3;
+  // load Q tile transposed: thread loads float4 along d for row r
+  {
+    int r = tid >> 2, qd = tid & 3;   // 64 rows x 4 quads of 16 -> loop 4 times over d quads
+    for (int it = 0; it < 4; ++it) {
+      int d = (qd * 4 + it) * 4;
+      float4 v = *reinterpret_cast<const float4 *>(base + (int64_t)(q0 + r) * C3 + qoff + d);
+      Qt[(d + 0) * AT_LD + r] = v.x; Qt[(d + 1) * AT_LD + r] = v.y; Qt[(d + 2) * AT_LD + r] = v.z; Qt[(d + 3) * AT_LD + r] = v.w;
+    }
+  }
+  float m_run[4], l_run[4], o[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    m_run[i] = -INFINITY; l_run[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
+  }
+  const float scale2 = 0.125f;  // (64^-1/4)^2
+  for (int k0 = 0; k0 < Tn; k0 += AT_K) {
+    __syncthreads();   // previous tile fully consumed (also orders the Q store on the first pass)
+    {
+      int r = tid >> 2, qd = tid & 3;
+      for (int it = 0; it < 4; ++it) {
+        int d = (qd * 4 + it) * 4;
+        const float *rowp = base + (int64_t)(k0 + r) * C3;
+        float4 kv = *reinterpret_cast<const float4 *>(rowp + koff + d);
+        Kt[(d + 0) * AT_LD + r] = kv.x; Kt[(d + 1) * AT_LD + r] = kv.y; Kt[(d + 2) * AT_LD + r] = kv.z; Kt[(d + 3) * AT_LD + r] = kv.w;
+        float4 vv = *reinterpret_cast<const float4 *>(rowp + voff + d);
+        *reinterpret_cast<float4 *>(&Vs[r * AT_LD + d]) = vv;
+      }
+    }
+    __syncthreads();
+    float s[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
+#pragma unroll 8
+    for (int d = 0; d < AT_D; ++d) {
+      float4 a4 = *reinterpret_cast<const float4 *>(&Qt[d * AT_LD + ty * 4]);
+      float4 b4 = *reinterpret_cast<const float4 *>(&Kt[d * AT_LD + tx * 4]);
+      float a_[4] = {a4.x, a4.y, a4.z, a4.w}, b_[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s[i][j] += a_[i] * b_[j];
+    }
+    // online softmax over this key tile; the 16 tx-lanes of a row share it (xor-shuffles stay inside the 16-lane group)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { s[i][j] *= scale2; mx = fmaxf(mx, s[i][j]); }
+#pragma unroll
+      for (int off = 1; off < 16; off <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+      float m_new = fmaxf(m_run[i], mx);
+      float corr = expf(m_run[i] - m_new);
+      float ps = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { s[i][j] = expf(s[i][j] - m_new); ps += s[i][j]; }
+#pragma unroll
+      for (int off = 1; off < 16; off <<= 1) ps += __shfl_xor_sync(0xffffffffu, ps, off);
+      l_run[i] = l_run[i] * corr + ps;
+      m_run[i] = m_new;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[i][j] *= corr;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) Pt[(tx * 4 + j) * AT_LD + ty * 4 + i] = s[i][j];
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int k = 0; k < AT_K; ++k) {
+      float4 p4 = *reinterpret_cast<const float4 *>(&Pt[k * AT_LD + ty * 4]);
+      float4 v4 = *reinterpret_cast<const float4 *>(&Vs[k * AT_LD + tx * 4]);
+      float p_[4] = {p4.x, p4.y, p4.z, p4.w}, v_[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[i][j] += p_[i] * v_[j];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float inv = 1.f / l_run[i];
+    float4 v = make_float4(o[i][0] * inv, o[i][1] * inv, o[i][2] * inv, o[i][3] * inv);
+    Store4<T>::st(out + ((int64_t)b * Tn + q0 + ty * 4 + i) * C + h * AT_D + tx * 4, v);
+  }
+}
+
+int launch_attention(const float *qkv, void *out, int out_half, int B, int T, int C, int heads, int new_order, cudaStream_t st) {
+  DPIR_REQUIRE(C == heads * AT_D, "attention: head dim must be 64 (C=%d heads=%d)", C, heads);
+  DPIR_REQUIRE(T % AT_Q == 0, "attention: token count must be a multiple of 64 (got %d)", T);
+  size_t smem = (size_t)4 * AT_D * AT_LD * sizeof(float);
+  dim3 grid(T / AT_Q, heads, B);
+  static bool attr_set = false;
+  if (!attr_set) {
+    DPIR_CUDA_CHECK(cudaFuncSetAttribute(k_attention<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DPIR_CUDA_CHECK(cudaFuncSetAttribute(k_attention<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  if (out_half) k_attention<__half><<<grid, 256, smem, st>>>(qkv, (__half *)out, T, C, heads, new_order);
+  else k_attention<float><<<grid, 256, smem, st>>>(qkv, (float *)out, T, C, heads, new_order);
+  DPIR_LAUNCH_CHECK();
+  return DPIR_OK;
+}
+
+// =========================================================================================== timestep embedding MLPs
+// hidden[b][o] = sum_i e(t_b)[i] * w0[o][i] + b0[o],  e = [cos(t f_j) | sin(t f_j)], f_j = freqs[j] (nn.py:112-118; the
+// table is computed once on the host with the reference's formula and uploaded).
+__global__ void k_time_embed0(const int64_t *__restrict__ t, const float *__restrict__ freqs, const float *__restrict__ w0,
+                              const float *__restrict__ b0, float *__restrict__ hidden, int mc, int ted) {
+  int b = blockIdx.y;
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= ted) return;
+  float tv = (float)t[b];
+  int half = mc / 2;
+  float acc = 0.f;
+  for (int i = lane; i < 2 * half; i += 32) {
+    int j = i < half ? i : i - half;
+    float a = tv * freqs[j];
+    float e = i < half ? cosf(a) : sinf(a);
+    acc += e * w0[(int64_t)warp * mc + i];
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if (lane == 0) hidden[(int64_t)b * ted + warp] = acc + b0[warp];
+}
+
+// y[b][o] = act_out(sum_i act_in(x[b][i]) W[o][i] + bias[o]); one warp per output row, the weight row is read once and
+// reused for every sample.
+__global__ void k_linear_rows(const float *__restrict__ x, const float *__restrict__ Wm, const float *__restrict__ bias,
+                              float *__restrict__ y, int B, int in_dim, int rows, int silu_in, int silu_out) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const float *wr = Wm + (int64_t)warp * in_dim;
+  float bz = bias[warp];
+  for (int b = 0; b < B; ++b) {
+    const float *xb = x + (int64_t)b * in_dim;
+    float acc = 0.f;
+    for (int i = lane; i < in_dim; i += 32) {
+      float v = xb[i];
+      if (silu_in) v = v / (1.f + expf(-v));
+      acc += v * wr[i];
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) {
+      float o = acc + bz;
+      if (silu_out) o = o / (1.f + expf(-o));
+      y[(int64_t)b * rows + warp] = o;
+    }
+  }
+}
+
+// emb_act = SiLU(time_embed(timestep_embedding(t)))  - every consumer (ResBlock.emb_layers, unet.py:199-205) starts with SiLU
+int launch_time_embed(const int64_t *t, const float *freqs, const float *w0, const float *b0, const float *w2, const float *b2,
+                      float *hidden, float *emb_act, int B, int mc, int ted, cudaStream_t st) {
+  dim3 grid(cdiv((int64_t)ted * 32, 256), B);
+  k_time_embed0<<<grid, 256, 0, st>>>(t, freqs, w0, b0, hidden, mc, ted);
+  DPIR_LAUNCH_CHECK();
+  return launch_linear_rows(hidden, w2, b2, emb_act, B, ted, ted, 1, 1, st);
+}
+
+int launch_linear_rows(const float *x, const float *W, const float *bias, float *y, int B, int in_dim, int rows, int silu_in,
+                       int silu_out, cudaStream_t st) {
+  k_linear_rows<<<cdiv((int64_t)rows * 32, 256), 256, 0, st>>>(x, W, bias, y, B, in_dim, rows, silu_in, silu_out);
+  DPIR_LAUNCH_CHECK();
+  return DPIR_OK;
+}
+
+}  // namespace dpir

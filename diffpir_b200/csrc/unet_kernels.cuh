@@ -1,0 +1,93 @@
+// unet_kernels.cuh - launch wrappers for the non-GEMM UNet kernels and the fp32 CUDA-core convolution.
+// All activations are NHWC; "virtual concat" sources (src1|src2 along C) implement th.cat of unet.py:660 without a copy.
+#pragma once
+#include "common.cuh"
+
+namespace dpir {
+
+enum Resample { RS_NONE = 0, RS_DOWN = 1, RS_UP = 2 };
+enum EpiMode { EPI_NHWC = 0, EPI_NCHW = 1, EPI_X0 = 2 };
+
+struct GnApplyArgs {
+  const float *src1; int C1;
+  const float *src2; int C2;          // may be null / 0
+  const double *stats;                // [B][32][2] (sum, sumsq) for this norm
+  const float *gamma, *beta;          // [C]
+  const float *film; int film_stride; // per-sample (scale[C], shift[C]) at film + b*film_stride, or null
+  int silu;                           // apply SiLU after the affine/FiLM
+  int resample;                       // Resample
+  int B, H, W;                        // input spatial size
+  int out_half;                       // 1: act / rawact are __half, 0: float
+  void *act;                          // activated output (resampled size)
+  float *raw32;                       // optional: raw (un-normalised) fp32 copy of the concat, resampled
+  void *rawact;                       // optional: raw copy in the activation dtype, resampled
+};
+
+struct ConvEpi {
+  int mode;                 // EpiMode
+  const float *bias;        // [Cout]
+  const float *residual;    // NHWC fp32 [B,H,W,Cout] or null (EPI_NHWC only)
+  float *out;               // NHWC [B,H,W,Cout] | NCHW [B,Cout,H,W] | x0 NCHW [B,3,H,W]
+  const float *x_nchw;      // EPI_X0: x_t (B,3,H,W)
+  const float *coef;        // EPI_X0: [T][2] (sqrt_recip_alphas_cumprod, sqrt_recipm1_alphas_cumprod) as float
+  const int64_t *t;         // EPI_X0: (B,) timesteps on device
+};
+
+#ifdef __CUDACC__
+// shared conv epilogue (bias / residual / NCHW / fused eps->x0); acc[0..ncols) = channels co.. of pixel (n,y,x)
+__device__ __forceinline__ void conv_epilogue_store(const ConvEpi &e, int n, int y, int x, int H, int W, int Cout, int co,
+                                                    const float *acc, int ncols) {
+  // acc[0..ncols) are output channels co..co+ncols of pixel (n,y,x)
+  if (e.mode == EPI_NHWC) {
+    int64_t pix = ((int64_t)n * H + y) * W + x;
+    float *o = e.out + pix * Cout + co;
+    const float *r = e.residual ? e.residual + pix * Cout + co : nullptr;
+    if (ncols == 4 && (Cout & 3) == 0) {
+      float4 b = *reinterpret_cast<const float4 *>(e.bias + co);
+      float4 v = make_float4(acc[0] + b.x, acc[1] + b.y, acc[2] + b.z, acc[3] + b.w);
+      if (r) { float4 rv = *reinterpret_cast<const float4 *>(r); v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w; }
+      *reinterpret_cast<float4 *>(o) = v;
+    } else {
+      for (int j = 0; j < ncols; ++j) o[j] = acc[j] + e.bias[co + j] + (r ? r[j] : 0.f);
+    }
+  } else if (e.mode == EPI_NCHW) {
+    for (int j = 0; j < ncols; ++j)
+      e.out[(((int64_t)n * Cout + co + j) * H + y) * W + x] = acc[j] + e.bias[co + j];
+  } else {  // EPI_X0: x0 = clamp(c1[t] x - c2[t] eps, -1, 1), eps = channels 0..2   [gaussian_diffusion.py:305-311,328-333]
+    int64_t tt = e.t[n];
+    float c1 = e.coef[2 * tt], c2 = e.coef[2 * tt + 1];
+    for (int j = 0; j < ncols; ++j) {
+      int c = co + j;
+      if (c < 3) {
+        int64_t idx = (((int64_t)n * 3 + c) * H + y) * W + x;
+        float v = c1 * e.x_nchw[idx] - c2 * (acc[j] + e.bias[c]);
+        e.out[idx] = fminf(fmaxf(v, -1.f), 1.f);
+      }
+    }
+  }
+}
+#endif
+
+int launch_conv_in(const float *x_nchw, const float *w, const float *bias, float *out, int B, int H, int W, int Cin, int Cout,
+                   cudaStream_t st);
+int launch_gn_stats(const float *src1, int C1, const float *src2, int C2, double *stats, int B, int HW, cudaStream_t st);
+int launch_gn_apply(const GnApplyArgs &a, cudaStream_t st);
+int launch_conv_simt(const float *act, const float *w, int ldw, const ConvEpi &epi, int B, int H, int W, int Cin, int Cout,
+                     int ksize, cudaStream_t st);
+// qkv fp32 [B,T,3C] -> out [B,T,C] (dtype per out_half); head dim 64
+int launch_attention(const float *qkv, void *out, int out_half, int B, int T, int C, int heads, int new_order, cudaStream_t st);
+// sinusoidal embedding + time_embed MLP (nn.py:103-121, unet.py:471-475): t (B,) int64 -> emb_act = SiLU(emb) [B][ted]
+int launch_time_embed(const int64_t *t, const float *freqs, const float *w0, const float *b0, const float *w2, const float *b2,
+                      float *hidden, float *emb_act, int B, int mc, int ted, cudaStream_t st);
+// y[b][o] = act_out(sum_i act_in(x[b][i]) W[o][i] + bias[o])  (emb_layers of every ResBlock in one launch)
+int launch_linear_rows(const float *x, const float *W, const float *bias, float *y, int B, int in_dim, int rows, int silu_in,
+                       int silu_out, cudaStream_t st);
+
+// tcgen05 convolution (conv_tc.cu)
+struct ConvTcPlan;  // opaque: tensor maps + geometry
+int conv_tc_plan_create(const void *act_half, const void *w_half, int B, int H, int W, int Cin, int CoutPad, int ksize,
+                        ConvTcPlan **out);
+void conv_tc_plan_destroy(ConvTcPlan *p);
+int launch_conv_tc(const ConvTcPlan *p, const ConvEpi &epi, int Cout, cudaStream_t st);
+
+}  // namespace dpir

@@ -1,0 +1,201 @@
+/*
+ * diffpir_b200.h - C-ABI of libdiffpir_b200.so: the B200 (sm_100a) DiffPIR sampling hot path.
+ *
+ * The reference (yuanzhi-zhu/DiffPIR) is pure Python/PyTorch and has no FFI; its "operator API" for
+ * this path is a set of Python call signatures used by the four drivers.  Each
+ * entry point below names the reference call it stands in for (file:line relative to the reference
+ * root).  diffpir_b200/*.py binds these with ctypes and re-exposes the reference signatures.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes only; no torch / C++ types cross the boundary.
+ *   - every pointer marked "dev" is a CUDA device pointer owned by the CALLER (contiguous, 16-byte aligned);
+ *     the library owns only what dpir_create / dpir_fft_plan_create allocate and frees it in *_destroy.
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, the library never
+ *     synchronises and never changes the current device.
+ *   - return value: 0 = ok, negative = error (DPIR_E_*); dpir_last_error() returns a message for the
+ *     calling thread.  No CPU fallback exists: without a GPU every compute call fails with DPIR_E_CUDA.
+ *   - handles are not thread-safe.
+ */
+#ifndef DIFFPIR_B200_H
+#define DIFFPIR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+#define DPIR_OK 0
+#define DPIR_E_ARG (-1)      /* bad argument / unsupported shape */
+#define DPIR_E_CUDA (-2)     /* CUDA runtime / driver error */
+#define DPIR_E_CUFFT (-3)    /* cuFFT error */
+#define DPIR_E_STATE (-4)    /* call order (e.g. forward before weights are complete) */
+#define DPIR_E_NOMEM (-5)
+
+#define DPIR_PRECISION_FP32 0  /* fp32 CUDA-core convolutions: parity mode (<=1e-4 rel-L2 vs reference) */
+#define DPIR_PRECISION_FP16 1  /* fp16 operands, fp32 accumulate on tcgen05 tensor cores: throughput mode */
+
+const char *dpir_last_error(void);
+int dpir_version(void);
+/* number of CUDA kernels launched by this library on the calling thread since the last reset */
+int64_t dpir_launch_count(void);
+void dpir_launch_count_reset(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * UNet denoiser engine.  Replaces the model object built by
+ *   guided_diffusion/script_util.py:74-184 create_model_and_diffusion / create_model  and
+ *   guided_diffusion/unet.py:396-663 UNetModel (forward :634-663).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct dpir_engine dpir_engine;
+
+typedef struct dpir_unet_config {
+  int32_t image_size;          /* script_util.py:147-158 picks channel_mult from it; informational here */
+  int32_t in_channels;         /* 3 */
+  int32_t model_channels;      /* 128 (FFHQ) / 256 (ImageNet); must be a multiple of 128 */
+  int32_t out_channels;        /* 6 (learn_sigma) */
+  int32_t num_res_blocks;
+  int32_t n_channel_mult;
+  int32_t channel_mult[8];
+  int32_t n_attention_ds;
+  int32_t attention_ds[8];     /* downsample rates with attention, unet.py:501, 577 */
+  int32_t num_heads;
+  int32_t num_head_channels;   /* 64; -1 => use num_heads */
+  int32_t num_heads_upsample;  /* -1 => num_heads */
+  int32_t use_new_attention_order; /* 0: QKVAttentionLegacy unet.py:328-358, 1: QKVAttention :361-393 */
+  int32_t precision;           /* DPIR_PRECISION_* */
+  int32_t diffusion_steps;     /* 1000: size of the eps->x0 coefficient tables */
+} dpir_unet_config;
+
+int dpir_create(const dpir_unet_config *cfg, dpir_engine **out);
+int dpir_destroy(dpir_engine *e);
+
+/* model.load_state_dict (main_ddpir.py:234): one call per checkpoint tensor, names exactly as in the
+ * reference state_dict (time_embed.0.weight, input_blocks.3.0.in_layers.2.weight, ...).  `data` is a
+ * HOST pointer to contiguous fp32 in the checkpoint layout (conv OIHW, conv1d (O,I,1), linear (O,I)).
+ * The tensor is repacked into the kernel-native layout inside the device weight arena. */
+int dpir_load_weight(dpir_engine *e, const char *name, const float *data, const int64_t *shape, int32_t ndim);
+/* number of checkpoint tensors still missing (0 => ready) */
+int dpir_missing_weights(dpir_engine *e);
+/* packed device weight arena (for the one-time NCCL broadcast); after a broadcast
+ * into it call dpir_mark_weights_loaded. */
+int dpir_weight_arena(dpir_engine *e, void **dev_ptr, size_t *bytes);
+int dpir_mark_weights_loaded(dpir_engine *e);
+
+/* Optional: override the built-in tables with host-computed ones (so they are bit-identical to the reference's numpy /
+ * torch evaluation): freqs[model_channels/2] of nn.py:112-114, coef[T][2] = (sqrt_recip_alphas_cumprod,
+ * sqrt_recipm1_alphas_cumprod) of gaussian_diffusion.py:150-151 cast to float (:905).  Either pointer may be NULL. */
+int dpir_set_tables(dpir_engine *e, const float *freqs, int32_t n_freqs, const float *coef, int32_t T);
+
+/* UNetModel.forward (unet.py:634-663): x dev (B,3,H,W) fp32 NCHW, t dev (B,) int64 -> out dev (B,6,H,W) fp32. */
+int dpir_unet_forward(dpir_engine *e, const float *x, const int64_t *t, float *out,
+                      int32_t B, int32_t H, int32_t W, void *stream);
+/* utils_model.model_fn(..., model_out_type='pred_xstart') = diffusion.p_sample(...)['pred_xstart']
+ * (utils/utils_model.py:207-258; gaussian_diffusion.py:258-311, 328-333): UNet forward with the
+ * eps->x0 conversion x0 = clamp(c1[t] x - c2[t] eps, -1, 1) fused into the output convolution. */
+int dpir_unet_x0(dpir_engine *e, const float *x, const int64_t *t, float *x0,
+                 int32_t B, int32_t H, int32_t W, void *stream);
+/* workspace bytes currently held for activations (diagnostics) */
+int64_t dpir_workspace_bytes(dpir_engine *e);
+/* 1 => replay the forward from a captured CUDA graph (per batch shape) instead of stream launches */
+int dpir_set_graph_mode(dpir_engine *e, int32_t enable);
+
+/* ------------------------------------------------------------------------------------------------
+ * FFT-domain data-fidelity solver.  Replaces utils/utils_sisr.py:
+ *   p2o :22-41, upsample :44-52, pre_calculate :78-95, splits :9-19, data_solution :65-75.
+ * Spectra are Hermitian half-spectra (H, W/2+1) complex64 (interleaved re,im).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct dpir_fft_plan dpir_fft_plan;
+/* batch = number of (H,W) planes transformed per call */
+int dpir_fft_plan_create(int32_t batch, int32_t H, int32_t W, dpir_fft_plan **out);
+int dpir_fft_plan_destroy(dpir_fft_plan *p);
+int dpir_rfft2(dpir_fft_plan *p, const float *in, float *out_spec, void *stream);
+/* unnormalised inverse; destroys spec */
+int dpir_irfft2(dpir_fft_plan *p, float *spec, float *out, void *stream);
+
+/* pre_calculate (utils_sisr.py:78-95).  y dev (B,C,H/sf,W/sf); k dev (Bk,1,kh,kw) with Bk in {1,B};
+ * outputs: FB (Bk,1,H,Wh) complex, F2B (Bk,1,H,Wh) real, FBFy (B,C,H,Wh) complex, Wh = W/2+1.
+ * plan_k has batch Bk, plan_y batch B*C.  scratch: dev, >= max(Bk, B*C) * H * W floats. */
+int dpir_fft_precalc(dpir_fft_plan *plan_k, dpir_fft_plan *plan_y, const float *y, const float *k,
+                     int32_t B, int32_t C, int32_t Bk, int32_t kh, int32_t kw, int32_t sf,
+                     float *FB, float *F2B, float *FBFy, float *scratch, void *stream);
+
+/* data_solution (utils_sisr.py:65-75) evaluated in the cancellation-free form
+ *   FX = Fx + conj(FB) (FBFy/conj(FB) - mean_alias(FB Fx)) / (mean_alias|FB|^2 + alpha)
+ * with the affine pre/post steps of the loop (main_ddpir.py:396-400) folded in:
+ *   x_in  = in_scale * x + in_bias;   Xest = data_solution(x_in, ...);
+ *   out   = blend * (out_scale * Xest + out_bias) + (1 - blend) * x
+ * Reference semantics (x -> Xest): in_scale=1,in_bias=0,out_scale=1,out_bias=0,blend=1.
+ * Loop semantics on x0 in [-1,1]: in 0.5,0.5; out 2,-1; blend = guidance_scale.
+ * spec: dev scratch, B*C*H*Wh complex.  out may alias x. */
+int dpir_fft_solve(dpir_fft_plan *plan_x, const float *x, const float *FB, const float *F2B, const float *FBFy,
+                   float alpha, int32_t B, int32_t C, int32_t Bk, int32_t sf,
+                   float in_scale, float in_bias, float out_scale, float out_bias, float blend,
+                   float *spec, float *out, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Elementwise steps of the loop (inline in the reference drivers).
+ * ------------------------------------------------------------------------------------------------ */
+/* inpaint prox, main_ddpir.py:393-394 / main_ddpir_inpainting.py:267-268:
+ *   x0_p = (mask*(y_scale*y + y_bias) + tau*x0)/(mask+tau); out = x0 + guidance*(x0_p - x0).  n elements. */
+int dpir_inpaint_prox(const float *x0, const float *y, const float *mask, float tau, float y_scale, float y_bias,
+                      float guidance, float *out, int64_t n, void *stream);
+/* re-noise, main_ddpir.py:451-456 with precomputed scalars:
+ *   eps = (x - sa_t*x0)/s1_t;  out = sa_p*x0 + c_eps*eps + c_eta*noise_eta + c_zeta*noise_zeta
+ * noise_eta may be NULL when c_eta == 0. */
+int dpir_renoise(const float *x, const float *x0, const float *noise_eta, const float *noise_zeta,
+                 float sa_t, float s1_t, float sa_p, float c_eps, float c_eta, float c_zeta,
+                 float *out, int64_t n, void *stream);
+/* eps -> x0 (gaussian_diffusion.py:328-333 + clamp :305-307) on an existing model output:
+ *   model_out dev (B,Cout>=3,H,W), x dev (B,3,H,W), coef dev (B,2) = (c1,c2) per sample. */
+int dpir_eps_to_x0(const float *model_out, const float *x, const float *coef, float *x0,
+                   int32_t B, int32_t Cout, int32_t HW, int32_t clip, void *stream);
+/* generic y = a*x + b (range conversions x/2+.5, 2x-1 around the operators) */
+int dpir_affine(const float *x, float a, float b, float *out, int64_t n, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Separable antialiased resize.  Replaces Resizer.forward, utils/utils_resizer.py:55-74: for each
+ * resized dim, out[o] = sum_t w[t][o] * in[fov[t][o]] (gather + weighted sum); weights / field-of-view
+ * tables come from Resizer.contributions :104-167 (host, init-time) and are passed in.
+ *   in dev (N, Hin, Win) planes; w_h/fov_h dev (taps_h, Hout); w_w/fov_w dev (taps_w, Wout);
+ *   tmp dev (N, Hout, Win) floats; out dev (N, Hout, Wout).
+ * ------------------------------------------------------------------------------------------------ */
+int dpir_resize_separable(const float *in, int32_t N, int32_t Hin, int32_t Win, int32_t Hout, int32_t Wout,
+                          const float *w_h, const int32_t *fov_h, int32_t taps_h,
+                          const float *w_w, const int32_t *fov_w, int32_t taps_w,
+                          float *tmp, float *out, void *stream);
+/* IBP update, main_ddpir.py:403-406 (one inner iteration), x0 in [-1,1], y and down in [0,1] low-res:
+ *   out = 2*((x0/2+.5) + gamma*nearest_up(y - down, sf)/(1+rho)) - 1 */
+int dpir_ibp_update(const float *x0, const float *y, const float *down, float gamma, float rho,
+                    int32_t N, int32_t H, int32_t W, int32_t sf, float *out, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Blur operator H (reference utils/utils_deblur.py:641-727 Blurkernel.forward: ReflectionPad2d(k//2) +
+ * depthwise conv).  x dev (B,C,H,W), k dev (kh,kw) shared by all planes. */
+int dpir_blur_reflect(const float *x, const float *k, int32_t planes, int32_t H, int32_t W, int32_t kh, int32_t kw,
+                      float *out, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Low-level entry points exposed for per-kernel parity tests and benchmarks (tests/ and bench.py).
+ * NHWC activations.  act_dtype: 0 = fp32, 1 = fp16.
+ * ------------------------------------------------------------------------------------------------ */
+/* 3x3 (pad 1) or 1x1 stride-1 convolution on tensor cores (tcgen05): act dev fp16 (B,H,W,Cin),
+ * w dev fp16 packed [tap][CoutPad][Cin], bias dev fp32 (Cout), residual dev fp32 (B,H,W,Cout) or NULL,
+ * out dev fp32 (B,H,W,Cout).  Cin % 64 == 0. */
+int dpir_conv_tc(const void *act, const void *w, const float *bias, const float *residual, float *out,
+                 int32_t B, int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t CoutPad, int32_t ksize,
+                 void *stream);
+/* same contract on CUDA cores in fp32: act fp32, w fp32 packed [tap][Cin][Cout]. */
+int dpir_conv_simt(const float *act, const float *w, const float *bias, const float *residual, float *out,
+                   int32_t B, int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t ksize, void *stream);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIFFPIR_B200_H */

@@ -1,0 +1,72 @@
+"""Trajectory parity: the sampling loop engine vs the CPU oracle loop with identical pre-drawn noise."""
+import numpy as np
+import pytest
+import torch
+
+from diffpir_b200 import synth
+from oracle import diffpir_oracle as orc
+from tests.util import make_model, psnr, rel_l2, small_config, weights
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(task, B=2, size=64, sf=1, seed=0):
+    imgs = synth.synthetic_images(B, size, seed=100 + seed)
+    gt = torch.from_numpy(imgs).permute(0, 3, 1, 2).float() / 255.0
+    k = mask = None
+    if task == "deblur":
+        kk = synth.gaussian_kernel(21, 2.0)
+        y = np.stack([synth.blur_measurement(imgs[b], kk, 0.05, seed=b) for b in range(B)])
+        y = torch.from_numpy(y).permute(0, 3, 1, 2).contiguous()
+        k = torch.from_numpy(kk)[None, None]
+    elif task == "sr":
+        kk = synth.gaussian_kernel(25, 1.6)
+        k = torch.from_numpy(kk)[None, None]
+        FBl = orc.p2o(k, (size, size))
+        blurred = torch.real(torch.fft.ifftn(FBl * torch.fft.fftn(gt, dim=(-2, -1)), dim=(-2, -1)))
+        y = blurred[..., 0::sf, 0::sf].contiguous()
+    else:
+        y = gt.clone()
+        mask = synth.random_mask(B, size, 0.5, seed=3)
+    return gt, y, k, mask
+
+
+CASES = [
+    ("deblur", 1, dict(lambda_=7.0, zeta=0.3, sigma=0.05)),
+    ("sr", 4, dict(lambda_=6.0, zeta=0.25, sigma=0.05)),
+    ("inpaint", 1, dict(lambda_=1.0, zeta=1.0, sigma=0.0)),
+]
+
+
+@pytest.mark.parametrize("task,sf,hp", CASES)
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_loop_matches_oracle(task, sf, hp, precision):
+    from diffpir_b200.sampler import DiffPIRSampler
+    cfg = small_config()
+    sd = weights(cfg)
+    B, size, iters = 2, 64, 8
+    gt, y, k, mask = _setup(task, B, size, sf)
+    init, zs = synth.predrawn_noise((B, 3, size, size), iters, seed=7)
+    x_init = None
+    if task == "sr":
+        x_init = torch.nn.functional.interpolate(y, scale_factor=sf, mode="bicubic", align_corners=False)
+    tr_ref = []
+    ref = orc.diffpir_loop(sd, cfg.as_dict(), task, y, k=(k.expand(B, 1, *k.shape[-2:]) if k is not None else None),
+                           mask=mask, sf=sf, iter_num=iters, init_noise=init, zeta_noise=zs, x_init=x_init, trace=tr_ref, **hp)
+    m = make_model(cfg, precision)
+    s = DiffPIRSampler(m, task, sf=sf, iter_num=iters, **hp)
+    tr = []
+    out = s.run(y.cuda(), k=(k.cuda() if k is not None else None), mask=(mask.cuda() if mask is not None else None),
+                x_init=(x_init.cuda() if x_init is not None else None), init_noise=init.cuda(),
+                zeta_noise=[z.cuda() for z in zs], trace=tr)
+    assert len(tr) == len(tr_ref)
+    tol = 1e-4 if precision == "fp32" else 1e-2
+    worst = 0.0
+    for (n1, i1, a), (n2, i2, b) in zip(tr, tr_ref):
+        assert (n1, i1) == (n2, i2)
+        worst = max(worst, rel_l2(a, b))
+    assert rel_l2(out, ref) < tol, (rel_l2(out, ref), worst)
+    # north-star bar: PSNR against ground truth within 0.01 dB of the reference path
+    assert abs(psnr(out, gt) - psnr(ref, gt)) < 0.01
+    if precision == "fp32":
+        assert worst < 5e-4, worst

@@ -1,0 +1,95 @@
+"""UNet engine parity against the CPU oracle (oracle/unet_oracle.py) on seeded synthetic weights."""
+import pytest
+import torch
+
+from oracle import diffpir_oracle as orc
+from oracle import unet_oracle
+from tests.util import make_model, rel_l2, small_config, weights
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": 1e-4, "fp16": 4e-3}   # rel-L2 of the eps prediction; fp16 = operand rounding of ~60 chained GEMMs
+
+
+def _inputs(B, size, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(B, 3, size, size, generator=g), torch.randint(0, 1000, (B,), generator=g)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_small_unet_forward_matches_oracle(precision):
+    cfg = small_config()
+    sd = weights(cfg)
+    x, t = _inputs(3, 64)
+    ref = unet_oracle.unet_forward(sd, cfg.as_dict(), x.double(), t)
+    m = make_model(cfg, precision)
+    out = m(x.cuda(), t.cuda())
+    assert tuple(out.shape) == (3, 6, 64, 64)
+    err = rel_l2(out, ref)
+    assert err < TOL[precision], err
+    # a second batch shape re-plans the workspace; results must not depend on the plan
+    out1 = m(x[:1].cuda(), t[:1].cuda())
+    assert rel_l2(out1, ref[:1]) < TOL[precision]
+    out3 = m(x.cuda(), t.cuda())
+    assert torch.equal(out3, out)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_small_unet_x0_matches_oracle(precision):
+    cfg = small_config()
+    sd = weights(cfg)
+    x, t = _inputs(2, 64, seed=1)
+    t = torch.tensor([999, 400])
+    eps = unet_oracle.unet_forward(sd, cfg.as_dict(), x.double(), t)
+    ref = orc.pred_xstart(eps, x.double(), t)
+    m = make_model(cfg, precision)
+    x0 = m.x0(x.cuda(), t.cuda())
+    # before the clamp the error of eps is amplified by sqrt(1/abar - 1) (157 at t=999): compare where not saturated too
+    assert float(x0.max()) <= 1 and float(x0.min()) >= -1
+    assert rel_l2(x0, ref) < (2e-4 if precision == "fp32" else 2e-2)
+    # the fused epilogue must agree with the unfused route on the same engine
+    from diffpir_b200 import ops
+    tabs = orc.diffusion_tables()
+    coef = torch.stack([torch.from_numpy(tabs["sqrt_recip_alphas_cumprod"])[t].float(),
+                        torch.from_numpy(tabs["sqrt_recipm1_alphas_cumprod"])[t].float()], 1).cuda()
+    x0b = ops.eps_to_x0(m(x.cuda(), t.cuda()), x.cuda(), coef)
+    assert rel_l2(x0, x0b) < 1e-6
+
+
+def test_graph_mode_matches_stream_mode():
+    cfg = small_config()
+    x, t = _inputs(2, 64, seed=2)
+    m = make_model(cfg, "fp16")
+    a = m(x.cuda(), t.cuda())
+    m.set_graph_mode(True)
+    b = m(x.cuda(), t.cuda())
+    c = m(x.cuda(), t.cuda())
+    assert torch.equal(a, b) and torch.equal(b, c)
+    x2, t2 = _inputs(2, 64, seed=3)
+    d = m(x2.cuda(), t2.cuda())
+    m.set_graph_mode(False)
+    assert torch.equal(d, m(x2.cuda(), t2.cuda()))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_ffhq_unet_forward_matches_oracle(precision):
+    """The real diffusion_ffhq_10m architecture at 256x256, one image."""
+    from diffpir_b200 import arch
+    cfg = arch.ffhq_config()
+    sd = weights(cfg)
+    x, _ = _inputs(1, 256, seed=4)
+    t = torch.tensor([321])
+    ref = unet_oracle.unet_forward(sd, cfg.as_dict(), x, t)
+    m = make_model(cfg, precision)
+    out = m(x.cuda(), t.cuda())
+    err = rel_l2(out, ref)
+    assert err < TOL[precision], err
+
+
+def test_missing_weights_is_an_error():
+    from diffpir_b200.unet import UNetModel
+    cfg = small_config()
+    m = UNetModel(cfg, precision="fp32")
+    assert m.missing_weights() > 0
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 3, 64, 64, device="cuda"), torch.zeros(1, dtype=torch.long, device="cuda"))

@@ -1,0 +1,82 @@
+"""Host-side logic (no GPU): architecture replay, schedule tables, resizer tables, measurement synthesis."""
+import numpy as np
+import torch
+
+from diffpir_b200 import arch, synth
+from diffpir_b200.sampler import StepTable, make_seq
+from oracle import diffpir_oracle as orc
+from oracle import unet_oracle
+
+
+def test_flops_match_survey():
+    assert abs(arch.flops_per_image(arch.ffhq_config()) / 1e9 - 387.93) < 0.01
+    assert abs(arch.flops_per_image(arch.imagenet_config()) / 1e9 - 2239.67) < 0.01
+
+
+def test_param_specs_counts():
+    f = arch.param_specs(arch.ffhq_config())
+    assert len(f) == 362 and sum(int(np.prod(s)) for _, s in f) == 93563910
+    i = arch.param_specs(arch.imagenet_config())
+    assert len(i) == 566 and sum(int(np.prod(s)) for _, s in i) == 552814086
+
+
+def test_layer_program_agrees_with_oracle_replay():
+    for cfg in (arch.ffhq_config(), arch.imagenet_config()):
+        a = arch.build_layers(cfg)
+        b = unet_oracle.block_program(cfg.as_dict())
+        for blocks_a, blocks_b in zip(a, (b[0], [b[1]], b[2])):
+            assert len(blocks_a) == len(blocks_b)
+            for la, lb in zip(blocks_a, blocks_b):
+                assert [(l.kind, l.cin, l.cout) for l in la] == [(x[0], x[1], x[2] if x[0] != "attn" else x[1]) for x in lb]
+                for l, x in zip(la, lb):
+                    if l.kind == "res":
+                        assert (l.updown or None) == x[3]
+                    if l.kind == "attn":
+                        assert l.heads == x[2]
+
+
+def test_step_table_matches_oracle_schedule():
+    for iters, skip in ((100, "quad"), (20, "quad"), (20, "uniform")):
+        tb = StepTable(sigma=0.05, lambda_=7.0, zeta=0.3, iter_num=iters, skip_type=skip)
+        sched = orc.driver_schedule()
+        rhos, sigmas = orc.rhos_sigmas(sched, 7.0, 0.05)
+        seq = orc.make_seq(1000, iters, skip)
+        assert seq == make_seq(1000, iters, skip) == tb.seq
+        red = sched["reduced_alpha_cumprod"].numpy()
+        assert len(tb.steps) == len(seq)
+        for st in tb.steps:
+            i = st["i"]
+            t_i = orc.find_nearest(red, sigmas[seq[i]].numpy())
+            assert st["t_i"] == t_i == 999 - seq[i]
+            assert np.float32(st["rho"]) == np.float32(rhos[t_i])
+            if not st["last"]:
+                assert st["t_im1"] == orc.find_nearest(red, sigmas[seq[i + 1]].numpy())
+        assert tb.steps[-1]["last"] and sum(s["last"] for s in tb.steps) == 1
+    tb = StepTable(sigma=0.0, lambda_=1.0, zeta=1.0, iter_num=100)
+    assert tb.steps[0]["t_i"] == 999 and tb.n_renoise == 99
+
+
+def test_resizer_tables_match_oracle():
+    from diffpir_b200.utils_resizer import Resizer
+    for n, scale in ((256, 0.25), (64, 0.5), (32, 2.0), (96, 1 / 3)):
+        r = Resizer((2, 3, n, n), scale)
+        w, f = orc.resizer_contributions(n, int(np.ceil(n * scale)), scale, antialiasing=scale < 1)
+        for d in (0, 1):
+            assert torch.equal(r._tabs[d][0], torch.tensor(w.T, dtype=torch.float32))
+            assert np.array_equal(r._tabs[d][1].numpy(), f.T.astype(np.int32))   # index tables: bit-exact
+
+
+def test_measurement_synthesis_truncates_like_scipy_uint8():
+    img = synth.synthetic_images(1, 64, seed=5)[0]
+    k = synth.gaussian_kernel(9, 1.5)
+    y = synth.blur_measurement(img, k, 0.0, seed=0)
+    q = y * 255.0
+    assert np.allclose(q, np.round(q), atol=1e-3)      # uint8-valued: the reference blurs in uint8 (main_ddpir.py:99)
+
+
+def test_masks():
+    m = synth.random_mask(2, 64, 0.5, seed=1)
+    assert m.shape == (2, 3, 64, 64) and set(np.unique(m.numpy())) == {0.0, 1.0}
+    assert int((m[0, 0] == 0).sum()) == 64 * 64 // 2 and torch.equal(m[:, 0], m[:, 2])
+    b = synth.box_mask(2, 256, 128, seed=2)
+    assert int((b[0, 0] == 0).sum()) == 128 * 128
