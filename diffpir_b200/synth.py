@@ -47,13 +47,13 @@ def synthetic_images(batch, size=256, seed=1234):
     return x.permute(0, 2, 3, 1).contiguous().numpy()      # (B,H,W,3) uint8
 
 
-def gaussian_kernel(size=61, std=3.0):
+def gaussian_kernel(size=61, std=3.0, dtype=np.float32):
     """Same construction as Blurkernel.weights_init, utils/utils_deblur.py:658-664 (scipy gaussian_filter
     of a centred delta)."""
     import scipy.ndimage
     n = np.zeros((size, size))
     n[size // 2, size // 2] = 1
-    return scipy.ndimage.gaussian_filter(n, sigma=std).astype(np.float32)
+    return scipy.ndimage.gaussian_filter(n, sigma=std).astype(dtype)
 
 
 def motion_kernel(size=61, intensity=0.5, seed=0):

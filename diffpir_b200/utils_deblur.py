@@ -41,7 +41,8 @@ class _BlurBase:
 class GaussialBlurOperator(_BlurBase):
     def __init__(self, kernel_size, intensity, device):
         super().__init__(kernel_size, device)
-        self.kernel = torch.from_numpy(synth.gaussian_kernel(kernel_size, intensity).astype(np.float64)).type(torch.float32)
+        # float64, as Blurkernel.weights_init / get_kernel return it (the drivers cast: main_ddpir_deblur.py:168)
+        self.kernel = torch.from_numpy(synth.gaussian_kernel(kernel_size, intensity, dtype=np.float64))
 
 
 GaussianBlurOperator = GaussialBlurOperator

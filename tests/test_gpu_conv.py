@@ -5,7 +5,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from tests.util import rel_l2
+from dpir_testutil import rel_l2
 
 pytestmark = pytest.mark.gpu
 

@@ -5,7 +5,7 @@ import torch
 
 from diffpir_b200 import synth
 from oracle import diffpir_oracle as orc
-from tests.util import make_model, psnr, rel_l2, small_config, weights
+from dpir_testutil import make_model, psnr, rel_l2, small_config, weights
 
 pytestmark = pytest.mark.gpu
 

@@ -4,7 +4,7 @@ import pytest
 import torch
 
 from oracle import diffpir_oracle as orc
-from tests.util import rel_l2
+from dpir_testutil import rel_l2
 
 pytestmark = pytest.mark.gpu
 
@@ -150,7 +150,7 @@ def test_blur_operator_forward_transpose_kernel():
     assert tuple(k.shape) == (1, 1, 21, 21) and abs(float(k.sum()) - 1) < 1e-3
     g = torch.Generator().manual_seed(9)
     x = torch.rand(2, 3, 48, 40, generator=g)
-    ref = F.conv2d(F.pad(x, (10, 10, 10, 10), mode="reflect"), k.expand(3, 1, 21, 21), groups=3)
+    ref = F.conv2d(F.pad(x, (10, 10, 10, 10), mode="reflect"), k.float().expand(3, 1, 21, 21), groups=3)
     out = op.forward(x.cuda())
     assert rel_l2(out, ref) < 1e-5
     assert op.transpose(x) is x

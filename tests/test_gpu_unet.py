@@ -4,7 +4,7 @@ import torch
 
 from oracle import diffpir_oracle as orc
 from oracle import unet_oracle
-from tests.util import make_model, rel_l2, small_config, weights
+from dpir_testutil import make_model, rel_l2, small_config, weights
 
 pytestmark = pytest.mark.gpu
 
