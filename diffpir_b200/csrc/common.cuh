@@ -20,6 +20,7 @@ extern thread_local int64_t g_launch_count;
     cudaError_t _e = (expr);                                                                     \
     if (_e != cudaSuccess) {                                                                     \
       dpir::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      (void)cudaGetLastError();                                                                  \
       return DPIR_E_CUDA;                                                                        \
     }                                                                                            \
   } while (0)
@@ -27,7 +28,7 @@ extern thread_local int64_t g_launch_count;
 #define DPIR_LAUNCH_CHECK()                                                                      \
   do {                                                                                           \
     dpir::g_launch_count++;                                                                      \
-    cudaError_t _e = cudaPeekAtLastError();                                                      \
+    cudaError_t _e = cudaGetLastError();                                                         \
     if (_e != cudaSuccess) {                                                                     \
       dpir::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
       return DPIR_E_CUDA;                                                                        \

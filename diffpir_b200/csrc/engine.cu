@@ -143,10 +143,19 @@ struct dpir_engine {
   size_t ws_bytes = 0;
   std::map<std::tuple<int, int, int>, std::unique_ptr<Plan>> plans;
   int graph_mode = 0;
+  // per-op CUDA-event profiler (bench / roofline accounting): events recorded on the launch stream around every op
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_events;      // pairs
+  std::vector<int> prof_op;                  // tape index per pair
+  Plan *prof_plan = nullptr;
   // staging buffers for graph mode (fixed addresses baked into the graph)
   float *g_x = nullptr, *g_out = nullptr;
   int64_t *g_t = nullptr;
   size_t g_cap = 0;
+  // graphs are captured and replayed on an engine-owned stream (the caller may be on the legacy default stream, which
+  // cannot be captured); ev_in / ev_out order it after / before the caller's stream
+  cudaStream_t gstream = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
 
   template <typename T> T *ap(size_t off) const { return reinterpret_cast<T *>(arena + off); }
 };
@@ -587,8 +596,16 @@ int get_plan(dpir_engine *e, int B, int H, int W, Plan **out) {
 }
 
 int run_plan(dpir_engine *e, Plan *plan, const float *x, const int64_t *t, float *out, int mode, cudaStream_t st) {
+  int op_index = -1;
   for (Op &op : plan->ops) {
     int rc = DPIR_OK;
+    ++op_index;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (e->profiling) {
+      DPIR_CUDA_CHECK(cudaEventCreate(&ev0));
+      DPIR_CUDA_CHECK(cudaEventCreate(&ev1));
+      DPIR_CUDA_CHECK(cudaEventRecord(ev0, st));
+    }
     switch (op.kind) {
       case OP_MEMSET:
         DPIR_CUDA_CHECK(cudaMemsetAsync(op.q0, 0, op.bytes, st));
@@ -630,6 +647,13 @@ int run_plan(dpir_engine *e, Plan *plan, const float *x, const int64_t *t, float
                               e->cfg.use_new_attention_order, st);
         break;
     }
+    if (e->profiling) {
+      DPIR_CUDA_CHECK(cudaEventRecord(ev1, st));
+      e->prof_events.push_back(ev0);
+      e->prof_events.push_back(ev1);
+      e->prof_op.push_back(op_index);
+      e->prof_plan = plan;
+    }
     if (rc) return rc;
   }
   return DPIR_OK;
@@ -658,36 +682,47 @@ int forward_impl(dpir_engine *e, const float *x, const int64_t *t, float *out, i
   Plan *plan = nullptr;
   int rc = get_plan(e, B, H, W, &plan);
   if (rc) return rc;
-  if (!e->graph_mode) return run_plan(e, plan, x, t, out, mode, st);
+  if (!e->graph_mode || e->profiling) return run_plan(e, plan, x, t, out, mode, st);
 
-  // graph mode: fixed staging buffers, one captured graph per (shape, output mode)
+  // graph mode: fixed staging buffers, one captured graph per (shape, output mode), replayed on the engine's stream
   rc = ensure_graph_staging(e, B, H, W);
   if (rc) return rc;
+  if (!e->gstream) {
+    DPIR_CUDA_CHECK(cudaStreamCreateWithFlags(&e->gstream, cudaStreamNonBlocking));
+    DPIR_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming));
+    DPIR_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming));
+  }
+  cudaStream_t gs = e->gstream;
   size_t xin = (size_t)B * 3 * H * W * 4;
   size_t xout = (size_t)B * (mode == EPI_X0 ? 3 : e->cfg.out_channels) * H * W * 4;
   cudaGraphExec_t &gexec = mode == EPI_X0 ? plan->graph_x0 : plan->graph_nchw;
-  DPIR_CUDA_CHECK(cudaMemcpyAsync(e->g_x, x, xin, cudaMemcpyDeviceToDevice, st));
-  DPIR_CUDA_CHECK(cudaMemcpyAsync(e->g_t, t, (size_t)B * 8, cudaMemcpyDeviceToDevice, st));
+  DPIR_CUDA_CHECK(cudaEventRecord(e->ev_in, st));
+  DPIR_CUDA_CHECK(cudaStreamWaitEvent(gs, e->ev_in, 0));
+  DPIR_CUDA_CHECK(cudaMemcpyAsync(e->g_x, x, xin, cudaMemcpyDeviceToDevice, gs));
+  DPIR_CUDA_CHECK(cudaMemcpyAsync(e->g_t, t, (size_t)B * 8, cudaMemcpyDeviceToDevice, gs));
   if (!gexec) {
     // warm-up run outside capture (sets function attributes, validates the tape), then capture
-    rc = run_plan(e, plan, e->g_x, e->g_t, e->g_out, mode, st);
+    rc = run_plan(e, plan, e->g_x, e->g_t, e->g_out, mode, gs);
     if (rc) return rc;
-    DPIR_CUDA_CHECK(cudaStreamSynchronize(st));
-    cudaGraph_t graph;
-    DPIR_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    DPIR_CUDA_CHECK(cudaStreamSynchronize(gs));
+    cudaGraph_t graph = nullptr;
+    DPIR_CUDA_CHECK(cudaStreamBeginCapture(gs, cudaStreamCaptureModeRelaxed));
     int64_t before = g_launch_count;
-    rc = run_plan(e, plan, e->g_x, e->g_t, e->g_out, mode, st);
+    rc = run_plan(e, plan, e->g_x, e->g_t, e->g_out, mode, gs);
     g_launch_count = before;
-    cudaError_t ce = cudaStreamEndCapture(st, &graph);
-    if (rc) return rc;
-    if (ce != cudaSuccess) { set_error("graph capture failed: %s", cudaGetErrorString(ce)); return DPIR_E_CUDA; }
-    DPIR_CUDA_CHECK(cudaGraphInstantiate(&gexec, graph, 0));
+    cudaError_t ce = cudaStreamEndCapture(gs, &graph);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (ce != cudaSuccess) { set_error("graph capture failed: %s", cudaGetErrorString(ce)); cudaGetLastError(); return DPIR_E_CUDA; }
+    cudaError_t ie = cudaGraphInstantiate(&gexec, graph, 0);
     cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) { gexec = nullptr; set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(ie)); cudaGetLastError(); return DPIR_E_CUDA; }
   }
-  DPIR_CUDA_CHECK(cudaGraphLaunch(gexec, st));
+  DPIR_CUDA_CHECK(cudaGraphLaunch(gexec, gs));
   // count the kernels the graph replays (same tape)
   for (Op &op : plan->ops) g_launch_count += (op.kind == OP_MEMSET ? 0 : (op.kind == OP_TIME_EMBED ? 2 : 1));
-  DPIR_CUDA_CHECK(cudaMemcpyAsync(out, e->g_out, xout, cudaMemcpyDeviceToDevice, st));
+  DPIR_CUDA_CHECK(cudaMemcpyAsync(out, e->g_out, xout, cudaMemcpyDeviceToDevice, gs));
+  DPIR_CUDA_CHECK(cudaEventRecord(e->ev_out, gs));
+  DPIR_CUDA_CHECK(cudaStreamWaitEvent(st, e->ev_out, 0));
   return DPIR_OK;
 }
 
@@ -728,6 +763,7 @@ int dpir_destroy(dpir_engine *e) {
   if (e->arena) cudaFree(e->arena);
   if (e->ws) cudaFree(e->ws);
   if (e->g_x) { cudaFree(e->g_x); cudaFree(e->g_out); cudaFree(e->g_t); }
+  if (e->gstream) { cudaStreamDestroy(e->gstream); cudaEventDestroy(e->ev_in); cudaEventDestroy(e->ev_out); }
   delete e;
   return DPIR_OK;
 }
@@ -829,6 +865,48 @@ int dpir_set_graph_mode(dpir_engine *e, int32_t enable) {
   DPIR_REQUIRE(e, "dpir_set_graph_mode: null engine");
   e->graph_mode = enable ? 1 : 0;
   return DPIR_OK;
+}
+
+int dpir_profile_begin(dpir_engine *e) {
+  DPIR_REQUIRE(e, "dpir_profile_begin: null engine");
+  for (auto ev : e->prof_events) cudaEventDestroy(ev);
+  e->prof_events.clear();
+  e->prof_op.clear();
+  e->prof_plan = nullptr;
+  e->profiling = true;
+  return DPIR_OK;
+}
+
+int dpir_profile_end(dpir_engine *e, int32_t *kind, int32_t *dims, float *ms, int32_t cap) {
+  DPIR_REQUIRE(e, "dpir_profile_end: null engine");
+  e->profiling = false;
+  DPIR_CUDA_CHECK(cudaDeviceSynchronize());
+  int n = (int)e->prof_op.size();
+  int nops = e->prof_plan ? (int)e->prof_plan->ops.size() : 0;
+  // accumulate over repeated forwards of the same plan: one row per tape op
+  std::vector<float> acc(nops, 0.f);
+  for (int i = 0; i < n; ++i) {
+    float t = 0.f;
+    cudaEventElapsedTime(&t, e->prof_events[2 * i], e->prof_events[2 * i + 1]);
+    if (e->prof_op[i] < nops) acc[e->prof_op[i]] += t;
+  }
+  for (auto ev : e->prof_events) cudaEventDestroy(ev);
+  e->prof_events.clear();
+  e->prof_op.clear();
+  int rows = nops < cap ? nops : cap;
+  for (int i = 0; i < rows && kind && dims && ms; ++i) {
+    const Op &op = e->prof_plan->ops[i];
+    kind[i] = (int)op.kind;
+    int H = op.H, W = op.W, Cin = op.Cin, Cout = op.Cout;
+    if (op.kind == OP_GN_APPLY) { H = op.gn.H; W = op.gn.W; Cin = op.gn.C1 + op.gn.C2; Cout = op.gn.resample; }
+    if (op.kind == OP_GN_STATS) { H = op.HW; W = 1; Cin = op.C1 + op.C2; Cout = 0; }
+    if (op.kind == OP_ATTN) { H = op.HW; W = 1; Cout = op.heads; }
+    if (op.kind == OP_CONV) Cout = op.Cout * 10 + op.ksize;   // packed: Cout*10 + ksize
+    dims[4 * i] = H; dims[4 * i + 1] = W; dims[4 * i + 2] = Cin; dims[4 * i + 3] = Cout;
+    ms[i] = acc[i];
+  }
+  e->prof_plan = nullptr;
+  return nops;
 }
 
 // ---- per-kernel entry points for tests / benchmarks

@@ -174,6 +174,26 @@ class UNetModel:
     def workspace_bytes(self):
         return int(self._lib.dpir_workspace_bytes(self._h))
 
+    # ---- per-op device timing (CUDA events inside the engine)
+    OP_KINDS = ("memset", "time_embed", "film", "conv_in", "gn_stats", "gn_apply", "conv", "attention")
+
+    def profile_begin(self):
+        _lib.check(self._lib.dpir_profile_begin(self._h), "dpir_profile_begin")
+
+    def profile_end(self):
+        """-> list of dicts (kind, dims, ms) per tape op, summed over the forwards since profile_begin."""
+        cap = 4096
+        kind = (ctypes.c_int32 * cap)()
+        dims = (ctypes.c_int32 * (4 * cap))()
+        ms = (ctypes.c_float * cap)()
+        n = self._lib.dpir_profile_end(self._h, kind, dims, ms, cap)
+        if n < 0:
+            _lib.check(n, "dpir_profile_end")
+        rows = []
+        for i in range(min(n, cap)):
+            rows.append(dict(kind=self.OP_KINDS[kind[i]], dims=tuple(dims[4 * i:4 * i + 4]), ms=float(ms[i])))
+        return rows
+
     def __del__(self):
         try:
             if getattr(self, "_h", None):

@@ -103,6 +103,15 @@ int64_t dpir_workspace_bytes(dpir_engine *e);
 /* 1 => replay the forward from a captured CUDA graph (per batch shape) instead of stream launches */
 int dpir_set_graph_mode(dpir_engine *e, int32_t enable);
 
+/* Per-op device timing of the forward tape with CUDA events on the launch stream (used by bench.py for the roofline
+ * accounting).  Between begin and end every forward runs un-graphed with an event pair around each op; `end`
+ * synchronises, sums the elapsed time per tape op over all forwards since `begin` and fills up to `cap` rows:
+ * kind[i] (0 memset, 1 time-embed, 2 FiLM linears, 3 stem conv, 4 GN stats, 5 GN apply, 6 conv, 7 attention),
+ * dims[4i..] = (H, W, Cin, Cout*10+ksize) for convs, (H, W, C, resample) for GN apply, (HW, 1, C, 0) for GN stats,
+ * (T, 1, C, heads) for attention; ms[i] = summed milliseconds.  Returns the number of tape ops. */
+int dpir_profile_begin(dpir_engine *e);
+int dpir_profile_end(dpir_engine *e, int32_t *kind, int32_t *dims, float *ms, int32_t cap);
+
 /* ------------------------------------------------------------------------------------------------
  * FFT-domain data-fidelity solver.  Replaces utils/utils_sisr.py:
  *   p2o :22-41, upsample :44-52, pre_calculate :78-95, splits :9-19, data_solution :65-75.

@@ -68,7 +68,7 @@ def test_conv_tc_matches_torch(B, H, W, Cin, Cout, k, residual):
     torch.cuda.synchronize()
     got = out.permute(0, 3, 1, 2)
     assert not torch.isnan(got).any()
-    assert rel_l2(got, ref) < 2e-6
+    assert rel_l2(got, ref) < 1e-5      # fp32 accumulation order over K = 9*Cin
     # and against the true fp32 conv: error is fp16 operand rounding only
     full = F.conv2d(x.double(), w.double(), b.double(), padding=k // 2) + (r.double() if r is not None else 0)
     assert rel_l2(got, full) < 1.5e-3
