@@ -99,6 +99,18 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def host_cores():
+    """Usable host threads: scheduler affinity, capped by the cgroup CPU quota (os.cpu_count() over-reports in containers)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = max(1, min(n, int(float(q) / float(p))))
+    except Exception:
+        pass
+    return min(n, 32)      # the oracle's torch-CPU convs stop scaling (and thrash) far below the box's thread count
+
+
 def make_inputs(B, seed):
     """Per-rank synthetic measurement batch (host tensors): y in [0,1] (B,3,256,256), k (B,1,27,27) zero-padded Levin-size PSFs."""
     imgs = synth.synthetic_images(B, SIZE, seed=1234 + seed)
@@ -124,7 +136,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     torch.set_num_threads(cores)
     cfg = arch.ffhq_config()
     sd = synth.synthetic_state_dict(cfg, 0)
@@ -182,7 +194,7 @@ def cpu_baseline_sample():
     """~10-30 s of the oracle's CPU evaluation of the same step, rank 0 / N=1 only."""
     from oracle import diffpir_oracle as orc
     from oracle import unet_oracle
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     torch.set_num_threads(cores)
     cfg = arch.ffhq_config()
     sd = synth.synthetic_state_dict(cfg, 0)
