@@ -230,38 +230,94 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(const __grid_constant__ 
     const bool valid = (n < g.B) && (yh < g.H) && (xw < g.W);
     const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16);
     if (BN >= 32) {
+      const bool warp_img_ok = n < g.B;       // the 32 rows of a warp lie in one image (TW*TH >= 32)
 #pragma unroll 1
       for (int c = 0; c < BN; c += 32) {
         uint32_t r[32];
         tmem_ld32(tbase + (uint32_t)c, r);
         tmem_ld_wait();
-        if (valid) {
-          const int co = co0 + c;
-          if (epi.mode == EPI_NHWC) {
+        const int co = co0 + c;
+        if (epi.mode == EPI_NHWC) {
+          float qs[8], qq[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { qs[j] = 0.f; qq[j] = 0.f; }
+          if (valid) {
             const int64_t pix = ((int64_t)n * g.H + yh) * g.W + xw;
-            float *o = epi.out + pix * g.Cout + co;
             const float *rs = epi.residual ? epi.residual + pix * g.Cout + co : nullptr;
+            float v[32];
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               if (co + j < g.Cout) {
                 float4 b4 = __ldg(reinterpret_cast<const float4 *>(epi.bias + co + j));
-                float4 v = make_float4(__uint_as_float(r[j]) + b4.x, __uint_as_float(r[j + 1]) + b4.y,
-                                       __uint_as_float(r[j + 2]) + b4.z, __uint_as_float(r[j + 3]) + b4.w);
+                v[j] = __uint_as_float(r[j]) + b4.x; v[j + 1] = __uint_as_float(r[j + 1]) + b4.y;
+                v[j + 2] = __uint_as_float(r[j + 2]) + b4.z; v[j + 3] = __uint_as_float(r[j + 3]) + b4.w;
                 if (rs) {
                   float4 rv = *reinterpret_cast<const float4 *>(rs + j);
-                  v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
+                  v[j] += rv.x; v[j + 1] += rv.y; v[j + 2] += rv.z; v[j + 3] += rv.w;
                 }
-                *reinterpret_cast<float4 *>(o + j) = v;
+                qs[j >> 2] = (v[j] + v[j + 1]) + (v[j + 2] + v[j + 3]);
+                qq[j >> 2] = (v[j] * v[j] + v[j + 1] * v[j + 1]) + (v[j + 2] * v[j + 2] + v[j + 3] * v[j + 3]);
+              } else {
+                v[j] = v[j + 1] = v[j + 2] = v[j + 3] = 0.f;
               }
             }
-          } else {
-            float acc[32];
+            if (epi.out_half) {
+              __half *o = reinterpret_cast<__half *>(epi.out) + pix * g.Cout + co;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(r[j]);
-            int ncols = g.Cout - co;
-            if (ncols > 32) ncols = 32;
-            if (ncols > 0) conv_epilogue_store(epi, n, yh, xw, g.H, g.W, g.Cout, co, acc, ncols);
+              for (int j = 0; j < 32; j += 8) {
+                if (co + j < g.Cout) {
+                  __half2 h0 = __floats2half2_rn(v[j], v[j + 1]), h1 = __floats2half2_rn(v[j + 2], v[j + 3]);
+                  __half2 h2 = __floats2half2_rn(v[j + 4], v[j + 5]), h3 = __floats2half2_rn(v[j + 6], v[j + 7]);
+                  uint4 u;
+                  u.x = *reinterpret_cast<uint32_t *>(&h0); u.y = *reinterpret_cast<uint32_t *>(&h1);
+                  u.z = *reinterpret_cast<uint32_t *>(&h2); u.w = *reinterpret_cast<uint32_t *>(&h3);
+                  *reinterpret_cast<uint4 *>(o + j) = u;
+                }
+              }
+            } else {
+              float *o = epi.out + pix * g.Cout + co;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                if (co + j < g.Cout) *reinterpret_cast<float4 *>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
           }
+          if (epi.qstats) {
+            // per-quad (4-channel) sums over the 32 pixels of this warp: reduce-scatter butterfly (8 -> 4 -> 2 -> 1 values
+            // per lane over xor 16/8/4, then plain xor 2/1), 18 shuffles per 32-column chunk; fp64 atomics per quad.
+            float a4[4], b4[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              float s_send = (lane & 16) ? qs[i] : qs[i + 4], s_keep = (lane & 16) ? qs[i + 4] : qs[i];
+              float q_send = (lane & 16) ? qq[i] : qq[i + 4], q_keep = (lane & 16) ? qq[i + 4] : qq[i];
+              a4[i] = s_keep + __shfl_xor_sync(0xffffffffu, s_send, 16);
+              b4[i] = q_keep + __shfl_xor_sync(0xffffffffu, q_send, 16);
+            }
+            float a2[2], b2[2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              float s_send = (lane & 8) ? a4[i] : a4[i + 2], s_keep = (lane & 8) ? a4[i + 2] : a4[i];
+              float q_send = (lane & 8) ? b4[i] : b4[i + 2], q_keep = (lane & 8) ? b4[i + 2] : b4[i];
+              a2[i] = s_keep + __shfl_xor_sync(0xffffffffu, s_send, 8);
+              b2[i] = q_keep + __shfl_xor_sync(0xffffffffu, q_send, 8);
+            }
+            float s1 = ((lane & 4) ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, (lane & 4) ? a2[0] : a2[1], 4);
+            float q1 = ((lane & 4) ? b2[1] : b2[0]) + __shfl_xor_sync(0xffffffffu, (lane & 4) ? b2[0] : b2[1], 4);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, 2); q1 += __shfl_xor_sync(0xffffffffu, q1, 2);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, 1); q1 += __shfl_xor_sync(0xffffffffu, q1, 1);
+            const int quad = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+            if ((lane & 3) == 0 && warp_img_ok && co + quad * 4 < g.Cout) {
+              double *qp = epi.qstats + ((int64_t)n * (g.Cout >> 2) + (co >> 2) + quad) * 2;
+              atomicAdd(qp, (double)s1);
+              atomicAdd(qp + 1, (double)q1);
+            }
+          }
+        } else if (valid) {
+          float acc[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(r[j]);
+          int ncols = g.Cout - co;
+          if (ncols > 32) ncols = 32;
+          if (ncols > 0) conv_epilogue_store(epi, n, yh, xw, g.H, g.W, g.Cout, co, acc, ncols);
         }
       }
     } else {

@@ -51,6 +51,8 @@ struct Buf {   // workspace tensor
   bool half = false;
   int refs = 0;
   int id = -1;
+  size_t stats_off = 0;   // quad statistics slot (workspace offset), valid when has_stats
+  bool has_stats = false;
 };
 
 enum OpKind { OP_MEMSET, OP_TIME_EMBED, OP_FILM, OP_CONV_IN, OP_GN_STATS, OP_GN_APPLY, OP_CONV, OP_ATTN };
@@ -352,13 +354,22 @@ struct PlanBuilder {
   int B, H, W;
   int err = DPIR_OK;
 
-  int new_buf(int B_, int H_, int W_, int C_, bool half) {
+  size_t stats_cur = 0, stats_bytes = 0;
+
+  int new_buf(int B_, int H_, int W_, int C_, bool half, bool want_stats = false) {
     Buf b;
     b.B = B_; b.H = H_; b.W = W_; b.C = C_; b.half = half;
     b.bytes = (size_t)B_ * H_ * W_ * C_ * (half ? 2 : 4);
     b.off = pool.alloc(b.bytes);
     b.refs = 1;
     b.id = (int)bufs.size();
+    if (want_stats) {
+      size_t need = (size_t)B_ * (C_ / 4) * 2 * sizeof(double);
+      if (stats_cur + need > stats_bytes) { set_error("internal: statistics arena overflow"); err = DPIR_E_STATE; }
+      b.stats_off = stats_off + stats_cur;
+      b.has_stats = true;
+      stats_cur += need;
+    }
     bufs.push_back(b);
     return b.id;
   }
@@ -370,7 +381,20 @@ struct PlanBuilder {
   // pointers are stored as workspace offsets (+1 so that 0 stays "null") and rebased after the workspace is allocated
   template <typename T> T *wp(size_t off) { return reinterpret_cast<T *>(off + 1); }
   template <typename T> T *bp(int id) { return wp<T>(bufs[id].off); }
-  double *stats_ptr(int norm_idx) { return wp<double>(stats_off + (size_t)norm_idx * B * 64 * sizeof(double)); }
+  double *sp(int id) {
+    if (!bufs[id].has_stats) { set_error("internal: tensor %d has no statistics", id); err = DPIR_E_STATE; return nullptr; }
+    return wp<double>(bufs[id].stats_off);
+  }
+
+  // separate statistics pass over an fp32 tensor (stem output; every conv output in fp32 mode)
+  void emit_stats(int id) {
+    const Buf &t = bufs[id];
+    Op st;
+    st.kind = OP_GN_STATS;
+    st.p0 = bp<float>(id); st.C1 = t.C;
+    st.q0 = sp(id); st.B = B; st.HW = t.H * t.W;
+    plan->ops.push_back(st);
+  }
 
   int gn(int src1, int src2, const NormW &nw, int film_row /*-1: none*/, int silu, int resample, bool want_raw32,
          bool want_rawact, int *act_id, int *raw32_id, int *rawact_id) {
@@ -379,22 +403,18 @@ struct PlanBuilder {
     int Hin = s1.H, Win = s1.W;
     int Ho = resample == RS_DOWN ? Hin / 2 : (resample == RS_UP ? Hin * 2 : Hin);
     int Wo = resample == RS_DOWN ? Win / 2 : (resample == RS_UP ? Win * 2 : Win);
-    int ni = n_norms++;
-    Op st;
-    st.kind = OP_GN_STATS;
-    st.p0 = bp<float>(src1); st.C1 = C1;
-    st.p1 = src2 >= 0 ? bp<float>(src2) : nullptr; st.C2 = C2;
-    st.q0 = stats_ptr(ni); st.B = B; st.HW = Hin * Win;
-    plan->ops.push_back(st);
+    n_norms++;
     *act_id = new_buf(B, Ho, Wo, C, e->half);
     *raw32_id = want_raw32 ? new_buf(B, Ho, Wo, C, false) : -1;
     *rawact_id = want_rawact ? new_buf(B, Ho, Wo, C, e->half) : -1;
     Op ap;
     ap.kind = OP_GN_APPLY;
     GnApplyArgs &a = ap.gn;
-    a.src1 = bp<float>(src1); a.C1 = C1;
-    a.src2 = src2 >= 0 ? bp<float>(src2) : nullptr; a.C2 = C2;
-    a.stats = stats_ptr(ni);
+    a.src1 = bp<void>(src1); a.C1 = C1;
+    a.src2 = src2 >= 0 ? bp<void>(src2) : nullptr; a.C2 = C2;
+    a.src_half = bufs[src1].half ? 1 : 0;
+    a.q1 = sp(src1);
+    a.q2 = src2 >= 0 ? sp(src2) : nullptr;
     a.gamma = e->ap<float>(nw.g_off); a.beta = e->ap<float>(nw.b_off);
     a.film = film_row >= 0 ? wp<float>(film_off + (size_t)film_row * 4) : nullptr;
     a.film_stride = e->film_rows;
@@ -406,10 +426,12 @@ struct PlanBuilder {
     return DPIR_OK;
   }
 
-  // conv on a workspace activation -> new fp32 NHWC buffer (residual optional)
-  int conv(int act, const ConvW &cw, int residual, int *out_id) {
+  // conv on a workspace activation -> new NHWC buffer (fp32, or fp16 when out_half in tensor-core mode); residual
+  // optional; want_stats attaches quad statistics to the output (fused in the tcgen05 epilogue, separate pass in fp32 mode)
+  int conv(int act, const ConvW &cw, int residual, int *out_id, bool want_stats = false, bool out_half = false) {
     const Buf &a = bufs[act];
-    *out_id = new_buf(B, a.H, a.W, cw.cout, false);
+    out_half = out_half && e->half;
+    *out_id = new_buf(B, a.H, a.W, cw.cout, out_half, want_stats);
     Op op;
     op.kind = OP_CONV;
     op.p0 = bp<void>(act);
@@ -419,7 +441,10 @@ struct PlanBuilder {
     op.epi.bias = e->ap<float>(cw.b_off);
     op.epi.residual = residual >= 0 ? bp<float>(residual) : nullptr;
     op.epi.out = bp<float>(*out_id);
+    op.epi.out_half = out_half ? 1 : 0;
+    op.epi.qstats = (want_stats && e->half) ? sp(*out_id) : nullptr;
     plan->ops.push_back(op);
+    if (want_stats && !e->half) emit_stats(*out_id);
     return DPIR_OK;
   }
 
@@ -438,7 +463,7 @@ struct PlanBuilder {
     }
     if (concat) release(skip);
     int h1;
-    conv(a1, rw.c1, -1, &h1);
+    conv(a1, rw.c1, -1, &h1, /*want_stats=*/true, /*out_half=*/true);   // h1 feeds only GroupNorm -> conv2
     release(a1);
     int a2, d0, d1;
     gn(h1, -1, rw.n2, rw.film_row, 1, RS_NONE, false, false, &a2, &d0, &d1);
@@ -447,7 +472,7 @@ struct PlanBuilder {
       conv(xraw, rw.skip, -1, &residual);
       release(xraw);
     }
-    conv(a2, rw.c2, residual, out);
+    conv(a2, rw.c2, residual, out, /*want_stats=*/true);
     release(a2);
     release(residual);
     return DPIR_OK;
@@ -468,7 +493,7 @@ struct PlanBuilder {
     op.B = B; op.HW = xb.H * xb.W; op.Cin = l.cin; op.heads = l.heads; op.out_half = e->half;
     plan->ops.push_back(op);
     release(qkv);
-    conv(a, aw.proj, x, out);
+    conv(a, aw.proj, x, out, /*want_stats=*/true);
     release(a);
     release(x);
     return DPIR_OK;
@@ -493,10 +518,14 @@ struct PlanBuilder {
     emb_off = pool.alloc((size_t)B * ted * 4);
     film_off = pool.alloc((size_t)B * e->film_rows * 4);
     int total_norms = 1;
+    size_t total_c = e->ch0;
     for (auto *grp : {&e->inputs, &e->middle, &e->outputs})
       for (auto &blk : *grp)
-        for (auto &l : blk) total_norms += l.kind == 1 ? 2 : (l.kind == 2 ? 1 : 0);
-    size_t stats_bytes = (size_t)total_norms * B * 64 * sizeof(double);
+        for (auto &l : blk) {
+          total_norms += l.kind == 1 ? 2 : (l.kind == 2 ? 1 : 0);
+          total_c += l.kind == 1 ? 2 * (size_t)l.cout : (l.kind == 2 ? (size_t)l.cin : 0);
+        }
+    stats_bytes = (size_t)B * (total_c / 4) * 2 * sizeof(double);
     stats_off = pool.alloc(stats_bytes);
 
     Op ms; ms.kind = OP_MEMSET; ms.q0 = wp<void>(stats_off); ms.bytes = stats_bytes;
@@ -507,9 +536,10 @@ struct PlanBuilder {
     plan->ops.push_back(fl);
 
     std::vector<int> hs;
-    int h = new_buf(B, H, W, e->ch0, false);
+    int h = new_buf(B, H, W, e->ch0, false, /*want_stats=*/true);
     Op ci; ci.kind = OP_CONV_IN; ci.bind_x = true; ci.q0 = bp<void>(h); ci.B = B; ci.H = H; ci.W = W;
     plan->ops.push_back(ci);
+    emit_stats(h);
     retain(h); hs.push_back(h);
     for (size_t i = 1; i < e->inputs.size(); ++i) {
       int o;
@@ -575,10 +605,11 @@ int get_plan(dpir_engine *e, int B, int H, int W, Plan **out) {
   for (Op &op : plan->ops) {
     rebase_c(op.p0, base); rebase_c(op.p1, base); rebase_c(op.p2, base); rebase(op.q0, base);
     if (op.kind == OP_GN_APPLY) {
-      rebase(op.gn.src1, base); rebase(op.gn.src2, base); rebase(op.gn.stats, base); rebase(op.gn.film, base);
+      rebase_c(op.gn.src1, base); rebase_c(op.gn.src2, base); rebase(op.gn.q1, base); rebase(op.gn.q2, base);
+      rebase(op.gn.film, base);
       rebase(op.gn.act, base); rebase(op.gn.raw32, base); rebase(op.gn.rawact, base);
     }
-    if (op.kind == OP_CONV) { rebase(op.epi.residual, base); rebase(op.epi.out, base); }
+    if (op.kind == OP_CONV) { rebase(op.epi.residual, base); rebase(op.epi.out, base); rebase(op.epi.qstats, base); }
   }
   if (e->half) {
     for (Op &op : plan->ops) {
@@ -624,7 +655,7 @@ int run_plan(dpir_engine *e, Plan *plan, const float *x, const int64_t *t, float
                             e->stem.cin, e->stem.cout, st);
         break;
       case OP_GN_STATS:
-        rc = launch_gn_stats((const float *)op.p0, op.C1, (const float *)op.p1, op.C2, (double *)op.q0, op.B, op.HW, st);
+        rc = launch_gn_stats((const float *)op.p0, op.C1, (double *)op.q0, op.B, op.HW, st);
         break;
       case OP_GN_APPLY:
         rc = launch_gn_apply(op.gn, st);

@@ -14,93 +14,124 @@
 namespace dpir {
 
 // =========================================================================================== input stem
-// input_blocks.0.0: Conv2d(3, C, 3, padding=1) reading the caller's NCHW image and writing NHWC fp32.
-// w packed [tap*Cin + ci][Cout].  One thread = one pixel x 4 output channels.
-__global__ void k_conv_in(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ bias,
-                          float *__restrict__ out, int B, int H, int W, int Cin, int Cout) {
-  extern __shared__ float sw[];  // [9*Cin][Cout]
-  int K = 9 * Cin;
-  for (int i = threadIdx.x; i < K * Cout; i += blockDim.x) sw[i] = w[i];
-  __syncthreads();
+// input_blocks.0.0: Conv2d(Cin<=4, C, 3, padding=1) reading the caller's NCHW image and writing NHWC fp32.
+// w packed [tap*Cin + ci][Cout].  One warp-lane = 4 output channels whose 9*CIN float4 weights stay in registers; every
+// iteration a thread produces a strip of 4 horizontally adjacent pixels from one 3x6 input patch per channel
+// (input loads are warp-broadcasts, output stores are 512 B contiguous per pixel).
+template <int CIN>
+__global__ void __launch_bounds__(256) k_conv_in(const float *__restrict__ x, const float *__restrict__ w,
+                                                 const float *__restrict__ bias, float *__restrict__ out, int B, int H, int W,
+                                                 int Cout) {
   int C4 = Cout / 4;
   int ppb = blockDim.x / C4;
   int lane_p = threadIdx.x / C4, c4 = threadIdx.x % C4;
   if (lane_p >= ppb) return;
-  int64_t npix = (int64_t)B * H * W;
+  float4 wr[9 * CIN];
+#pragma unroll
+  for (int i = 0; i < 9 * CIN; ++i) wr[i] = reinterpret_cast<const float4 *>(w + (int64_t)i * Cout)[c4];
   float4 bv = reinterpret_cast<const float4 *>(bias)[c4];
-  for (int64_t p = (int64_t)blockIdx.x * ppb + lane_p; p < npix; p += (int64_t)gridDim.x * ppb) {
-    int xw = (int)(p % W);
-    int yh = (int)((p / W) % H);
-    int n = (int)(p / ((int64_t)W * H));
-    float4 acc = bv;
-    for (int dy = 0; dy < 3; ++dy) {
-      int yy = yh + dy - 1;
-      if (yy < 0 || yy >= H) continue;
-      for (int dx = 0; dx < 3; ++dx) {
-        int xx = xw + dx - 1;
-        if (xx < 0 || xx >= W) continue;
-        for (int ci = 0; ci < Cin; ++ci) {
-          float v = __ldg(&x[(((int64_t)n * Cin + ci) * H + yy) * W + xx]);
-          float4 wv = reinterpret_cast<const float4 *>(sw + ((dy * 3 + dx) * Cin + ci) * Cout)[c4];
-          acc.x += v * wv.x; acc.y += v * wv.y; acc.z += v * wv.z; acc.w += v * wv.w;
+  int Ws = W / 4;
+  int64_t nstrips = (int64_t)B * H * Ws;
+  for (int64_t sidx = (int64_t)blockIdx.x * ppb + lane_p; sidx < nstrips; sidx += (int64_t)gridDim.x * ppb) {
+    int xs = (int)(sidx % Ws) * 4;
+    int yh = (int)((sidx / Ws) % H);
+    int n = (int)(sidx / ((int64_t)Ws * H));
+    float4 acc[4] = {bv, bv, bv, bv};
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci) {
+      const float *xp = x + ((int64_t)n * CIN + ci) * H * W;
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy) {
+        int yy = yh + dy - 1;
+        float r[6];
+        bool rowok = yy >= 0 && yy < H;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+          int xx = xs + j - 1;
+          r[j] = (rowok && xx >= 0 && xx < W) ? __ldg(xp + (int64_t)yy * W + xx) : 0.f;
+        }
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          float4 wv = wr[(dy * 3 + dx) * CIN + ci];
+#pragma unroll
+          for (int pxl = 0; pxl < 4; ++pxl) {
+            float v = r[pxl + dx];
+            acc[pxl].x += v * wv.x; acc[pxl].y += v * wv.y; acc[pxl].z += v * wv.z; acc[pxl].w += v * wv.w;
+          }
         }
       }
     }
-    reinterpret_cast<float4 *>(out + p * Cout)[c4] = acc;
+    int64_t p = ((int64_t)n * H + yh) * W + xs;
+#pragma unroll
+    for (int pxl = 0; pxl < 4; ++pxl) reinterpret_cast<float4 *>(out + (p + pxl) * Cout)[c4] = acc[pxl];
   }
 }
 
 int launch_conv_in(const float *x, const float *w, const float *bias, float *out, int B, int H, int W, int Cin, int Cout,
                    cudaStream_t st) {
   DPIR_REQUIRE(Cout % 4 == 0 && Cout / 4 <= 256, "conv_in: Cout must be a multiple of 4 and <= 1024");
+  DPIR_REQUIRE(W % 4 == 0, "conv_in: W must be a multiple of 4");
+  DPIR_REQUIRE(Cin >= 1 && Cin <= 4, "conv_in: Cin must be 1..4");
   int C4 = Cout / 4;
-  int threads = C4 * (256 / C4 > 0 ? 256 / C4 : 1);
-  size_t smem = (size_t)9 * Cin * Cout * sizeof(float);
-  DPIR_REQUIRE(smem <= 200 * 1024, "conv_in: weights do not fit in shared memory");
-  static size_t attr_smem = 48 * 1024;
-  if (smem > attr_smem) {
-    DPIR_CUDA_CHECK(cudaFuncSetAttribute(k_conv_in, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_smem = smem;
+  int ppb = 256 / C4 > 0 ? 256 / C4 : 1;
+  int threads = C4 * ppb;
+  int64_t nstrips = (int64_t)B * H * (W / 4);
+  int64_t want = (nstrips + ppb - 1) / ppb;
+  int grid = (int)(want < 1 ? 1 : (want > 148 * 16 ? 148 * 16 : want));
+  switch (Cin) {
+    case 1: k_conv_in<1><<<grid, threads, 0, st>>>(x, w, bias, out, B, H, W, Cout); break;
+    case 2: k_conv_in<2><<<grid, threads, 0, st>>>(x, w, bias, out, B, H, W, Cout); break;
+    case 3: k_conv_in<3><<<grid, threads, 0, st>>>(x, w, bias, out, B, H, W, Cout); break;
+    default: k_conv_in<4><<<grid, threads, 0, st>>>(x, w, bias, out, B, H, W, Cout); break;
   }
-  int64_t npix = (int64_t)B * H * W;
-  int ppb = threads / C4;
-  int64_t want = (npix + ppb * 8 - 1) / (ppb * 8);
-  int grid = (int)(want < 1 ? 1 : (want > 148 * 8 ? 148 * 8 : want));
-  k_conv_in<<<grid, threads, smem, st>>>(x, w, bias, out, B, H, W, Cin, Cout);
   DPIR_LAUNCH_CHECK();
   return DPIR_OK;
 }
 
 // =========================================================================================== GroupNorm statistics
-// sums over (C/32 channels x HW) per (sample, group), accumulated in fp64: stats[b][g] = (sum, sumsq).
-// Thread = one float4 channel lane (a float4 never straddles a group because C % 128 == 0), loops over pixels.
-constexpr int GN_PIX_PER_BLOCK = 256;
+// Statistics are attached to the TENSOR, not to the norm: qstats[b][c/4] = (sum, sumsq) over all pixels of channel quad
+// c/4 (fp64).  They are produced where the tensor is produced - the tcgen05 conv epilogue (conv_tc.cu) or this kernel
+// (stem output, fp32 mode) - and any later GroupNorm over the tensor, alone or inside a channel concat whose groups
+// straddle the two sources (e.g. 768 = 512 + 256 -> 24 channels per group), folds the quads of its 32 groups on the fly.
+constexpr int GN_PIX_PER_BLOCK = 512;
 
-__global__ void k_gn_stats(const float *__restrict__ s1, int C1, const float *__restrict__ s2, int C2,
-                           double *__restrict__ stats, int HW) {
-  __shared__ double sh[64];
-  int C = C1 + C2, C4 = C / 4;
+__global__ void k_gn_stats(const float *__restrict__ src, int C, double *__restrict__ qstats, int HW) {
+  int C4 = C / 4;
   int ppb = blockDim.x / C4;
   int lane_p = threadIdx.x / C4, c4 = threadIdx.x % C4;
   int b = blockIdx.y;
-  if (threadIdx.x < 64) sh[threadIdx.x] = 0.0;
-  __syncthreads();
   int p0 = blockIdx.x * GN_PIX_PER_BLOCK;
   int p1 = min(p0 + GN_PIX_PER_BLOCK, HW);
-  const float *src; int Cs, cc;
-  if (c4 * 4 < C1) { src = s1 + (int64_t)b * HW * C1; Cs = C1; cc = c4 * 4; }
-  else             { src = s2 + (int64_t)b * HW * C2; Cs = C2; cc = c4 * 4 - C1; }
+  const float *base = src + (int64_t)b * HW * C + c4 * 4;
   float s = 0.f, ss = 0.f;
-  for (int p = p0 + lane_p; p < p1; p += ppb) {
-    float4 v = *reinterpret_cast<const float4 *>(src + (int64_t)p * Cs + cc);
+  int p = p0 + lane_p;
+  for (; p + 3 * ppb < p1; p += 4 * ppb) {
+    float4 v0 = *reinterpret_cast<const float4 *>(base + (int64_t)p * C);
+    float4 v1 = *reinterpret_cast<const float4 *>(base + (int64_t)(p + ppb) * C);
+    float4 v2 = *reinterpret_cast<const float4 *>(base + (int64_t)(p + 2 * ppb) * C);
+    float4 v3 = *reinterpret_cast<const float4 *>(base + (int64_t)(p + 3 * ppb) * C);
+    s += ((v0.x + v0.y) + (v0.z + v0.w)) + ((v1.x + v1.y) + (v1.z + v1.w)) + ((v2.x + v2.y) + (v2.z + v2.w)) +
+         ((v3.x + v3.y) + (v3.z + v3.w));
+    ss += ((v0.x * v0.x + v0.y * v0.y) + (v0.z * v0.z + v0.w * v0.w)) + ((v1.x * v1.x + v1.y * v1.y) + (v1.z * v1.z + v1.w * v1.w)) +
+          ((v2.x * v2.x + v2.y * v2.y) + (v2.z * v2.z + v2.w * v2.w)) + ((v3.x * v3.x + v3.y * v3.y) + (v3.z * v3.z + v3.w * v3.w));
+  }
+  for (; p < p1; p += ppb) {
+    float4 v = *reinterpret_cast<const float4 *>(base + (int64_t)p * C);
     s += (v.x + v.y) + (v.z + v.w);
     ss += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
   }
-  int g = c4 / (C4 / 32);
-  atomicAdd(&sh[2 * g], (double)s);
-  atomicAdd(&sh[2 * g + 1], (double)ss);
+  // combine the ppb pixel-lanes of a quad through shared memory, then one fp64 atomic pair per quad per block
+  extern __shared__ float red[];   // [ppb][C4][2]
+  red[(lane_p * C4 + c4) * 2] = s;
+  red[(lane_p * C4 + c4) * 2 + 1] = ss;
   __syncthreads();
-  if (threadIdx.x < 64) atomicAdd(&stats[(int64_t)b * 64 + threadIdx.x], sh[threadIdx.x]);
+  if (lane_p == 0) {
+    double ds = 0.0, dss = 0.0;
+    for (int l = 0; l < ppb; ++l) { ds += (double)red[(l * C4 + c4) * 2]; dss += (double)red[(l * C4 + c4) * 2 + 1]; }
+    double *q = qstats + ((int64_t)b * C4 + c4) * 2;
+    atomicAdd(q, ds);
+    atomicAdd(q + 1, dss);
+  }
 }
 
 static inline int gn_threads(int C) {
@@ -110,11 +141,11 @@ static inline int gn_threads(int C) {
   return C4 * ppb;
 }
 
-int launch_gn_stats(const float *s1, int C1, const float *s2, int C2, double *stats, int B, int HW, cudaStream_t st) {
-  int C = C1 + C2;
-  DPIR_REQUIRE(C % 128 == 0 && C1 % 4 == 0 && C <= 4096, "gn_stats: channels must be a multiple of 128 (got %d)", C);
+int launch_gn_stats(const float *src, int C, double *qstats, int B, int HW, cudaStream_t st) {
+  DPIR_REQUIRE(C % 4 == 0 && C <= 4096, "gn_stats: channels must be a multiple of 4 (got %d)", C);
   dim3 grid(cdiv(HW, GN_PIX_PER_BLOCK), B);
-  k_gn_stats<<<grid, gn_threads(C), 0, st>>>(s1, C1, s2, C2, stats, HW);
+  int threads = gn_threads(C);
+  k_gn_stats<<<grid, threads, (size_t)threads * 2 * sizeof(float), st>>>(src, C, qstats, HW);
   DPIR_LAUNCH_CHECK();
   return DPIR_OK;
 }
@@ -133,10 +164,22 @@ template <> struct Store4<__half> {
     *reinterpret_cast<uint2 *>(p) = u;
   }
 };
+template <typename T> struct Load4;
+template <> struct Load4<float> {
+  static __device__ __forceinline__ float4 ld(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+};
+template <> struct Load4<__half> {
+  static __device__ __forceinline__ float4 ld(const __half *p) {
+    uint2 u = *reinterpret_cast<const uint2 *>(p);
+    float2 a = __half22float2(*reinterpret_cast<__half2 *>(&u.x)), b = __half22float2(*reinterpret_cast<__half2 *>(&u.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+};
 
 struct GnDev {
-  const float *s1; int C1; const float *s2; int C2;
-  const double *stats; const float *gamma, *beta; const float *film; int film_stride;
+  const void *s1; int C1; const void *s2; int C2;
+  const double *q1, *q2;             // quad statistics of the two sources
+  const float *gamma, *beta; const float *film; int film_stride;
   int silu, H, W;
   float *raw32;
 };
@@ -159,19 +202,27 @@ __device__ __forceinline__ float4 gn_act(float4 v, float mean, float rstd, float
   return o;
 }
 
-constexpr int GN_APPLY_PIX = 64;  // work pixels per block
+constexpr int GN_APPLY_PIX = 128;  // work pixels per block
+constexpr int GN_UNROLL = 4;
 
 // MODE none: one work pixel = one pixel.  MODE down: work pixel = output pixel (reads 2x2 inputs, averages the
 // ACTIVATED values as unet.py:238-241 does: in_rest(x) then h_upd).  MODE up: work pixel = input pixel, written 2x2.
-template <typename T, int MODE>
+template <typename T, typename TI, int MODE>
 __global__ void k_gn_apply(GnDev a, T *__restrict__ act, T *__restrict__ rawact) {
   __shared__ float s_mean[32], s_rstd[32];
   int C = a.C1 + a.C2, C4 = C / 4;
   int b = blockIdx.y;
   int H = a.H, W = a.W, HW = H * W;
   if (threadIdx.x < 32) {
+    int qpg = C4 / 32, Q1 = a.C1 / 4;
+    double su = 0.0, sq = 0.0;
+    for (int j = 0; j < qpg; ++j) {
+      int q = threadIdx.x * qpg + j;
+      const double *src = q < Q1 ? a.q1 + ((int64_t)b * Q1 + q) * 2 : a.q2 + ((int64_t)b * (C4 - Q1) + (q - Q1)) * 2;
+      su += src[0];
+      sq += src[1];
+    }
     double n = (double)HW * (double)(C / 32);
-    double su = a.stats[(int64_t)b * 64 + 2 * threadIdx.x], sq = a.stats[(int64_t)b * 64 + 2 * threadIdx.x + 1];
     double mean = su / n;
     double var = sq / n - mean * mean;
     if (var < 0.0) var = 0.0;
@@ -192,48 +243,68 @@ __global__ void k_gn_apply(GnDev a, T *__restrict__ act, T *__restrict__ rawact)
     sc = reinterpret_cast<const float4 *>(f)[c4];
     sh = reinterpret_cast<const float4 *>(f + C)[c4];
   }
-  const float *src; int Cs, cc;
-  if (c4 * 4 < a.C1) { src = a.s1 + (int64_t)b * HW * a.C1; Cs = a.C1; cc = c4 * 4; }
-  else               { src = a.s2 + (int64_t)b * HW * a.C2; Cs = a.C2; cc = c4 * 4 - a.C1; }
+  const TI *src; int Cs, cc;
+  if (c4 * 4 < a.C1) { src = reinterpret_cast<const TI *>(a.s1) + (int64_t)b * HW * a.C1; Cs = a.C1; cc = c4 * 4; }
+  else               { src = reinterpret_cast<const TI *>(a.s2) + (int64_t)b * HW * a.C2; Cs = a.C2; cc = c4 * 4 - a.C1; }
   int Hw = (MODE == RS_DOWN) ? H / 2 : H, Ww = (MODE == RS_DOWN) ? W / 2 : W;   // work grid
   int Ho = (MODE == RS_UP) ? H * 2 : Hw, Wo = (MODE == RS_UP) ? W * 2 : Ww;     // output grid
   int nwork = Hw * Ww;
   int p0 = blockIdx.x * GN_APPLY_PIX;
   int p1 = min(p0 + GN_APPLY_PIX, nwork);
   int64_t obase = (int64_t)b * Ho * Wo;
-  for (int p = p0 + lane_p; p < p1; p += ppb) {
-    if (MODE == RS_NONE) {
-      float4 v = *reinterpret_cast<const float4 *>(src + (int64_t)p * Cs + cc);
-      float4 o = gn_act(v, mean, rstd, ga, be, has_film, sc, sh, a.silu);
-      Store4<T>::st(act + (obase + p) * C + c4 * 4, o);
-      if (a.raw32) *reinterpret_cast<float4 *>(a.raw32 + (obase + p) * C + c4 * 4) = v;
-      if (rawact) Store4<T>::st(rawact + (obase + p) * C + c4 * 4, v);
-    } else if (MODE == RS_DOWN) {
+  if (MODE == RS_NONE) {
+    int p = p0 + lane_p;
+    for (; p + (GN_UNROLL - 1) * ppb < p1; p += GN_UNROLL * ppb) {
+      float4 v[GN_UNROLL];
+#pragma unroll
+      for (int u = 0; u < GN_UNROLL; ++u) v[u] = Load4<TI>::ld(src + (int64_t)(p + u * ppb) * Cs + cc);
+#pragma unroll
+      for (int u = 0; u < GN_UNROLL; ++u) {
+        int64_t o = (obase + p + u * ppb) * C + c4 * 4;
+        Store4<T>::st(act + o, gn_act(v[u], mean, rstd, ga, be, has_film, sc, sh, a.silu));
+        if (a.raw32) *reinterpret_cast<float4 *>(a.raw32 + o) = v[u];
+        if (rawact) Store4<T>::st(rawact + o, v[u]);
+      }
+    }
+    for (; p < p1; p += ppb) {
+      float4 v = Load4<TI>::ld(src + (int64_t)p * Cs + cc);
+      int64_t o = (obase + p) * C + c4 * 4;
+      Store4<T>::st(act + o, gn_act(v, mean, rstd, ga, be, has_film, sc, sh, a.silu));
+      if (a.raw32) *reinterpret_cast<float4 *>(a.raw32 + o) = v;
+      if (rawact) Store4<T>::st(rawact + o, v);
+    }
+  } else if (MODE == RS_DOWN) {
+    for (int p = p0 + lane_p; p < p1; p += ppb) {
       int yo = p / Ww, xo = p % Ww;
+      float4 v[4];
+#pragma unroll
+      for (int d = 0; d < 4; ++d)
+        v[d] = Load4<TI>::ld(src + ((int64_t)(2 * yo + (d >> 1)) * W + 2 * xo + (d & 1)) * Cs + cc);
       float4 accA = make_float4(0, 0, 0, 0), accR = accA;
 #pragma unroll
       for (int d = 0; d < 4; ++d) {
-        int yi = 2 * yo + (d >> 1), xi = 2 * xo + (d & 1);
-        float4 v = *reinterpret_cast<const float4 *>(src + ((int64_t)yi * W + xi) * Cs + cc);
-        float4 o = gn_act(v, mean, rstd, ga, be, has_film, sc, sh, a.silu);
+        float4 o = gn_act(v[d], mean, rstd, ga, be, has_film, sc, sh, a.silu);
         accA.x += o.x; accA.y += o.y; accA.z += o.z; accA.w += o.w;
-        accR.x += v.x; accR.y += v.y; accR.z += v.z; accR.w += v.w;
+        accR.x += v[d].x; accR.y += v[d].y; accR.z += v[d].z; accR.w += v[d].w;
       }
       accA.x *= 0.25f; accA.y *= 0.25f; accA.z *= 0.25f; accA.w *= 0.25f;
       accR.x *= 0.25f; accR.y *= 0.25f; accR.z *= 0.25f; accR.w *= 0.25f;
-      Store4<T>::st(act + (obase + p) * C + c4 * 4, accA);
-      if (a.raw32) *reinterpret_cast<float4 *>(a.raw32 + (obase + p) * C + c4 * 4) = accR;
-      if (rawact) Store4<T>::st(rawact + (obase + p) * C + c4 * 4, accR);
-    } else {
+      int64_t o = (obase + p) * C + c4 * 4;
+      Store4<T>::st(act + o, accA);
+      if (a.raw32) *reinterpret_cast<float4 *>(a.raw32 + o) = accR;
+      if (rawact) Store4<T>::st(rawact + o, accR);
+    }
+  } else {
+    for (int p = p0 + lane_p; p < p1; p += ppb) {
       int yi = p / W, xi = p % W;
-      float4 v = *reinterpret_cast<const float4 *>(src + (int64_t)p * Cs + cc);
+      float4 v = Load4<TI>::ld(src + (int64_t)p * Cs + cc);
       float4 o = gn_act(v, mean, rstd, ga, be, has_film, sc, sh, a.silu);
 #pragma unroll
       for (int d = 0; d < 4; ++d) {
-        int64_t q = obase + (int64_t)(2 * yi + (d >> 1)) * Wo + 2 * xi + (d & 1);
-        Store4<T>::st(act + q * C + c4 * 4, o);
-        if (a.raw32) *reinterpret_cast<float4 *>(a.raw32 + q * C + c4 * 4) = v;
-        if (rawact) Store4<T>::st(rawact + q * C + c4 * 4, v);
+        int64_t q = (obase + (int64_t)(2 * yi + (d >> 1)) * Wo + 2 * xi + (d & 1)) * C + c4 * 4;
+        Store4<T>::st(act + q, o);
+        if (a.raw32) *reinterpret_cast<float4 *>(a.raw32 + q) = v;
+        if (rawact) Store4<T>::st(rawact + q, v);
       }
     }
   }
@@ -243,19 +314,24 @@ int launch_gn_apply(const GnApplyArgs &a, cudaStream_t st) {
   int C = a.C1 + a.C2;
   DPIR_REQUIRE(C % 128 == 0 && a.C1 % 4 == 0 && C <= 4096, "gn_apply: channels must be a multiple of 128 (got %d)", C);
   DPIR_REQUIRE(a.resample != RS_DOWN || (a.H % 2 == 0 && a.W % 2 == 0), "gn_apply: downsample needs even H, W");
-  GnDev d{a.src1, a.C1, a.src2, a.C2, a.stats, a.gamma, a.beta, a.film, a.film_stride, a.silu, a.H, a.W, a.raw32};
+  DPIR_REQUIRE(!a.src_half || (a.C2 == 0 && a.out_half), "gn_apply: fp16 source only for a single-source fp16 pipeline");
+  GnDev d{a.src1, a.C1, a.src2, a.C2, a.q1, a.q2, a.gamma, a.beta, a.film, a.film_stride, a.silu, a.H, a.W, a.raw32};
   int nwork = (a.resample == RS_DOWN) ? (a.H / 2) * (a.W / 2) : a.H * a.W;
   dim3 grid(cdiv(nwork, GN_APPLY_PIX), a.B);
   int threads = gn_threads(C);
-#define GN_LAUNCH(T, M) k_gn_apply<T, M><<<grid, threads, 0, st>>>(d, (T *)a.act, (T *)a.rawact)
-  if (a.out_half) {
-    if (a.resample == RS_NONE) GN_LAUNCH(__half, RS_NONE);
-    else if (a.resample == RS_DOWN) GN_LAUNCH(__half, RS_DOWN);
-    else GN_LAUNCH(__half, RS_UP);
+#define GN_LAUNCH(T, TI, M) k_gn_apply<T, TI, M><<<grid, threads, 0, st>>>(d, (T *)a.act, (T *)a.rawact)
+  if (a.out_half && a.src_half) {
+    if (a.resample == RS_NONE) GN_LAUNCH(__half, __half, RS_NONE);
+    else if (a.resample == RS_DOWN) GN_LAUNCH(__half, __half, RS_DOWN);
+    else GN_LAUNCH(__half, __half, RS_UP);
+  } else if (a.out_half) {
+    if (a.resample == RS_NONE) GN_LAUNCH(__half, float, RS_NONE);
+    else if (a.resample == RS_DOWN) GN_LAUNCH(__half, float, RS_DOWN);
+    else GN_LAUNCH(__half, float, RS_UP);
   } else {
-    if (a.resample == RS_NONE) GN_LAUNCH(float, RS_NONE);
-    else if (a.resample == RS_DOWN) GN_LAUNCH(float, RS_DOWN);
-    else GN_LAUNCH(float, RS_UP);
+    if (a.resample == RS_NONE) GN_LAUNCH(float, float, RS_NONE);
+    else if (a.resample == RS_DOWN) GN_LAUNCH(float, float, RS_DOWN);
+    else GN_LAUNCH(float, float, RS_UP);
   }
 #undef GN_LAUNCH
   DPIR_LAUNCH_CHECK();

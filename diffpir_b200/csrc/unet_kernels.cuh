@@ -9,9 +9,10 @@ enum Resample { RS_NONE = 0, RS_DOWN = 1, RS_UP = 2 };
 enum EpiMode { EPI_NHWC = 0, EPI_NCHW = 1, EPI_X0 = 2 };
 
 struct GnApplyArgs {
-  const float *src1; int C1;
-  const float *src2; int C2;          // may be null / 0
-  const double *stats;                // [B][32][2] (sum, sumsq) for this norm
+  const void *src1; int C1;           // fp32 (or fp16 when src_half) NHWC
+  const void *src2; int C2;           // may be null / 0 (fp32 only)
+  int src_half;                       // 1: src1 is __half (single source)
+  const double *q1, *q2;              // per-tensor quad statistics [B][C/4][2] (sum, sumsq) of src1 / src2
   const float *gamma, *beta;          // [C]
   const float *film; int film_stride; // per-sample (scale[C], shift[C]) at film + b*film_stride, or null
   int silu;                           // apply SiLU after the affine/FiLM
@@ -28,6 +29,8 @@ struct ConvEpi {
   const float *bias;        // [Cout]
   const float *residual;    // NHWC fp32 [B,H,W,Cout] or null (EPI_NHWC only)
   float *out;               // NHWC [B,H,W,Cout] | NCHW [B,Cout,H,W] | x0 NCHW [B,3,H,W]
+  int out_half;             // EPI_NHWC on tensor cores: store __half instead of float (out is then a __half*)
+  double *qstats;           // EPI_NHWC on tensor cores: accumulate quad statistics [B][Cout/4][2] of the stored tensor, or null
   const float *x_nchw;      // EPI_X0: x_t (B,3,H,W)
   const float *coef;        // EPI_X0: [T][2] (sqrt_recip_alphas_cumprod, sqrt_recipm1_alphas_cumprod) as float
   const int64_t *t;         // EPI_X0: (B,) timesteps on device
@@ -70,7 +73,7 @@ __device__ __forceinline__ void conv_epilogue_store(const ConvEpi &e, int n, int
 
 int launch_conv_in(const float *x_nchw, const float *w, const float *bias, float *out, int B, int H, int W, int Cin, int Cout,
                    cudaStream_t st);
-int launch_gn_stats(const float *src1, int C1, const float *src2, int C2, double *stats, int B, int HW, cudaStream_t st);
+int launch_gn_stats(const float *src, int C, double *qstats, int B, int HW, cudaStream_t st);
 int launch_gn_apply(const GnApplyArgs &a, cudaStream_t st);
 int launch_conv_simt(const float *act, const float *w, int ldw, const ConvEpi &epi, int B, int H, int W, int Cin, int Cout,
                      int ksize, cudaStream_t st);
