@@ -62,6 +62,7 @@ SIGNATURES = {
     "dpir_blur_reflect": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "dpir_conv_tc": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
                                c_int32, c_int32, c_int32, c_void_p]),
+    "dpir_conv_tc_variant": (c_int32, [c_int32]),
     "dpir_conv_simt": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
                                  c_int32, c_int32, c_void_p]),
 }

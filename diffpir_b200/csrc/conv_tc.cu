@@ -145,6 +145,85 @@ struct ConvTcGeom {
   int tiles_w, tiles_h, tiles_n;
 };
 
+// NHWC epilogue of one 32-column chunk held by one warp (lane = pixel row): + bias (+ residual), store fp32 or fp16,
+// and (optionally) accumulate the per-quad GroupNorm statistics of the stored tensor.
+__device__ __forceinline__ void epi_nhwc_chunk32(const ConvEpi &epi, const ConvTcGeom &g, const uint32_t *r, bool valid, int n,
+                                                 int yh, int xw, int co, int lane, bool warp_img_ok) {
+  float qs[8], qq[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { qs[j] = 0.f; qq[j] = 0.f; }
+  if (valid) {
+    const int64_t pix = ((int64_t)n * g.H + yh) * g.W + xw;
+    const float *rs = epi.residual ? epi.residual + pix * g.Cout + co : nullptr;
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      if (co + j < g.Cout) {
+        float4 b4 = __ldg(reinterpret_cast<const float4 *>(epi.bias + co + j));
+        v[j] = __uint_as_float(r[j]) + b4.x; v[j + 1] = __uint_as_float(r[j + 1]) + b4.y;
+        v[j + 2] = __uint_as_float(r[j + 2]) + b4.z; v[j + 3] = __uint_as_float(r[j + 3]) + b4.w;
+        if (rs) {
+          float4 rv = *reinterpret_cast<const float4 *>(rs + j);
+          v[j] += rv.x; v[j + 1] += rv.y; v[j + 2] += rv.z; v[j + 3] += rv.w;
+        }
+        qs[j >> 2] = (v[j] + v[j + 1]) + (v[j + 2] + v[j + 3]);
+        qq[j >> 2] = (v[j] * v[j] + v[j + 1] * v[j + 1]) + (v[j + 2] * v[j + 2] + v[j + 3] * v[j + 3]);
+      } else {
+        v[j] = v[j + 1] = v[j + 2] = v[j + 3] = 0.f;
+      }
+    }
+    if (epi.out_half) {
+      __half *o = reinterpret_cast<__half *>(epi.out) + pix * g.Cout + co;
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        if (co + j < g.Cout) {
+          __half2 h0 = __floats2half2_rn(v[j], v[j + 1]), h1 = __floats2half2_rn(v[j + 2], v[j + 3]);
+          __half2 h2 = __floats2half2_rn(v[j + 4], v[j + 5]), h3 = __floats2half2_rn(v[j + 6], v[j + 7]);
+          uint4 u;
+          u.x = *reinterpret_cast<uint32_t *>(&h0); u.y = *reinterpret_cast<uint32_t *>(&h1);
+          u.z = *reinterpret_cast<uint32_t *>(&h2); u.w = *reinterpret_cast<uint32_t *>(&h3);
+          *reinterpret_cast<uint4 *>(o + j) = u;
+        }
+      }
+    } else {
+      float *o = epi.out + pix * g.Cout + co;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        if (co + j < g.Cout) *reinterpret_cast<float4 *>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    }
+  }
+  if (epi.qstats) {
+    // per-quad (4-channel) sums over the 32 pixels of this warp: reduce-scatter butterfly (8 -> 4 -> 2 -> 1 values
+    // per lane over xor 16/8/4, then plain xor 2/1), 18 shuffles per 32-column chunk; fp64 atomics per quad.
+    float a4[4], b4[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float s_send = (lane & 16) ? qs[i] : qs[i + 4], s_keep = (lane & 16) ? qs[i + 4] : qs[i];
+      float q_send = (lane & 16) ? qq[i] : qq[i + 4], q_keep = (lane & 16) ? qq[i + 4] : qq[i];
+      a4[i] = s_keep + __shfl_xor_sync(0xffffffffu, s_send, 16);
+      b4[i] = q_keep + __shfl_xor_sync(0xffffffffu, q_send, 16);
+    }
+    float a2[2], b2[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      float s_send = (lane & 8) ? a4[i] : a4[i + 2], s_keep = (lane & 8) ? a4[i + 2] : a4[i];
+      float q_send = (lane & 8) ? b4[i] : b4[i + 2], q_keep = (lane & 8) ? b4[i + 2] : b4[i];
+      a2[i] = s_keep + __shfl_xor_sync(0xffffffffu, s_send, 8);
+      b2[i] = q_keep + __shfl_xor_sync(0xffffffffu, q_send, 8);
+    }
+    float s1 = ((lane & 4) ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, (lane & 4) ? a2[0] : a2[1], 4);
+    float q1 = ((lane & 4) ? b2[1] : b2[0]) + __shfl_xor_sync(0xffffffffu, (lane & 4) ? b2[0] : b2[1], 4);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, 2); q1 += __shfl_xor_sync(0xffffffffu, q1, 2);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, 1); q1 += __shfl_xor_sync(0xffffffffu, q1, 1);
+    const int quad = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+    if ((lane & 3) == 0 && warp_img_ok && co + quad * 4 < g.Cout) {
+      double *qp = epi.qstats + ((int64_t)n * (g.Cout >> 2) + (co >> 2) + quad) * 2;
+      atomicAdd(qp, (double)s1);
+      atomicAdd(qp + 1, (double)q1);
+    }
+  }
+}
+
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(const __grid_constant__ CUtensorMap tmA,
                                                          const __grid_constant__ CUtensorMap tmB, ConvTcGeom g, ConvEpi epi) {
@@ -238,79 +317,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(const __grid_constant__ 
         tmem_ld_wait();
         const int co = co0 + c;
         if (epi.mode == EPI_NHWC) {
-          float qs[8], qq[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) { qs[j] = 0.f; qq[j] = 0.f; }
-          if (valid) {
-            const int64_t pix = ((int64_t)n * g.H + yh) * g.W + xw;
-            const float *rs = epi.residual ? epi.residual + pix * g.Cout + co : nullptr;
-            float v[32];
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (co + j < g.Cout) {
-                float4 b4 = __ldg(reinterpret_cast<const float4 *>(epi.bias + co + j));
-                v[j] = __uint_as_float(r[j]) + b4.x; v[j + 1] = __uint_as_float(r[j + 1]) + b4.y;
-                v[j + 2] = __uint_as_float(r[j + 2]) + b4.z; v[j + 3] = __uint_as_float(r[j + 3]) + b4.w;
-                if (rs) {
-                  float4 rv = *reinterpret_cast<const float4 *>(rs + j);
-                  v[j] += rv.x; v[j + 1] += rv.y; v[j + 2] += rv.z; v[j + 3] += rv.w;
-                }
-                qs[j >> 2] = (v[j] + v[j + 1]) + (v[j + 2] + v[j + 3]);
-                qq[j >> 2] = (v[j] * v[j] + v[j + 1] * v[j + 1]) + (v[j + 2] * v[j + 2] + v[j + 3] * v[j + 3]);
-              } else {
-                v[j] = v[j + 1] = v[j + 2] = v[j + 3] = 0.f;
-              }
-            }
-            if (epi.out_half) {
-              __half *o = reinterpret_cast<__half *>(epi.out) + pix * g.Cout + co;
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                if (co + j < g.Cout) {
-                  __half2 h0 = __floats2half2_rn(v[j], v[j + 1]), h1 = __floats2half2_rn(v[j + 2], v[j + 3]);
-                  __half2 h2 = __floats2half2_rn(v[j + 4], v[j + 5]), h3 = __floats2half2_rn(v[j + 6], v[j + 7]);
-                  uint4 u;
-                  u.x = *reinterpret_cast<uint32_t *>(&h0); u.y = *reinterpret_cast<uint32_t *>(&h1);
-                  u.z = *reinterpret_cast<uint32_t *>(&h2); u.w = *reinterpret_cast<uint32_t *>(&h3);
-                  *reinterpret_cast<uint4 *>(o + j) = u;
-                }
-              }
-            } else {
-              float *o = epi.out + pix * g.Cout + co;
-#pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                if (co + j < g.Cout) *reinterpret_cast<float4 *>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            }
-          }
-          if (epi.qstats) {
-            // per-quad (4-channel) sums over the 32 pixels of this warp: reduce-scatter butterfly (8 -> 4 -> 2 -> 1 values
-            // per lane over xor 16/8/4, then plain xor 2/1), 18 shuffles per 32-column chunk; fp64 atomics per quad.
-            float a4[4], b4[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              float s_send = (lane & 16) ? qs[i] : qs[i + 4], s_keep = (lane & 16) ? qs[i + 4] : qs[i];
-              float q_send = (lane & 16) ? qq[i] : qq[i + 4], q_keep = (lane & 16) ? qq[i + 4] : qq[i];
-              a4[i] = s_keep + __shfl_xor_sync(0xffffffffu, s_send, 16);
-              b4[i] = q_keep + __shfl_xor_sync(0xffffffffu, q_send, 16);
-            }
-            float a2[2], b2[2];
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              float s_send = (lane & 8) ? a4[i] : a4[i + 2], s_keep = (lane & 8) ? a4[i + 2] : a4[i];
-              float q_send = (lane & 8) ? b4[i] : b4[i + 2], q_keep = (lane & 8) ? b4[i + 2] : b4[i];
-              a2[i] = s_keep + __shfl_xor_sync(0xffffffffu, s_send, 8);
-              b2[i] = q_keep + __shfl_xor_sync(0xffffffffu, q_send, 8);
-            }
-            float s1 = ((lane & 4) ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, (lane & 4) ? a2[0] : a2[1], 4);
-            float q1 = ((lane & 4) ? b2[1] : b2[0]) + __shfl_xor_sync(0xffffffffu, (lane & 4) ? b2[0] : b2[1], 4);
-            s1 += __shfl_xor_sync(0xffffffffu, s1, 2); q1 += __shfl_xor_sync(0xffffffffu, q1, 2);
-            s1 += __shfl_xor_sync(0xffffffffu, s1, 1); q1 += __shfl_xor_sync(0xffffffffu, q1, 1);
-            const int quad = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-            if ((lane & 3) == 0 && warp_img_ok && co + quad * 4 < g.Cout) {
-              double *qp = epi.qstats + ((int64_t)n * (g.Cout >> 2) + (co >> 2) + quad) * 2;
-              atomicAdd(qp, (double)s1);
-              atomicAdd(qp + 1, (double)q1);
-            }
-          }
+          epi_nhwc_chunk32(epi, g, r, valid, n, yh, xw, co, lane, warp_img_ok);
         } else if (valid) {
           float acc[32];
 #pragma unroll
@@ -339,12 +346,172 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(const __grid_constant__ 
   if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
+// ------------------------------------------------------------------------------------------------ v2: persistent 3x3 kernel
+// The v1 kernel above re-fetches the A tile once per tap (9x) and the weight tile once per CTA: ncu shows it bound by
+// L2->SM traffic (8.5 TB/s through the crossbar, tensor pipe 19-27 % active), not by the tensor cores.  v2 cuts that
+// traffic ~2.3x and hides the epilogue:
+//   * M tile = 16 x 16 pixels = two 128-row sub-tiles (image rows 0-7 / 8-15) with separate TMEM accumulators that SHARE
+//     every weight tile (B traffic per pixel halved);
+//   * per (64-channel chunk, dx) ONE 4-D TMA fetches an 18-row x 16-col halo box (shifted by dx-1 in W, zero-filled
+//     outside the image); the three vertical taps dy are three views into it, each starting dy*16 pixels = dy*2048 B
+//     further - still 1024 B aligned, so the same SWIZZLE_128B descriptors apply (A traffic 3 x 18/16 = 3.4x instead of 9x);
+//   * persistent CTAs (one per SM) walk a static tile list; TMEM holds 2 x (2 x 128) accumulator columns so the epilogue
+//     of tile i (8 warps) overlaps the TMA/MMA main loop of tile i+1.
+constexpr int V2_A_BYTES = 18 * 16 * 128;            // halo box: 288 pixel rows x 64 fp16
+constexpr int V2_B_BYTES = 3 * 128 * 128;            // 3 vertical taps x (128 couts x 64 fp16)
+constexpr int V2_STAGE_BYTES = V2_A_BYTES + V2_B_BYTES;   // 86,016 B
+constexpr int V2_STAGES = 2;
+constexpr int V2_THREADS = 320;                       // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
+constexpr int V2_SMEM = V2_STAGES * V2_STAGE_BYTES + 1024 + 256;
+
+struct ConvV2Geom {
+  int B, H, W, Cin, Cout;
+  int tiles_w, tiles_h, n_tiles;      // 16x16 pixel tiles per image, Cout/128 column tiles
+  int total_tiles;                    // B * tiles_h * tiles_w * n_tiles
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(V2_THREADS, 1) k_conv3x3_v2(const __grid_constant__ CUtensorMap tmA,
+                                                               const __grid_constant__ CUtensorMap tmB, ConvV2Geom g,
+                                                               ConvEpi epi) {
+  constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem + V2_STAGES * V2_STAGE_BYTES);
+  uint64_t *empty = full + V2_STAGES;
+  uint64_t *tmem_full = empty + V2_STAGES;     // [2]
+  uint64_t *tmem_empty = tmem_full + 2;        // [2]
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int chunks = g.Cin / TC_BK;
+  const int num_k = 3 * chunks;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < V2_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 8); }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // tile id -> (image, tile row, tile col, cout tile); the cout tile varies fastest so that concurrently running CTAs
+  // share the same activation box in L2
+  auto decode = [&](int tile, int &n, int &h0, int &w0, int &co0) {
+    int nt = tile % g.n_tiles;
+    int mt = tile / g.n_tiles;
+    co0 = nt * 128;
+    w0 = (mt % g.tiles_w) * 16;
+    h0 = ((mt / g.tiles_w) % g.tiles_h) * 16;
+    n = mt / (g.tiles_w * g.tiles_h);
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+        int n, h0, w0, co0;
+        decode(tile, n, h0, w0, co0);
+        for (int k = 0; k < num_k; ++k, ++it) {
+          const int s = it % V2_STAGES;
+          const uint32_t ph = (it / V2_STAGES) & 1u;
+          mbar_wait(&empty[s], ph ^ 1u);
+          const int ch = k / 3, dx = k - ch * 3;
+          uint8_t *sa = smem + s * V2_STAGE_BYTES;
+          mbar_expect_tx(&full[s], V2_STAGE_BYTES);
+          tma_load_4d(sa, &tmA, &full[s], ch * TC_BK, w0 + dx - 1, h0 - 1, n);
+#pragma unroll
+          for (int dy = 0; dy < 3; ++dy)
+            tma_load_3d(sa + V2_A_BYTES + dy * (128 * 128), &tmB, &full[s], ch * TC_BK, co0, dy * 3 + dx);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t it = 0, tc = 0;
+      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++tc) {
+        const uint32_t ab = tc & 1u, aph = (tc >> 1) & 1u;
+        mbar_wait(&tmem_empty[ab], aph ^ 1u);      // epilogue has drained this accumulator pair
+        tc_fence_after();
+        for (int k = 0; k < num_k; ++k, ++it) {
+          const int s = it % V2_STAGES;
+          const uint32_t ph = (it / V2_STAGES) & 1u;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * V2_STAGE_BYTES);
+#pragma unroll
+          for (int dy = 0; dy < 3; ++dy) {
+            const uint64_t bdesc = make_sw128_desc(sa + V2_A_BYTES + dy * (128 * 128));
+#pragma unroll
+            for (int sub = 0; sub < 2; ++sub) {
+              // rows (sub*8 + dy) .. +7 of the 18-row halo box, 16 pixels each: 128 consecutive 128 B rows
+              const uint64_t adesc = make_sw128_desc(sa + (uint32_t)((sub * 8 + dy) * 16 * 128));
+              const uint32_t d = tmem_base + ab * 256u + (uint32_t)sub * 128u;
+#pragma unroll
+              for (int kk = 0; kk < TC_BK / 16; ++kk)
+                umma_f16(d, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), IDESC, (k | dy | kk) ? 1u : 0u);
+            }
+          }
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&tmem_full[ab]);
+      }
+    }
+  } else {
+    const int ew = warp - 2;              // 0..7
+    const int q = warp & 3;               // TMEM lane quarter accessible to this warp
+    const int sub = ew >> 2;              // which 128-row sub-tile
+    const int row = q * 32 + lane;        // row inside the sub-tile: 8 image rows x 16 cols
+    ConvTcGeom gg;
+    gg.B = g.B; gg.H = g.H; gg.W = g.W; gg.Cin = g.Cin; gg.Cout = g.Cout;
+    uint32_t tc = 0;
+    for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++tc) {
+      const uint32_t ab = tc & 1u, aph = (tc >> 1) & 1u;
+      int n, h0, w0, co0;
+      decode(tile, n, h0, w0, co0);
+      const int yh = h0 + sub * 8 + (row >> 4);
+      const int xw = w0 + (row & 15);
+      const bool valid = (yh < g.H) && (xw < g.W);
+      mbar_wait(&tmem_full[ab], aph);
+      tc_fence_after();
+      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + ab * 256u + (uint32_t)sub * 128u;
+#pragma unroll 1
+      for (int c = 0; c < 128; c += 32) {
+        uint32_t r[32];
+        tmem_ld32(tbase + (uint32_t)c, r);
+        tmem_ld_wait();
+        epi_nhwc_chunk32(epi, gg, r, valid, n, yh, xw, co0 + c, lane, true);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[ab]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 struct ConvTcPlan {
   CUtensorMap tmA, tmB;
   ConvTcGeom g;
   int BN, CoutPad;
+  bool v2 = false;        // persistent 3x3 kernel (k_conv3x3_v2)
+  ConvV2Geom g2;
 };
+
+static int g_force_v1 = 0;   // tests / A-B benchmarking: dpir_conv_tc_variant(1) forces the v1 kernel everywhere
+static int g_num_sms = 0;
 
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
@@ -379,10 +546,18 @@ int conv_tc_plan_create(const void *act_half, const void *w_half, int B, int H, 
   g.tiles_w = cdiv(W, g.TW); g.tiles_h = cdiv(H, g.TH); g.tiles_n = cdiv(B, g.TN);
   p->BN = CoutPad == 16 ? 16 : 128;
   p->CoutPad = CoutPad;
+  p->v2 = !g_force_v1 && ksize == 3 && H >= 16 && W >= 16 && CoutPad % 128 == 0;
+  if (p->v2) {
+    ConvV2Geom &g2 = p->g2;
+    g2.B = B; g2.H = H; g2.W = W; g2.Cin = Cin; g2.Cout = 0;
+    g2.tiles_w = cdiv(W, 16); g2.tiles_h = cdiv(H, 16); g2.n_tiles = CoutPad / 128;
+    g2.total_tiles = B * g2.tiles_w * g2.tiles_h * g2.n_tiles;
+  }
   {
     cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t gstr[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
     cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)g.TW, (cuuint32_t)g.TH, (cuuint32_t)g.TN};
+    if (p->v2) { box[1] = 16; box[2] = 18; box[3] = 1; }
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = encode(&p->tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(act_half), gdim, gstr, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -419,9 +594,28 @@ static int launch_tc_impl(const ConvTcPlan *p, const ConvTcGeom &g, const ConvEp
   return DPIR_OK;
 }
 
+void conv_tc_force_v1(int on) { g_force_v1 = on; }
+
 int launch_conv_tc(const ConvTcPlan *p, const ConvEpi &epi, int Cout, cudaStream_t st) {
   DPIR_REQUIRE(Cout <= p->CoutPad, "conv_tc: Cout exceeds padded weight rows");
   DPIR_REQUIRE(epi.mode != EPI_NHWC || Cout % 4 == 0, "conv_tc: NHWC epilogue needs Cout %% 4 == 0");
+  if (p->v2 && epi.mode == EPI_NHWC) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      DPIR_CUDA_CHECK(cudaFuncSetAttribute(k_conv3x3_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, V2_SMEM));
+      int dev = 0;
+      DPIR_CUDA_CHECK(cudaGetDevice(&dev));
+      DPIR_CUDA_CHECK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+      attr_set = true;
+    }
+    ConvV2Geom g2 = p->g2;
+    g2.Cout = Cout;
+    int grid = g2.total_tiles < g_num_sms ? g2.total_tiles : g_num_sms;
+    k_conv3x3_v2<<<grid, V2_THREADS, V2_SMEM, st>>>(p->tmA, p->tmB, g2, epi);
+    DPIR_LAUNCH_CHECK();
+    return DPIR_OK;
+  }
+  DPIR_REQUIRE(!p->v2, "conv_tc: the persistent 3x3 kernel only has the NHWC epilogue");
   ConvTcGeom g = p->g;
   g.Cout = Cout;
   if (p->BN == 16) return launch_tc_impl<16, 4>(p, g, epi, st);

@@ -954,6 +954,11 @@ int dpir_conv_tc(const void *act, const void *w, const float *bias, const float 
   return rc;
 }
 
+int dpir_conv_tc_variant(int32_t force_v1) {
+  conv_tc_force_v1(force_v1 ? 1 : 0);
+  return DPIR_OK;
+}
+
 int dpir_conv_simt(const float *act, const float *w, const float *bias, const float *residual, float *out, int32_t B, int32_t H,
                    int32_t W, int32_t Cin, int32_t Cout, int32_t ksize, void *stream) {
   DPIR_REQUIRE(act && w && bias && out, "dpir_conv_simt: null pointer");

@@ -92,5 +92,6 @@ int conv_tc_plan_create(const void *act_half, const void *w_half, int B, int H, 
                         ConvTcPlan **out);
 void conv_tc_plan_destroy(ConvTcPlan *p);
 int launch_conv_tc(const ConvTcPlan *p, const ConvEpi &epi, int Cout, cudaStream_t st);
+void conv_tc_force_v1(int on);   // 1: use the one-tile-per-CTA kernel for every shape (A/B testing)
 
 }  // namespace dpir

@@ -48,10 +48,17 @@ SHAPES = [
 ]
 
 
-@pytest.mark.parametrize("B,H,W,Cin,Cout,k,residual", SHAPES)
-def test_conv_tc_matches_torch(B, H, W, Cin, Cout, k, residual):
+@pytest.mark.parametrize("variant", ["auto", "v1"])
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k,residual", SHAPES + [
+    (5, 32, 32, 128, 256, 3, True),     # persistent kernel: 40 tiles, 2 cout tiles, odd batch
+    (2, 48, 80, 128, 128, 3, True),     # H, W multiples of 16 but not powers of two
+    (1, 24, 40, 192, 128, 3, False),    # ragged: partial 16x16 tiles on both edges
+    (7, 16, 16, 256, 512, 3, False),
+])
+def test_conv_tc_matches_torch(B, H, W, Cin, Cout, k, residual, variant):
     from diffpir_b200 import _lib
     lib = _lib.load()
+    lib.dpir_conv_tc_variant(1 if variant == "v1" else 0)
     x, w, b, r = _case(B, H, W, Cin, Cout, k, 0, residual)
     # reference: fp32 conv of the fp16-rounded operands (isolates kernel correctness from operand rounding)
     xh, wh = x.half().float(), w.half().float()
@@ -66,6 +73,7 @@ def test_conv_tc_matches_torch(B, H, W, Cin, Cout, k, residual):
     _lib.check(lib.dpir_conv_tc(_lib.ptr(act), _lib.ptr(wp), _lib.ptr(bias), _lib.ptr(res), _lib.ptr(out), B, H, W, Cin, Cout,
                                 Cout, k, _lib.stream_ptr()), "dpir_conv_tc")
     torch.cuda.synchronize()
+    lib.dpir_conv_tc_variant(0)
     got = out.permute(0, 3, 1, 2)
     assert not torch.isnan(got).any()
     assert rel_l2(got, ref) < 1e-5      # fp32 accumulation order over K = 9*Cin
