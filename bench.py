@@ -370,9 +370,8 @@ def main():
         conv_flops = 0.0
         for r in rows:
             if r["kind"] == "conv":
-                H, W, Cin, packed = r["dims"]
-                Cout, ks = packed // 10, packed % 10
-                conv_flops += 2.0 * B * H * W * ks * ks * Cin * Cout
+                H, W, Cin, Cout, ks, Cin2 = r["dims"]
+                conv_flops += 2.0 * B * H * W * (ks * ks * Cin + Cin2) * Cout
         peak = peaks.get("bf16_tflops_sustained", FALLBACK_PEAKS["bf16_tflops_sustained"])
         achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
         unet_ms = sum(by_kind.values())

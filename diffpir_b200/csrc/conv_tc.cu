@@ -160,6 +160,10 @@ __device__ __forceinline__ void epi_nhwc_chunk32(const ConvEpi &epi, const ConvT
     for (int j = 0; j < 32; j += 4) {
       if (co + j < g.Cout) {
         float4 b4 = __ldg(reinterpret_cast<const float4 *>(epi.bias + co + j));
+        if (epi.bias2) {
+          float4 c4 = __ldg(reinterpret_cast<const float4 *>(epi.bias2 + co + j));
+          b4.x += c4.x; b4.y += c4.y; b4.z += c4.z; b4.w += c4.w;
+        }
         v[j] = __uint_as_float(r[j]) + b4.x; v[j + 1] = __uint_as_float(r[j + 1]) + b4.y;
         v[j + 2] = __uint_as_float(r[j + 2]) + b4.z; v[j + 3] = __uint_as_float(r[j + 3]) + b4.w;
         if (rs) {
@@ -366,6 +370,7 @@ constexpr int V2_SMEM = V2_STAGES * V2_STAGE_BYTES + 1024 + 256;
 
 struct ConvV2Geom {
   int B, H, W, Cin, Cout;
+  int skip_chunks;                    // extra K chunks of a fused 1x1 convolution on a second operand (ResBlock skip), or 0
   int tiles_w, tiles_h, n_tiles;      // 16x16 pixel tiles per image, Cout/128 column tiles
   int total_tiles;                    // B * tiles_h * tiles_w * n_tiles
 };
@@ -374,8 +379,13 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// Optional fusion of the ResBlock's 1x1 skip_connection (unet.py:222, 256): out = conv3x3(a2) + conv1x1(x) is one
+// accumulation - after the 3*chunks (chunk, dx) stages, `skip_chunks` more stages load the centre-aligned halo box of the
+// second operand (tmA2) and the 1x1 weights (tmB2) and issue only the dy = 1 view.
 __global__ void __launch_bounds__(V2_THREADS, 1) k_conv3x3_v2(const __grid_constant__ CUtensorMap tmA,
-                                                               const __grid_constant__ CUtensorMap tmB, ConvV2Geom g,
+                                                               const __grid_constant__ CUtensorMap tmB,
+                                                               const __grid_constant__ CUtensorMap tmA2,
+                                                               const __grid_constant__ CUtensorMap tmB2, ConvV2Geom g,
                                                                ConvEpi epi) {
   constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   extern __shared__ uint8_t smem_raw[];
@@ -388,11 +398,13 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_conv3x3_v2(const __grid_const
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int chunks = g.Cin / TC_BK;
-  const int num_k = 3 * chunks;
+  const int num_main = 3 * chunks;
+  const int num_k = num_main + g.skip_chunks;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (g.skip_chunks) { tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmB2); }
     for (int s = 0; s < V2_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 8); }
     fence_barrier_init();
@@ -425,13 +437,20 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_conv3x3_v2(const __grid_const
           const int s = it % V2_STAGES;
           const uint32_t ph = (it / V2_STAGES) & 1u;
           mbar_wait(&empty[s], ph ^ 1u);
-          const int ch = k / 3, dx = k - ch * 3;
           uint8_t *sa = smem + s * V2_STAGE_BYTES;
-          mbar_expect_tx(&full[s], V2_STAGE_BYTES);
-          tma_load_4d(sa, &tmA, &full[s], ch * TC_BK, w0 + dx - 1, h0 - 1, n);
+          if (k < num_main) {
+            const int ch = k / 3, dx = k - ch * 3;
+            mbar_expect_tx(&full[s], V2_STAGE_BYTES);
+            tma_load_4d(sa, &tmA, &full[s], ch * TC_BK, w0 + dx - 1, h0 - 1, n);
 #pragma unroll
-          for (int dy = 0; dy < 3; ++dy)
-            tma_load_3d(sa + V2_A_BYTES + dy * (128 * 128), &tmB, &full[s], ch * TC_BK, co0, dy * 3 + dx);
+            for (int dy = 0; dy < 3; ++dy)
+              tma_load_3d(sa + V2_A_BYTES + dy * (128 * 128), &tmB, &full[s], ch * TC_BK, co0, dy * 3 + dx);
+          } else {
+            const int ch = k - num_main;
+            mbar_expect_tx(&full[s], V2_A_BYTES + 128 * 128);
+            tma_load_4d(sa, &tmA2, &full[s], ch * TC_BK, w0, h0 - 1, n);
+            tma_load_3d(sa + V2_A_BYTES + 1 * (128 * 128), &tmB2, &full[s], ch * TC_BK, co0, 0);
+          }
         }
       }
     }
@@ -448,8 +467,8 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_conv3x3_v2(const __grid_const
           mbar_wait(&full[s], ph);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * V2_STAGE_BYTES);
-#pragma unroll
-          for (int dy = 0; dy < 3; ++dy) {
+          const int dy_lo = k < num_main ? 0 : 1, dy_hi = k < num_main ? 3 : 2;
+          for (int dy = dy_lo; dy < dy_hi; ++dy) {
             const uint64_t bdesc = make_sw128_desc(sa + V2_A_BYTES + dy * (128 * 128));
 #pragma unroll
             for (int sub = 0; sub < 2; ++sub) {
@@ -508,6 +527,7 @@ struct ConvTcPlan {
   int BN, CoutPad;
   bool v2 = false;        // persistent 3x3 kernel (k_conv3x3_v2)
   ConvV2Geom g2;
+  CUtensorMap tmA2, tmB2; // fused 1x1 skip operand / weights (v2 only; copies of tmA/tmB when unused)
 };
 
 static int g_force_v1 = 0;   // tests / A-B benchmarking: dpir_conv_tc_variant(1) forces the v1 kernel everywhere
@@ -549,7 +569,7 @@ int conv_tc_plan_create(const void *act_half, const void *w_half, int B, int H, 
   p->v2 = !g_force_v1 && ksize == 3 && H >= 16 && W >= 16 && CoutPad % 128 == 0;
   if (p->v2) {
     ConvV2Geom &g2 = p->g2;
-    g2.B = B; g2.H = H; g2.W = W; g2.Cin = Cin; g2.Cout = 0;
+    g2.B = B; g2.H = H; g2.W = W; g2.Cin = Cin; g2.Cout = 0; g2.skip_chunks = 0;
     g2.tiles_w = cdiv(W, 16); g2.tiles_h = cdiv(H, 16); g2.n_tiles = CoutPad / 128;
     g2.total_tiles = B * g2.tiles_w * g2.tiles_h * g2.n_tiles;
   }
@@ -574,7 +594,42 @@ int conv_tc_plan_create(const void *act_half, const void *w_half, int B, int H, 
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled(B) failed: %d", (int)r); delete p; return DPIR_E_CUDA; }
   }
+  p->tmA2 = p->tmA;
+  p->tmB2 = p->tmB;
   *out = p;
+  return DPIR_OK;
+}
+
+bool conv_tc_plan_is_v2(const ConvTcPlan *p) { return p->v2; }
+
+// attach a fused 1x1 convolution on a second NHWC fp16 operand (same B,H,W; Cin2 channels; weights [1][CoutPad][Cin2])
+int conv_tc_plan_add_skip(ConvTcPlan *p, const void *act2_half, const void *w2_half, int Cin2) {
+  DPIR_REQUIRE(p->v2, "conv_tc: skip fusion needs the persistent 3x3 kernel");
+  DPIR_REQUIRE(Cin2 % TC_BK == 0, "conv_tc: fused skip Cin must be a multiple of 64");
+  auto encode = get_encode_fn();
+  if (!encode) { set_error("conv_tc: cuTensorMapEncodeTiled entry point unavailable"); return DPIR_E_CUDA; }
+  const ConvTcGeom &g = p->g;
+  {
+    cuuint64_t gdim[4] = {(cuuint64_t)Cin2, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.B};
+    cuuint64_t gstr[3] = {(cuuint64_t)Cin2 * 2, (cuuint64_t)g.W * Cin2 * 2, (cuuint64_t)g.H * g.W * Cin2 * 2};
+    cuuint32_t box[4] = {(cuuint32_t)TC_BK, 16, 18, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = encode(&p->tmA2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(act2_half), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled(A2) failed: %d", (int)r); return DPIR_E_CUDA; }
+  }
+  {
+    cuuint64_t gdim[3] = {(cuuint64_t)Cin2, (cuuint64_t)p->CoutPad, 1};
+    cuuint64_t gstr[2] = {(cuuint64_t)Cin2 * 2, (cuuint64_t)p->CoutPad * Cin2 * 2};
+    cuuint32_t box[3] = {(cuuint32_t)TC_BK, 128, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode(&p->tmB2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void *>(w2_half), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled(B2) failed: %d", (int)r); return DPIR_E_CUDA; }
+  }
+  p->g2.skip_chunks = Cin2 / TC_BK;
   return DPIR_OK;
 }
 
@@ -595,6 +650,7 @@ static int launch_tc_impl(const ConvTcPlan *p, const ConvTcGeom &g, const ConvEp
 }
 
 void conv_tc_force_v1(int on) { g_force_v1 = on; }
+bool conv_tc_v2_enabled() { return !g_force_v1; }
 
 int launch_conv_tc(const ConvTcPlan *p, const ConvEpi &epi, int Cout, cudaStream_t st) {
   DPIR_REQUIRE(Cout <= p->CoutPad, "conv_tc: Cout exceeds padded weight rows");
@@ -611,7 +667,7 @@ int launch_conv_tc(const ConvTcPlan *p, const ConvEpi &epi, int Cout, cudaStream
     ConvV2Geom g2 = p->g2;
     g2.Cout = Cout;
     int grid = g2.total_tiles < g_num_sms ? g2.total_tiles : g_num_sms;
-    k_conv3x3_v2<<<grid, V2_THREADS, V2_SMEM, st>>>(p->tmA, p->tmB, g2, epi);
+    k_conv3x3_v2<<<grid, V2_THREADS, V2_SMEM, st>>>(p->tmA, p->tmB, p->tmA2, p->tmB2, g2, epi);
     DPIR_LAUNCH_CHECK();
     return DPIR_OK;
   }

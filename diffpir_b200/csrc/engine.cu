@@ -64,6 +64,8 @@ struct Op {
   const void *p0 = nullptr, *p1 = nullptr, *p2 = nullptr;   // workspace tensors (offset-encoded until the plan is rebased)
   void *q0 = nullptr;                                        // workspace tensor (output)
   const void *w = nullptr;                                   // absolute pointer into the weight arena
+  const void *w2 = nullptr;                                  // fused 1x1 skip weights (arena) for the persistent 3x3 kernel
+  int Cin2 = 0;                                              // channels of the fused skip operand (p2)
   size_t bytes = 0;
   int B = 0, H = 0, W = 0, C1 = 0, C2 = 0, Cin = 0, Cout = 0, ldw = 0, ksize = 0, heads = 0, HW = 0, out_half = 0;
   ConvTcPlan *tc = nullptr;
@@ -428,7 +430,14 @@ struct PlanBuilder {
 
   // conv on a workspace activation -> new NHWC buffer (fp32, or fp16 when out_half in tensor-core mode); residual
   // optional; want_stats attaches quad statistics to the output (fused in the tcgen05 epilogue, separate pass in fp32 mode)
-  int conv(int act, const ConvW &cw, int residual, int *out_id, bool want_stats = false, bool out_half = false) {
+  // whether the tensor-core path will run this conv on the persistent 3x3 kernel (mirrors conv_tc_plan_create)
+  bool v2_eligible(int act, const ConvW &cw) const {
+    const Buf &a = bufs[act];
+    return e->half && conv_tc_v2_enabled() && cw.ksize == 3 && a.H >= 16 && a.W >= 16 && cw.ldw % 128 == 0;
+  }
+
+  int conv(int act, const ConvW &cw, int residual, int *out_id, bool want_stats = false, bool out_half = false,
+           int skip_act = -1, const ConvW *skip_w = nullptr) {
     const Buf &a = bufs[act];
     out_half = out_half && e->half;
     *out_id = new_buf(B, a.H, a.W, cw.cout, out_half, want_stats);
@@ -443,6 +452,12 @@ struct PlanBuilder {
     op.epi.out = bp<float>(*out_id);
     op.epi.out_half = out_half ? 1 : 0;
     op.epi.qstats = (want_stats && e->half) ? sp(*out_id) : nullptr;
+    if (skip_act >= 0) {   // out = conv3x3(act) + conv1x1(skip_act): one accumulation (unet.py:222, 256)
+      op.p2 = bp<void>(skip_act);
+      op.w2 = e->arena + skip_w->w_off;
+      op.Cin2 = skip_w->cin;
+      op.epi.bias2 = e->ap<float>(skip_w->b_off);
+    }
     plan->ops.push_back(op);
     if (want_stats && !e->half) emit_stats(*out_id);
     return DPIR_OK;
@@ -468,13 +483,18 @@ struct PlanBuilder {
     int a2, d0, d1;
     gn(h1, -1, rw.n2, rw.film_row, 1, RS_NONE, false, false, &a2, &d0, &d1);
     release(h1);
-    if (rw.has_skip) {
-      conv(xraw, rw.skip, -1, &residual);
+    if (rw.has_skip && v2_eligible(a2, rw.c2)) {
+      conv(a2, rw.c2, -1, out, /*want_stats=*/true, false, xraw, &rw.skip);
       release(xraw);
+    } else {
+      if (rw.has_skip) {
+        conv(xraw, rw.skip, -1, &residual);
+        release(xraw);
+      }
+      conv(a2, rw.c2, residual, out, /*want_stats=*/true);
+      release(residual);
     }
-    conv(a2, rw.c2, residual, out, /*want_stats=*/true);
     release(a2);
-    release(residual);
     return DPIR_OK;
   }
 
@@ -619,6 +639,11 @@ int get_plan(dpir_engine *e, int B, int H, int W, Plan **out) {
       if (rc) return rc;
       op.tc = tp;
       plan->tc_plans.push_back(tp);
+      if (op.p2) {
+        if (!conv_tc_plan_is_v2(tp)) { set_error("internal: skip fusion planned for a non-persistent conv"); return DPIR_E_STATE; }
+        rc = conv_tc_plan_add_skip(tp, op.p2, op.w2, op.Cin2);
+        if (rc) return rc;
+      }
     }
   }
   *out = plan.get();
@@ -932,8 +957,9 @@ int dpir_profile_end(dpir_engine *e, int32_t *kind, int32_t *dims, float *ms, in
     if (op.kind == OP_GN_APPLY) { H = op.gn.H; W = op.gn.W; Cin = op.gn.C1 + op.gn.C2; Cout = op.gn.resample; }
     if (op.kind == OP_GN_STATS) { H = op.HW; W = 1; Cin = op.C1 + op.C2; Cout = 0; }
     if (op.kind == OP_ATTN) { H = op.HW; W = 1; Cout = op.heads; }
-    if (op.kind == OP_CONV) Cout = op.Cout * 10 + op.ksize;   // packed: Cout*10 + ksize
-    dims[4 * i] = H; dims[4 * i + 1] = W; dims[4 * i + 2] = Cin; dims[4 * i + 3] = Cout;
+    dims[6 * i] = H; dims[6 * i + 1] = W; dims[6 * i + 2] = Cin; dims[6 * i + 3] = Cout;
+    dims[6 * i + 4] = op.kind == OP_CONV ? op.ksize : 0;
+    dims[6 * i + 5] = op.kind == OP_CONV ? op.Cin2 : 0;
     ms[i] = acc[i];
   }
   e->prof_plan = nullptr;

@@ -15,74 +15,80 @@ namespace dpir {
 
 // =========================================================================================== input stem
 // input_blocks.0.0: Conv2d(Cin<=4, C, 3, padding=1) reading the caller's NCHW image and writing NHWC fp32.
-// w packed [tap*Cin + ci][Cout].  One warp-lane = 4 output channels whose 9*CIN float4 weights stay in registers; every
-// iteration a thread produces a strip of 4 horizontally adjacent pixels from one 3x6 input patch per channel
-// (input loads are warp-broadcasts, output stores are 512 B contiguous per pixel).
+// w packed [tap*Cin + ci][Cout].  One CTA = an 8 x 32 pixel tile whose (10 x 34 x CIN) input patch is staged in shared
+// memory (zero-filled outside the image = the conv padding).  One warp = one tile row; a lane owns 4 output channels
+// whose 9*CIN float4 weights stay in registers and produces 4 horizontally adjacent pixels per iteration from a 3 x 6
+// patch per input channel (shared-memory broadcasts, no predication in the inner loop); stores are 512 B contiguous.
+constexpr int CI_TH = 8, CI_TW = 32;
+
 template <int CIN>
 __global__ void __launch_bounds__(256) k_conv_in(const float *__restrict__ x, const float *__restrict__ w,
                                                  const float *__restrict__ bias, float *__restrict__ out, int B, int H, int W,
                                                  int Cout) {
-  int C4 = Cout / 4;
-  int ppb = blockDim.x / C4;
-  int lane_p = threadIdx.x / C4, c4 = threadIdx.x % C4;
-  if (lane_p >= ppb) return;
-  float4 wr[9 * CIN];
+  __shared__ float patch[CIN][CI_TH + 2][CI_TW + 2];
+  const int tiles_w = (W + CI_TW - 1) / CI_TW, tiles_h = (H + CI_TH - 1) / CI_TH;
+  int t = blockIdx.x;
+  const int w0 = (t % tiles_w) * CI_TW;
+  const int h0 = ((t / tiles_w) % tiles_h) * CI_TH;
+  const int n = t / (tiles_w * tiles_h);
+  for (int i = threadIdx.x; i < CIN * (CI_TH + 2) * (CI_TW + 2); i += blockDim.x) {
+    int c = i / ((CI_TH + 2) * (CI_TW + 2));
+    int r = (i / (CI_TW + 2)) % (CI_TH + 2);
+    int col = i % (CI_TW + 2);
+    int yy = h0 + r - 1, xx = w0 + col - 1;
+    float v = 0.f;
+    if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = __ldg(x + (((int64_t)n * CIN + c) * H + yy) * W + xx);
+    patch[c][r][col] = v;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int yh = h0 + warp;
+  if (yh >= H) return;
+  const int C4 = Cout / 4;
+  for (int c4 = lane; c4 < C4; c4 += 32) {
+    float4 wr[9 * CIN];
 #pragma unroll
-  for (int i = 0; i < 9 * CIN; ++i) wr[i] = reinterpret_cast<const float4 *>(w + (int64_t)i * Cout)[c4];
-  float4 bv = reinterpret_cast<const float4 *>(bias)[c4];
-  int Ws = W / 4;
-  int64_t nstrips = (int64_t)B * H * Ws;
-  for (int64_t sidx = (int64_t)blockIdx.x * ppb + lane_p; sidx < nstrips; sidx += (int64_t)gridDim.x * ppb) {
-    int xs = (int)(sidx % Ws) * 4;
-    int yh = (int)((sidx / Ws) % H);
-    int n = (int)(sidx / ((int64_t)Ws * H));
-    float4 acc[4] = {bv, bv, bv, bv};
+    for (int i = 0; i < 9 * CIN; ++i) wr[i] = __ldg(reinterpret_cast<const float4 *>(w + (int64_t)i * Cout) + c4);
+    const float4 bv = __ldg(reinterpret_cast<const float4 *>(bias) + c4);
+#pragma unroll 1
+    for (int xs = 0; xs < CI_TW; xs += 4) {
+      float4 acc[4] = {bv, bv, bv, bv};
 #pragma unroll
-    for (int ci = 0; ci < CIN; ++ci) {
-      const float *xp = x + ((int64_t)n * CIN + ci) * H * W;
+      for (int ci = 0; ci < CIN; ++ci) {
 #pragma unroll
-      for (int dy = 0; dy < 3; ++dy) {
-        int yy = yh + dy - 1;
-        float r[6];
-        bool rowok = yy >= 0 && yy < H;
+        for (int dy = 0; dy < 3; ++dy) {
+          float r[6];
 #pragma unroll
-        for (int j = 0; j < 6; ++j) {
-          int xx = xs + j - 1;
-          r[j] = (rowok && xx >= 0 && xx < W) ? __ldg(xp + (int64_t)yy * W + xx) : 0.f;
-        }
+          for (int j = 0; j < 6; ++j) r[j] = patch[ci][warp + dy][xs + j];
 #pragma unroll
-        for (int dx = 0; dx < 3; ++dx) {
-          float4 wv = wr[(dy * 3 + dx) * CIN + ci];
+          for (int dx = 0; dx < 3; ++dx) {
+            const float4 wv = wr[(dy * 3 + dx) * CIN + ci];
 #pragma unroll
-          for (int pxl = 0; pxl < 4; ++pxl) {
-            float v = r[pxl + dx];
-            acc[pxl].x += v * wv.x; acc[pxl].y += v * wv.y; acc[pxl].z += v * wv.z; acc[pxl].w += v * wv.w;
+            for (int pxl = 0; pxl < 4; ++pxl) {
+              const float v = r[pxl + dx];
+              acc[pxl].x += v * wv.x; acc[pxl].y += v * wv.y; acc[pxl].z += v * wv.z; acc[pxl].w += v * wv.w;
+            }
           }
         }
       }
-    }
-    int64_t p = ((int64_t)n * H + yh) * W + xs;
+      const int64_t p = ((int64_t)n * H + yh) * W + w0 + xs;
 #pragma unroll
-    for (int pxl = 0; pxl < 4; ++pxl) reinterpret_cast<float4 *>(out + (p + pxl) * Cout)[c4] = acc[pxl];
+      for (int pxl = 0; pxl < 4; ++pxl)
+        if (w0 + xs + pxl < W) reinterpret_cast<float4 *>(out + (p + pxl) * Cout)[c4] = acc[pxl];
+    }
   }
 }
 
 int launch_conv_in(const float *x, const float *w, const float *bias, float *out, int B, int H, int W, int Cin, int Cout,
                    cudaStream_t st) {
-  DPIR_REQUIRE(Cout % 4 == 0 && Cout / 4 <= 256, "conv_in: Cout must be a multiple of 4 and <= 1024");
-  DPIR_REQUIRE(W % 4 == 0, "conv_in: W must be a multiple of 4");
+  DPIR_REQUIRE(Cout % 4 == 0, "conv_in: Cout must be a multiple of 4");
   DPIR_REQUIRE(Cin >= 1 && Cin <= 4, "conv_in: Cin must be 1..4");
-  int C4 = Cout / 4;
-  int ppb = 256 / C4 > 0 ? 256 / C4 : 1;
-  int threads = C4 * ppb;
-  int64_t nstrips = (int64_t)B * H * (W / 4);
-  int64_t want = (nstrips + ppb - 1) / ppb;
-  int grid = (int)(want < 1 ? 1 : (want > 148 * 16 ? 148 * 16 : want));
+  int grid = B * cdiv(H, CI_TH) * cdiv(W, CI_TW);
   switch (Cin) {
-    case 1: k_conv_in<1><<<grid, threads, 0, st>>>(x, w, bias, out, B, H, W, Cout); break;
-    case 2: k_conv_in<2><<<grid, threads, 0, st>>>(x, w, bias, out, B, H, W, Cout); break;
-    case 3: k_conv_in<3><<<grid, threads, 0, st>>>(x, w, bias, out, B, H, W, Cout); break;
-    default: k_conv_in<4><<<grid, threads, 0, st>>>(x, w, bias, out, B, H, W, Cout); break;
+    case 1: k_conv_in<1><<<grid, 256, 0, st>>>(x, w, bias, out, B, H, W, Cout); break;
+    case 2: k_conv_in<2><<<grid, 256, 0, st>>>(x, w, bias, out, B, H, W, Cout); break;
+    case 3: k_conv_in<3><<<grid, 256, 0, st>>>(x, w, bias, out, B, H, W, Cout); break;
+    default: k_conv_in<4><<<grid, 256, 0, st>>>(x, w, bias, out, B, H, W, Cout); break;
   }
   DPIR_LAUNCH_CHECK();
   return DPIR_OK;

@@ -27,6 +27,7 @@ struct GnApplyArgs {
 struct ConvEpi {
   int mode;                 // EpiMode
   const float *bias;        // [Cout]
+  const float *bias2;       // second bias (fused 1x1 skip convolution) or null; tensor-core NHWC epilogue only
   const float *residual;    // NHWC fp32 [B,H,W,Cout] or null (EPI_NHWC only)
   float *out;               // NHWC [B,H,W,Cout] | NCHW [B,Cout,H,W] | x0 NCHW [B,3,H,W]
   int out_half;             // EPI_NHWC on tensor cores: store __half instead of float (out is then a __half*)
@@ -91,7 +92,10 @@ struct ConvTcPlan;  // opaque: tensor maps + geometry
 int conv_tc_plan_create(const void *act_half, const void *w_half, int B, int H, int W, int Cin, int CoutPad, int ksize,
                         ConvTcPlan **out);
 void conv_tc_plan_destroy(ConvTcPlan *p);
+bool conv_tc_plan_is_v2(const ConvTcPlan *p);
+int conv_tc_plan_add_skip(ConvTcPlan *p, const void *act2_half, const void *w2_half, int Cin2);
 int launch_conv_tc(const ConvTcPlan *p, const ConvEpi &epi, int Cout, cudaStream_t st);
+bool conv_tc_v2_enabled();
 void conv_tc_force_v1(int on);   // 1: use the one-tile-per-CTA kernel for every shape (A/B testing)
 
 }  // namespace dpir

@@ -184,14 +184,14 @@ class UNetModel:
         """-> list of dicts (kind, dims, ms) per tape op, summed over the forwards since profile_begin."""
         cap = 4096
         kind = (ctypes.c_int32 * cap)()
-        dims = (ctypes.c_int32 * (4 * cap))()
+        dims = (ctypes.c_int32 * (6 * cap))()
         ms = (ctypes.c_float * cap)()
         n = self._lib.dpir_profile_end(self._h, kind, dims, ms, cap)
         if n < 0:
             _lib.check(n, "dpir_profile_end")
         rows = []
         for i in range(min(n, cap)):
-            rows.append(dict(kind=self.OP_KINDS[kind[i]], dims=tuple(dims[4 * i:4 * i + 4]), ms=float(ms[i])))
+            rows.append(dict(kind=self.OP_KINDS[kind[i]], dims=tuple(dims[6 * i:6 * i + 6]), ms=float(ms[i])))
         return rows
 
     def __del__(self):

@@ -107,8 +107,9 @@ int dpir_set_graph_mode(dpir_engine *e, int32_t enable);
  * accounting).  Between begin and end every forward runs un-graphed with an event pair around each op; `end`
  * synchronises, sums the elapsed time per tape op over all forwards since `begin` and fills up to `cap` rows:
  * kind[i] (0 memset, 1 time-embed, 2 FiLM linears, 3 stem conv, 4 GN stats, 5 GN apply, 6 conv, 7 attention),
- * dims[4i..] = (H, W, Cin, Cout*10+ksize) for convs, (H, W, C, resample) for GN apply, (HW, 1, C, 0) for GN stats,
- * (T, 1, C, heads) for attention; ms[i] = summed milliseconds.  Returns the number of tape ops. */
+ * dims[6i..] = (H, W, Cin, Cout, ksize, Cin2) for convs (Cin2 = channels of a fused 1x1 skip operand), (H, W, C, resample,
+ * 0, 0) for GN apply, (HW, 1, C, 0, 0, 0) for GN stats, (T, 1, C, heads, 0, 0) for attention; ms[i] = summed milliseconds.
+ * Returns the number of tape ops. */
 int dpir_profile_begin(dpir_engine *e);
 int dpir_profile_end(dpir_engine *e, int32_t *kind, int32_t *dims, float *ms, int32_t cap);
 

@@ -43,23 +43,22 @@ def main():
         d = r["dims"]
         rate = ""
         if r["kind"] == "conv":
-            H, W, Cin, packed = d
-            Cout, ks = packed // 10, packed % 10
-            fl = 2.0 * B * H * W * ks * ks * Cin * Cout
+            H, W, Cin, Cout, ks, Cin2 = d
+            fl = 2.0 * B * H * W * (ks * ks * Cin + Cin2) * Cout
             rate = f"{fl / ms / 1e9:8.1f} TF/s"
-            key = ("conv", H, Cin, Cout, ks)
+            key = ("conv", H, Cin, Cout, ks, Cin2)
         elif r["kind"] == "gn_apply":
-            H, W, C, rs = d
+            H, W, C, rs = d[:4]
             by = B * H * W * C * (4 + 2)
             rate = f"{by / ms / 1e6:8.1f} GB/s~"
-            key = ("gn_apply", H, C, rs, 0)
+            key = ("gn_apply", H, C, rs, 0, 0)
         elif r["kind"] == "gn_stats":
-            HW, _, C, _ = d
+            HW, _, C = d[:3]
             by = B * HW * C * 4
             rate = f"{by / ms / 1e6:8.1f} GB/s"
-            key = ("gn_stats", HW, C, 0, 0)
+            key = ("gn_stats", HW, C, 0, 0, 0)
         else:
-            key = (r["kind"], 0, 0, 0, 0)
+            key = (r["kind"], 0, 0, 0, 0, 0)
         agg.setdefault(key, [0.0, 0])
         agg[key][0] += ms
         agg[key][1] += 1
