@@ -145,6 +145,38 @@ struct ConvTcGeom {
   int tiles_w, tiles_h, tiles_n;
 };
 
+// Per-quad (4-channel) sums over the 32 pixel rows held by a warp: reduce-scatter butterfly (8 -> 4 -> 2 -> 1 values per
+// lane over xor 16/8/4, then plain xor 2/1: 18 shuffles per 32-column chunk), then one fp64 atomic pair per quad.
+__device__ __forceinline__ void warp_quad_stats(const float *qs, const float *qq, int lane, bool ok, double *qstats, int n,
+                                                int Cout, int co) {
+  float a4[4], b4[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float s_send = (lane & 16) ? qs[i] : qs[i + 4], s_keep = (lane & 16) ? qs[i + 4] : qs[i];
+    float q_send = (lane & 16) ? qq[i] : qq[i + 4], q_keep = (lane & 16) ? qq[i + 4] : qq[i];
+    a4[i] = s_keep + __shfl_xor_sync(0xffffffffu, s_send, 16);
+    b4[i] = q_keep + __shfl_xor_sync(0xffffffffu, q_send, 16);
+  }
+  float a2[2], b2[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    float s_send = (lane & 8) ? a4[i] : a4[i + 2], s_keep = (lane & 8) ? a4[i + 2] : a4[i];
+    float q_send = (lane & 8) ? b4[i] : b4[i + 2], q_keep = (lane & 8) ? b4[i + 2] : b4[i];
+    a2[i] = s_keep + __shfl_xor_sync(0xffffffffu, s_send, 8);
+    b2[i] = q_keep + __shfl_xor_sync(0xffffffffu, q_send, 8);
+  }
+  float s1 = ((lane & 4) ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, (lane & 4) ? a2[0] : a2[1], 4);
+  float q1 = ((lane & 4) ? b2[1] : b2[0]) + __shfl_xor_sync(0xffffffffu, (lane & 4) ? b2[0] : b2[1], 4);
+  s1 += __shfl_xor_sync(0xffffffffu, s1, 2); q1 += __shfl_xor_sync(0xffffffffu, q1, 2);
+  s1 += __shfl_xor_sync(0xffffffffu, s1, 1); q1 += __shfl_xor_sync(0xffffffffu, q1, 1);
+  const int quad = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+  if ((lane & 3) == 0 && ok && co + quad * 4 < Cout) {
+    double *qp = qstats + ((int64_t)n * (Cout >> 2) + (co >> 2) + quad) * 2;
+    atomicAdd(qp, (double)s1);
+    atomicAdd(qp + 1, (double)q1);
+  }
+}
+
 // NHWC epilogue of one 32-column chunk held by one warp (lane = pixel row): + bias (+ residual), store fp32 or fp16,
 // and (optionally) accumulate the per-quad GroupNorm statistics of the stored tensor.
 __device__ __forceinline__ void epi_nhwc_chunk32(const ConvEpi &epi, const ConvTcGeom &g, const uint32_t *r, bool valid, int n,
@@ -196,36 +228,7 @@ __device__ __forceinline__ void epi_nhwc_chunk32(const ConvEpi &epi, const ConvT
         if (co + j < g.Cout) *reinterpret_cast<float4 *>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
     }
   }
-  if (epi.qstats) {
-    // per-quad (4-channel) sums over the 32 pixels of this warp: reduce-scatter butterfly (8 -> 4 -> 2 -> 1 values
-    // per lane over xor 16/8/4, then plain xor 2/1), 18 shuffles per 32-column chunk; fp64 atomics per quad.
-    float a4[4], b4[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float s_send = (lane & 16) ? qs[i] : qs[i + 4], s_keep = (lane & 16) ? qs[i + 4] : qs[i];
-      float q_send = (lane & 16) ? qq[i] : qq[i + 4], q_keep = (lane & 16) ? qq[i + 4] : qq[i];
-      a4[i] = s_keep + __shfl_xor_sync(0xffffffffu, s_send, 16);
-      b4[i] = q_keep + __shfl_xor_sync(0xffffffffu, q_send, 16);
-    }
-    float a2[2], b2[2];
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      float s_send = (lane & 8) ? a4[i] : a4[i + 2], s_keep = (lane & 8) ? a4[i + 2] : a4[i];
-      float q_send = (lane & 8) ? b4[i] : b4[i + 2], q_keep = (lane & 8) ? b4[i + 2] : b4[i];
-      a2[i] = s_keep + __shfl_xor_sync(0xffffffffu, s_send, 8);
-      b2[i] = q_keep + __shfl_xor_sync(0xffffffffu, q_send, 8);
-    }
-    float s1 = ((lane & 4) ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, (lane & 4) ? a2[0] : a2[1], 4);
-    float q1 = ((lane & 4) ? b2[1] : b2[0]) + __shfl_xor_sync(0xffffffffu, (lane & 4) ? b2[0] : b2[1], 4);
-    s1 += __shfl_xor_sync(0xffffffffu, s1, 2); q1 += __shfl_xor_sync(0xffffffffu, q1, 2);
-    s1 += __shfl_xor_sync(0xffffffffu, s1, 1); q1 += __shfl_xor_sync(0xffffffffu, q1, 1);
-    const int quad = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-    if ((lane & 3) == 0 && warp_img_ok && co + quad * 4 < g.Cout) {
-      double *qp = epi.qstats + ((int64_t)n * (g.Cout >> 2) + (co >> 2) + quad) * 2;
-      atomicAdd(qp, (double)s1);
-      atomicAdd(qp + 1, (double)q1);
-    }
-  }
+  if (epi.qstats) warp_quad_stats(qs, qq, lane, warp_img_ok, epi.qstats, n, g.Cout, co);
 }
 
 template <int BN, int STAGES>
@@ -366,7 +369,8 @@ constexpr int V2_B_BYTES = 3 * 128 * 128;            // 3 vertical taps x (128 c
 constexpr int V2_STAGE_BYTES = V2_A_BYTES + V2_B_BYTES;   // 86,016 B
 constexpr int V2_STAGES = 2;
 constexpr int V2_THREADS = 320;                       // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
-constexpr int V2_SMEM = V2_STAGES * V2_STAGE_BYTES + 1024 + 256;
+constexpr int V2_STG_BYTES = 8 * 4096;                // per-epilogue-warp 32 x 128 B transpose buffers
+constexpr int V2_SMEM = V2_STAGES * V2_STAGE_BYTES + V2_STG_BYTES + 1024 + 256;
 
 struct ConvV2Geom {
   int B, H, W, Cin, Cout;
@@ -390,7 +394,8 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_conv3x3_v2(const __grid_const
   constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t *full = reinterpret_cast<uint64_t *>(smem + V2_STAGES * V2_STAGE_BYTES);
+  uint8_t *stg_base = smem + V2_STAGES * V2_STAGE_BYTES;
+  uint64_t *full = reinterpret_cast<uint64_t *>(stg_base + V2_STG_BYTES);
   uint64_t *empty = full + V2_STAGES;
   uint64_t *tmem_full = empty + V2_STAGES;     // [2]
   uint64_t *tmem_empty = tmem_full + 2;        // [2]
@@ -486,29 +491,128 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_conv3x3_v2(const __grid_const
       }
     }
   } else {
+    // ---------------------------------------------------------------- epilogue: 8 warps, coalesced through shared memory
+    // A lane owns one pixel row of the accumulator (TMEM lane), but a pixel's channels are what is contiguous in NHWC:
+    // writing row-per-lane touches 32 different 128 B lines per instruction.  Each warp therefore transposes 32 rows x 128 B
+    // through a private XOR-swizzled buffer (16 B column c of row r at c ^ (r & 7): conflict-free both ways) so that global
+    // loads/stores are issued with 8 consecutive lanes covering one full 128 B line (4 lines per instruction).
     const int ew = warp - 2;              // 0..7
     const int q = warp & 3;               // TMEM lane quarter accessible to this warp
     const int sub = ew >> 2;              // which 128-row sub-tile
-    const int row = q * 32 + lane;        // row inside the sub-tile: 8 image rows x 16 cols
-    ConvTcGeom gg;
-    gg.B = g.B; gg.H = g.H; gg.W = g.W; gg.Cin = g.Cin; gg.Cout = g.Cout;
+    float4 *stg = reinterpret_cast<float4 *>(stg_base + ew * 4096);
+    const int tr = lane >> 3, tcn = lane & 7;     // transposed role: row (4i + tr), 16-byte column tcn
     uint32_t tc = 0;
     for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++tc) {
       const uint32_t ab = tc & 1u, aph = (tc >> 1) & 1u;
       int n, h0, w0, co0;
       decode(tile, n, h0, w0, co0);
-      const int yh = h0 + sub * 8 + (row >> 4);
-      const int xw = w0 + (row & 15);
-      const bool valid = (yh < g.H) && (xw < g.W);
+      // pixel of sub-tile row rr (0..31 inside this warp's quarter)
+      auto pix_of = [&](int rr, bool &ok) -> int64_t {
+        const int row = q * 32 + rr;
+        const int yh = h0 + sub * 8 + (row >> 4), xw = w0 + (row & 15);
+        ok = (yh < g.H) && (xw < g.W);
+        return ((int64_t)n * g.H + yh) * g.W + xw;
+      };
+      bool my_ok;
+      (void)pix_of(lane, my_ok);
       mbar_wait(&tmem_full[ab], aph);
       tc_fence_after();
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + ab * 256u + (uint32_t)sub * 128u;
+      if (!epi.out_half) {
 #pragma unroll 1
-      for (int c = 0; c < 128; c += 32) {
-        uint32_t r[32];
-        tmem_ld32(tbase + (uint32_t)c, r);
-        tmem_ld_wait();
-        epi_nhwc_chunk32(epi, gg, r, valid, n, yh, xw, co0 + c, lane, true);
+        for (int c = 0; c < 128; c += 32) {
+          const int co = co0 + c;
+          float4 res[8];
+          if (epi.residual) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rr = 4 * i + tr;
+              bool ok;
+              const int64_t pix = pix_of(rr, ok);
+              float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (ok) v4 = *reinterpret_cast<const float4 *>(epi.residual + pix * g.Cout + co + tcn * 4);
+              stg[rr * 8 + (tcn ^ (rr & 7))] = v4;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) res[j] = stg[lane * 8 + (j ^ (lane & 7))];
+            __syncwarp();
+          }
+          uint32_t r[32];
+          tmem_ld32(tbase + (uint32_t)c, r);
+          tmem_ld_wait();
+          float qs[8], qq[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 b4 = __ldg(reinterpret_cast<const float4 *>(epi.bias + co + 4 * j));
+            if (epi.bias2) {
+              float4 c4 = __ldg(reinterpret_cast<const float4 *>(epi.bias2 + co + 4 * j));
+              b4.x += c4.x; b4.y += c4.y; b4.z += c4.z; b4.w += c4.w;
+            }
+            float4 v4 = make_float4(__uint_as_float(r[4 * j]) + b4.x, __uint_as_float(r[4 * j + 1]) + b4.y,
+                                    __uint_as_float(r[4 * j + 2]) + b4.z, __uint_as_float(r[4 * j + 3]) + b4.w);
+            if (epi.residual) { v4.x += res[j].x; v4.y += res[j].y; v4.z += res[j].z; v4.w += res[j].w; }
+            qs[j] = my_ok ? (v4.x + v4.y) + (v4.z + v4.w) : 0.f;
+            qq[j] = my_ok ? (v4.x * v4.x + v4.y * v4.y) + (v4.z * v4.z + v4.w * v4.w) : 0.f;
+            stg[lane * 8 + (j ^ (lane & 7))] = v4;
+          }
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = 4 * i + tr;
+            bool ok;
+            const int64_t pix = pix_of(rr, ok);
+            if (ok) *reinterpret_cast<float4 *>(epi.out + pix * g.Cout + co + tcn * 4) = stg[rr * 8 + (tcn ^ (rr & 7))];
+          }
+          __syncwarp();
+          if (epi.qstats) warp_quad_stats(qs, qq, lane, true, epi.qstats, n, g.Cout, co);
+        }
+      } else {
+        // fp16 output (conv1 -> GroupNorm -> conv2): 64 columns = 128 B per row per round
+        __half *outh = reinterpret_cast<__half *>(epi.out);
+#pragma unroll 1
+        for (int c = 0; c < 128; c += 64) {
+          const int co = co0 + c;
+#pragma unroll
+          for (int hlf = 0; hlf < 2; ++hlf) {
+            uint32_t r[32];
+            tmem_ld32(tbase + (uint32_t)(c + 32 * hlf), r);
+            tmem_ld_wait();
+            float qs[8], qq[8];
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) {
+              float v[8];
+#pragma unroll
+              for (int u = 0; u < 2; ++u) {
+                float4 b4 = __ldg(reinterpret_cast<const float4 *>(epi.bias + co + 32 * hlf + 4 * (j + u)));
+                v[4 * u + 0] = __uint_as_float(r[4 * (j + u) + 0]) + b4.x;
+                v[4 * u + 1] = __uint_as_float(r[4 * (j + u) + 1]) + b4.y;
+                v[4 * u + 2] = __uint_as_float(r[4 * (j + u) + 2]) + b4.z;
+                v[4 * u + 3] = __uint_as_float(r[4 * (j + u) + 3]) + b4.w;
+                qs[j + u] = my_ok ? (v[4 * u] + v[4 * u + 1]) + (v[4 * u + 2] + v[4 * u + 3]) : 0.f;
+                qq[j + u] = my_ok ? (v[4 * u] * v[4 * u] + v[4 * u + 1] * v[4 * u + 1]) +
+                                        (v[4 * u + 2] * v[4 * u + 2] + v[4 * u + 3] * v[4 * u + 3]) : 0.f;
+              }
+              __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+              __half2 h2 = __floats2half2_rn(v[4], v[5]), h3 = __floats2half2_rn(v[6], v[7]);
+              float4 pk;
+              pk.x = __uint_as_float(*reinterpret_cast<uint32_t *>(&h0)); pk.y = __uint_as_float(*reinterpret_cast<uint32_t *>(&h1));
+              pk.z = __uint_as_float(*reinterpret_cast<uint32_t *>(&h2)); pk.w = __uint_as_float(*reinterpret_cast<uint32_t *>(&h3));
+              const int col16 = 4 * hlf + (j >> 1);      // 16-byte column (8 halves) inside the 128 B row
+              stg[lane * 8 + (col16 ^ (lane & 7))] = pk;
+            }
+            if (epi.qstats) warp_quad_stats(qs, qq, lane, true, epi.qstats, n, g.Cout, co + 32 * hlf);
+          }
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = 4 * i + tr;
+            bool ok;
+            const int64_t pix = pix_of(rr, ok);
+            if (ok) *reinterpret_cast<float4 *>(outh + pix * g.Cout + co + tcn * 8) = stg[rr * 8 + (tcn ^ (rr & 7))];
+          }
+          __syncwarp();
+        }
       }
       tc_fence_before();
       __syncwarp();

@@ -190,6 +190,14 @@ struct GnDev {
   float *raw32;
 };
 
+// FAST: fp16-output pipelines use ex2/rcp approximations (2 ulp, far below the fp16 rounding of the stored value);
+// the fp32 parity mode keeps expf and IEEE division.
+template <bool FAST> __device__ __forceinline__ float silu1(float o) {
+  if (FAST) return __fdividef(o, 1.f + __expf(-o));
+  return o / (1.f + expf(-o));
+}
+
+template <bool FAST>
 __device__ __forceinline__ float4 gn_act(float4 v, float mean, float rstd, float4 g, float4 be, bool has_film, float4 sc,
                                          float4 sh, int silu) {
   float4 o;
@@ -201,10 +209,7 @@ __device__ __forceinline__ float4 gn_act(float4 v, float mean, float rstd, float
     o.x = o.x * (1.f + sc.x) + sh.x; o.y = o.y * (1.f + sc.y) + sh.y;
     o.z = o.z * (1.f + sc.z) + sh.z; o.w = o.w * (1.f + sc.w) + sh.w;
   }
-  if (silu) {
-    o.x = o.x / (1.f + expf(-o.x)); o.y = o.y / (1.f + expf(-o.y));
-    o.z = o.z / (1.f + expf(-o.z)); o.w = o.w / (1.f + expf(-o.w));
-  }
+  if (silu) { o.x = silu1<FAST>(o.x); o.y = silu1<FAST>(o.y); o.z = silu1<FAST>(o.z); o.w = silu1<FAST>(o.w); }
   return o;
 }
 
@@ -215,6 +220,7 @@ constexpr int GN_UNROLL = 4;
 // ACTIVATED values as unet.py:238-241 does: in_rest(x) then h_upd).  MODE up: work pixel = input pixel, written 2x2.
 template <typename T, typename TI, int MODE>
 __global__ void k_gn_apply(GnDev a, T *__restrict__ act, T *__restrict__ rawact) {
+  constexpr bool FAST = sizeof(T) == 2;
   __shared__ float s_mean[32], s_rstd[32];
   int C = a.C1 + a.C2, C4 = C / 4;
   int b = blockIdx.y;
@@ -267,7 +273,7 @@ __global__ void k_gn_apply(GnDev a, T *__restrict__ act, T *__restrict__ rawact)
 #pragma unroll
       for (int u = 0; u < GN_UNROLL; ++u) {
         int64_t o = (obase + p + u * ppb) * C + c4 * 4;
-        Store4<T>::st(act + o, gn_act(v[u], mean, rstd, ga, be, has_film, sc, sh, a.silu));
+        Store4<T>::st(act + o, gn_act<FAST>(v[u], mean, rstd, ga, be, has_film, sc, sh, a.silu));
         if (a.raw32) *reinterpret_cast<float4 *>(a.raw32 + o) = v[u];
         if (rawact) Store4<T>::st(rawact + o, v[u]);
       }
@@ -275,7 +281,7 @@ __global__ void k_gn_apply(GnDev a, T *__restrict__ act, T *__restrict__ rawact)
     for (; p < p1; p += ppb) {
       float4 v = Load4<TI>::ld(src + (int64_t)p * Cs + cc);
       int64_t o = (obase + p) * C + c4 * 4;
-      Store4<T>::st(act + o, gn_act(v, mean, rstd, ga, be, has_film, sc, sh, a.silu));
+      Store4<T>::st(act + o, gn_act<FAST>(v, mean, rstd, ga, be, has_film, sc, sh, a.silu));
       if (a.raw32) *reinterpret_cast<float4 *>(a.raw32 + o) = v;
       if (rawact) Store4<T>::st(rawact + o, v);
     }
@@ -289,7 +295,7 @@ __global__ void k_gn_apply(GnDev a, T *__restrict__ act, T *__restrict__ rawact)
       float4 accA = make_float4(0, 0, 0, 0), accR = accA;
 #pragma unroll
       for (int d = 0; d < 4; ++d) {
-        float4 o = gn_act(v[d], mean, rstd, ga, be, has_film, sc, sh, a.silu);
+        float4 o = gn_act<FAST>(v[d], mean, rstd, ga, be, has_film, sc, sh, a.silu);
         accA.x += o.x; accA.y += o.y; accA.z += o.z; accA.w += o.w;
         accR.x += v[d].x; accR.y += v[d].y; accR.z += v[d].z; accR.w += v[d].w;
       }
@@ -304,7 +310,7 @@ __global__ void k_gn_apply(GnDev a, T *__restrict__ act, T *__restrict__ rawact)
     for (int p = p0 + lane_p; p < p1; p += ppb) {
       int yi = p / W, xi = p % W;
       float4 v = Load4<TI>::ld(src + (int64_t)p * Cs + cc);
-      float4 o = gn_act(v, mean, rstd, ga, be, has_film, sc, sh, a.silu);
+      float4 o = gn_act<FAST>(v, mean, rstd, ga, be, has_film, sc, sh, a.silu);
 #pragma unroll
       for (int d = 0; d < 4; ++d) {
         int64_t q = (obase + (int64_t)(2 * yi + (d >> 1)) * Wo + 2 * xi + (d & 1)) * C + c4 * 4;

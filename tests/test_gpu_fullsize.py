@@ -1,0 +1,92 @@
+"""BASELINE-size checks (256x256, batch 32 / real FFHQ architecture) through size-independent properties and a short
+trajectory against the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from diffpir_b200 import arch, synth
+from dpir_testutil import make_model, psnr, rel_l2, weights
+from oracle import diffpir_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _batch(B=32, size=256, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.rand(B, 3, size, size, generator=g)
+
+
+def test_fft_solver_properties_full_size():
+    """argmin ||y - k*x||^2 + a||x - z||^2 at B=32, 256^2, per-image kernels:
+    (i) consistent data (y = k*z circularly) => solution == z for every a;  (ii) a -> inf => z;
+    (iii) a -> 0 with an invertible blur => inverse-filter solution reproduces y when re-blurred."""
+    from diffpir_b200 import utils_sisr as sr
+    B = 32
+    z = _batch(B).cuda()
+    ks = synth.levin_like_kernels()
+    kmax = max(k.shape[0] for k in ks)
+    kt = torch.zeros(B, 1, kmax, kmax)
+    for b in range(B):
+        k = ks[b % len(ks)]
+        o = (kmax - k.shape[0]) // 2
+        kt[b, 0, o:o + k.shape[0], o:o + k.shape[1]] = torch.from_numpy(k)
+    kt = kt.cuda()
+    FB, FBC, F2B, FBFy0 = sr.pre_calculate(z, kt, 1)
+    # circular blur of z through the same OTF
+    y = torch.fft.irfft2(FB * torch.fft.rfft2(z), s=(256, 256)).contiguous()
+    t = sr.pre_calculate(y, kt, 1)
+    for a in (1e-4, 0.1, 50.0):
+        out = sr.data_solution(z, *t, a, 1)
+        assert rel_l2(out, z) < 2e-5, a
+    other = _batch(B, seed=1).cuda()
+    assert rel_l2(sr.data_solution(other, *t, 1e7, 1), other) < 1e-5
+    inv = sr.data_solution(other, *t, 1e-7, 1)
+    reblur = torch.fft.irfft2(FB * torch.fft.rfft2(inv), s=(256, 256))
+    assert rel_l2(reblur, y) < 1e-3
+
+
+def test_inpaint_and_renoise_properties_full_size():
+    from diffpir_b200 import ops
+    B = 64
+    x0 = (_batch(B, seed=2) * 2 - 1).cuda()
+    y = _batch(B, seed=3).cuda()
+    mask = synth.random_mask(B, 256, 0.5, seed=4).cuda()
+    out = ops.inpaint_prox(x0, y, mask, 1e-3)
+    hole = mask == 0
+    assert torch.equal(out[hole], x0[hole])                    # unknown pixels untouched (bit-exact)
+    assert float((out[~hole] - (2 * y - 1)[~hole]).abs().max()) < 3e-3   # known pixels pulled to the data (tau small)
+    assert torch.equal(ops.inpaint_prox(out, y, mask, 1e-3)[hole], out[hole])
+    # renoise with zero noise and eps-consistency: x = sa*x0 + s1*e  ->  out = sa_p*x0 + c_eps*e
+    e = torch.randn_like(x0)
+    x = 0.8 * x0 + 0.6 * e
+    out = ops.renoise(x, x0, torch.zeros_like(x0), 0.8, 0.6, 0.9, 0.3, 0.0)
+    assert rel_l2(out, 0.9 * x0 + 0.3 * e) < 1e-6
+
+
+def test_ffhq_deblur_trajectory_matches_oracle():
+    """BASELINE config-2 shape (FFHQ architecture, 256x256, Levin-size kernels, sigma 12.75/255, lambda 7, zeta 0.3) for
+    3 NFE on 2 images, fp16 tensor-core path, pre-drawn noise; oracle evaluated in fp64."""
+    from diffpir_b200.sampler import DiffPIRSampler
+    cfg = arch.ffhq_config()
+    sd = weights(cfg)
+    B, iters = 2, 3
+    imgs = synth.synthetic_images(B, 256, seed=21)
+    gt = torch.from_numpy(imgs).permute(0, 3, 1, 2).float() / 255.0
+    ks = synth.levin_like_kernels()[:B]
+    kmax = max(k.shape[0] for k in ks)
+    kt = torch.zeros(B, 1, kmax, kmax)
+    ys = []
+    for b in range(B):
+        ys.append(synth.blur_measurement(imgs[b], ks[b], 12.75 / 255, seed=b))
+        o = (kmax - ks[b].shape[0]) // 2
+        kt[b, 0, o:o + ks[b].shape[0], o:o + ks[b].shape[1]] = torch.from_numpy(ks[b])
+    y = torch.from_numpy(np.stack(ys)).permute(0, 3, 1, 2).contiguous()
+    init, zs = synth.predrawn_noise((B, 3, 256, 256), iters, seed=11)
+    hp = dict(lambda_=7.0, zeta=0.3, sigma=12.75 / 255)
+    ref = orc.diffpir_loop(sd, cfg.as_dict(), "deblur", y.double(), k=kt.double(), sf=1, iter_num=iters,
+                           init_noise=init.double(), zeta_noise=[z.double() for z in zs], **hp)
+    m = make_model(cfg, "fp16")
+    out = DiffPIRSampler(m, "deblur", iter_num=iters, **hp).run(y.cuda(), k=kt.cuda(), init_noise=init.cuda(),
+                                                                zeta_noise=[z.cuda() for z in zs])
+    assert rel_l2(out, ref) < 1e-2
+    assert abs(psnr(out, gt) - psnr(ref, gt)) < 0.01

@@ -93,3 +93,17 @@ def test_missing_weights_is_an_error():
     assert m.missing_weights() > 0
     with pytest.raises(RuntimeError):
         m(torch.zeros(1, 3, 64, 64, device="cuda"), torch.zeros(1, dtype=torch.long, device="cuda"))
+
+
+def test_imagenet_unet_forward_matches_oracle():
+    """The 256x256_diffusion_uncond architecture (552 M parameters, 16 attention blocks, T up to 1024), one image."""
+    from diffpir_b200 import arch
+    cfg = arch.imagenet_config()
+    sd = weights(cfg)
+    x, _ = _inputs(1, 256, seed=5)
+    t = torch.tensor([77])
+    ref = unet_oracle.unet_forward(sd, cfg.as_dict(), x, t)
+    m = make_model(cfg, "fp16")
+    out = m(x.cuda(), t.cuda())
+    err = rel_l2(out, ref)
+    assert err < TOL["fp16"], err
