@@ -39,6 +39,7 @@ SIGNATURES = {
     "dpir_unet_x0": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),
     "dpir_workspace_bytes": (c_int64, [c_void_p]),
     "dpir_set_graph_mode": (c_int32, [c_void_p, c_int32]),
+    "dpir_set_film_table": (c_int32, [c_void_p, c_int32]),
     "dpir_profile_begin": (c_int32, [c_void_p]),
     "dpir_profile_end": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32]),
     "dpir_fft_plan_create": (c_int32, [c_int32, c_int32, c_int32, POINTER(c_void_p)]),

@@ -66,6 +66,7 @@ struct Op {
   const void *w = nullptr;                                   // absolute pointer into the weight arena
   const void *w2 = nullptr;                                  // fused 1x1 skip weights (arena) for the persistent 3x3 kernel
   int Cin2 = 0;                                              // channels of the fused skip operand (p2)
+  int film_row = -1;                                         // GN apply with FiLM: first row in the FiLM matrix
   size_t bytes = 0;
   int B = 0, H = 0, W = 0, C1 = 0, C2 = 0, Cin = 0, Cout = 0, ldw = 0, ksize = 0, heads = 0, HW = 0, out_half = 0;
   ConvTcPlan *tc = nullptr;
@@ -147,6 +148,11 @@ struct dpir_engine {
   size_t ws_bytes = 0;
   std::map<std::tuple<int, int, int>, std::unique_ptr<Plan>> plans;
   int graph_mode = 0;
+  // FiLM table: (scale, shift) of every ResBlock for every integer timestep, computed once from the loaded weights
+  // (emb_layers(SiLU(time_embed(timestep_embedding(t)))) depends on t only) -> zero embedding work per forward
+  int use_film_table = 1;
+  float *film_table = nullptr;     // [diffusion_steps][film_rows]
+  bool film_table_valid = false;
   // per-op CUDA-event profiler (bench / roofline accounting): events recorded on the launch stream around every op
   bool profiling = false;
   std::vector<cudaEvent_t> prof_events;      // pairs
@@ -420,6 +426,7 @@ struct PlanBuilder {
     a.gamma = e->ap<float>(nw.g_off); a.beta = e->ap<float>(nw.b_off);
     a.film = film_row >= 0 ? wp<float>(film_off + (size_t)film_row * 4) : nullptr;
     a.film_stride = e->film_rows;
+    ap.film_row = film_row;
     a.silu = silu; a.resample = resample; a.B = B; a.H = Hin; a.W = Win; a.out_half = e->half;
     a.act = bp<void>(*act_id);
     a.raw32 = want_raw32 ? bp<float>(*raw32_id) : nullptr;
@@ -667,11 +674,13 @@ int run_plan(dpir_engine *e, Plan *plan, const float *x, const int64_t *t, float
         DPIR_CUDA_CHECK(cudaMemsetAsync(op.q0, 0, op.bytes, st));
         break;
       case OP_TIME_EMBED:
+        if (e->use_film_table) break;
         rc = launch_time_embed(t, e->ap<float>(e->freqs_off), e->ap<float>(e->te_w0), e->ap<float>(e->te_b0),
                                e->ap<float>(e->te_w2), e->ap<float>(e->te_b2), (float *)op.q0, (float *)const_cast<void *>(op.p1),
                                op.B, e->cfg.model_channels, e->ted, st);
         break;
       case OP_FILM:
+        if (e->use_film_table) break;
         rc = launch_linear_rows((const float *)op.p0, e->ap<float>(e->film_w), e->ap<float>(e->film_b), (float *)op.q0, op.B,
                                 e->ted, e->film_rows, 0, 0, st);
         break;
@@ -683,7 +692,14 @@ int run_plan(dpir_engine *e, Plan *plan, const float *x, const int64_t *t, float
         rc = launch_gn_stats((const float *)op.p0, op.C1, (double *)op.q0, op.B, op.HW, st);
         break;
       case OP_GN_APPLY:
-        rc = launch_gn_apply(op.gn, st);
+        if (op.film_row >= 0 && e->use_film_table) {
+          GnApplyArgs ga = op.gn;
+          ga.film = e->film_table + op.film_row;
+          ga.tsteps = t;
+          rc = launch_gn_apply(ga, st);
+        } else {
+          rc = launch_gn_apply(op.gn, st);
+        }
         break;
       case OP_CONV: {
         ConvEpi epi = op.epi;
@@ -731,12 +747,41 @@ int ensure_graph_staging(dpir_engine *e, int B, int H, int W) {
   return DPIR_OK;
 }
 
+int build_film_table(dpir_engine *e, cudaStream_t st) {
+  const int T = e->cfg.diffusion_steps, ted = e->ted;
+  if (!e->film_table) {
+    cudaError_t ce = cudaMalloc(&e->film_table, (size_t)T * e->film_rows * sizeof(float));
+    if (ce != cudaSuccess) { set_error("FiLM table cudaMalloc failed: %s", cudaGetErrorString(ce)); return DPIR_E_NOMEM; }
+  }
+  int64_t *tt = nullptr;
+  float *hidden = nullptr, *emb = nullptr;
+  DPIR_CUDA_CHECK(cudaMalloc(&tt, (size_t)T * sizeof(int64_t)));
+  DPIR_CUDA_CHECK(cudaMalloc(&hidden, (size_t)T * ted * sizeof(float)));
+  DPIR_CUDA_CHECK(cudaMalloc(&emb, (size_t)T * ted * sizeof(float)));
+  std::vector<int64_t> ht(T);
+  for (int i = 0; i < T; ++i) ht[i] = i;
+  DPIR_CUDA_CHECK(cudaMemcpyAsync(tt, ht.data(), (size_t)T * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  int rc = launch_time_embed(tt, e->ap<float>(e->freqs_off), e->ap<float>(e->te_w0), e->ap<float>(e->te_b0),
+                             e->ap<float>(e->te_w2), e->ap<float>(e->te_b2), hidden, emb, T, e->cfg.model_channels, ted, st);
+  if (!rc) rc = launch_linear_rows(emb, e->ap<float>(e->film_w), e->ap<float>(e->film_b), e->film_table, T, ted, e->film_rows, 0, 0, st);
+  DPIR_CUDA_CHECK(cudaStreamSynchronize(st));
+  cudaFree(tt); cudaFree(hidden); cudaFree(emb);
+  if (rc) return rc;
+  e->film_table_valid = true;
+  return DPIR_OK;
+}
+
 int forward_impl(dpir_engine *e, const float *x, const int64_t *t, float *out, int B, int H, int W, int mode, void *stream) {
   DPIR_REQUIRE(e && x && t && out, "unet forward: null pointer");
   if (dpir_missing_weights(e) != 0) { set_error("unet forward: %d checkpoint tensors not loaded", dpir_missing_weights(e)); return DPIR_E_STATE; }
   cudaStream_t st = (cudaStream_t)stream;
   Plan *plan = nullptr;
-  int rc = get_plan(e, B, H, W, &plan);
+  int rc = DPIR_OK;
+  if (e->use_film_table && !e->film_table_valid) {
+    rc = build_film_table(e, st);
+    if (rc) return rc;
+  }
+  rc = get_plan(e, B, H, W, &plan);
   if (rc) return rc;
   if (!e->graph_mode || e->profiling) return run_plan(e, plan, x, t, out, mode, st);
 
@@ -775,7 +820,11 @@ int forward_impl(dpir_engine *e, const float *x, const int64_t *t, float *out, i
   }
   DPIR_CUDA_CHECK(cudaGraphLaunch(gexec, gs));
   // count the kernels the graph replays (same tape)
-  for (Op &op : plan->ops) g_launch_count += (op.kind == OP_MEMSET ? 0 : (op.kind == OP_TIME_EMBED ? 2 : 1));
+  for (Op &op : plan->ops) {
+    if (op.kind == OP_MEMSET) continue;
+    if (op.kind == OP_TIME_EMBED || op.kind == OP_FILM) { g_launch_count += e->use_film_table ? 0 : (op.kind == OP_TIME_EMBED ? 2 : 1); continue; }
+    g_launch_count += 1;
+  }
   DPIR_CUDA_CHECK(cudaMemcpyAsync(out, e->g_out, xout, cudaMemcpyDeviceToDevice, gs));
   DPIR_CUDA_CHECK(cudaEventRecord(e->ev_out, gs));
   DPIR_CUDA_CHECK(cudaStreamWaitEvent(st, e->ev_out, 0));
@@ -817,6 +866,7 @@ int dpir_destroy(dpir_engine *e) {
   cudaDeviceSynchronize();
   e->plans.clear();
   if (e->arena) cudaFree(e->arena);
+  if (e->film_table) cudaFree(e->film_table);
   if (e->ws) cudaFree(e->ws);
   if (e->g_x) { cudaFree(e->g_x); cudaFree(e->g_out); cudaFree(e->g_t); }
   if (e->gstream) { cudaStreamDestroy(e->gstream); cudaEventDestroy(e->ev_in); cudaEventDestroy(e->ev_out); }
@@ -870,6 +920,7 @@ int dpir_load_weight(dpir_engine *e, const char *name, const float *data, const 
     }
   }
   s.loaded = true;
+  e->film_table_valid = false;
   return DPIR_OK;
 }
 
@@ -890,6 +941,7 @@ int dpir_weight_arena(dpir_engine *e, void **dev_ptr, size_t *bytes) {
 int dpir_mark_weights_loaded(dpir_engine *e) {
   DPIR_REQUIRE(e, "dpir_mark_weights_loaded: null engine");
   for (auto &kv : e->slots) kv.second.loaded = true;
+  e->film_table_valid = false;
   return DPIR_OK;
 }
 
@@ -898,6 +950,7 @@ int dpir_set_tables(dpir_engine *e, const float *freqs, int32_t n_freqs, const f
   if (freqs) {
     DPIR_REQUIRE(n_freqs == e->cfg.model_channels / 2, "dpir_set_tables: need model_channels/2 frequencies");
     DPIR_CUDA_CHECK(cudaMemcpy(e->arena + e->freqs_off, freqs, (size_t)n_freqs * 4, cudaMemcpyHostToDevice));
+    e->film_table_valid = false;
   }
   if (coef) {
     DPIR_REQUIRE(T == e->cfg.diffusion_steps, "dpir_set_tables: coefficient table must have diffusion_steps rows");
@@ -916,6 +969,19 @@ int dpir_unet_x0(dpir_engine *e, const float *x, const int64_t *t, float *x0, in
 }
 
 int64_t dpir_workspace_bytes(dpir_engine *e) { return e ? (int64_t)e->ws_bytes : 0; }
+
+int dpir_set_film_table(dpir_engine *e, int32_t enable) {
+  DPIR_REQUIRE(e, "dpir_set_film_table: null engine");
+  if ((e->use_film_table != 0) != (enable != 0)) {
+    // captured graphs bake the choice in: drop them
+    for (auto &kv : e->plans) {
+      if (kv.second->graph_nchw) { cudaGraphExecDestroy(kv.second->graph_nchw); kv.second->graph_nchw = nullptr; }
+      if (kv.second->graph_x0) { cudaGraphExecDestroy(kv.second->graph_x0); kv.second->graph_x0 = nullptr; }
+    }
+  }
+  e->use_film_table = enable ? 1 : 0;
+  return DPIR_OK;
+}
 
 int dpir_set_graph_mode(dpir_engine *e, int32_t enable) {
   DPIR_REQUIRE(e, "dpir_set_graph_mode: null engine");

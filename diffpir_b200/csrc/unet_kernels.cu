@@ -185,7 +185,7 @@ template <> struct Load4<__half> {
 struct GnDev {
   const void *s1; int C1; const void *s2; int C2;
   const double *q1, *q2;             // quad statistics of the two sources
-  const float *gamma, *beta; const float *film; int film_stride;
+  const float *gamma, *beta; const float *film; int film_stride; const int64_t *tsteps;
   int silu, H, W;
   float *raw32;
 };
@@ -251,7 +251,7 @@ __global__ void k_gn_apply(GnDev a, T *__restrict__ act, T *__restrict__ rawact)
   bool has_film = a.film != nullptr;
   float4 sc = make_float4(0, 0, 0, 0), sh = sc;
   if (has_film) {
-    const float *f = a.film + (int64_t)b * a.film_stride;
+    const float *f = a.film + (a.tsteps ? a.tsteps[b] : (int64_t)b) * a.film_stride;
     sc = reinterpret_cast<const float4 *>(f)[c4];
     sh = reinterpret_cast<const float4 *>(f + C)[c4];
   }
@@ -327,7 +327,7 @@ int launch_gn_apply(const GnApplyArgs &a, cudaStream_t st) {
   DPIR_REQUIRE(C % 128 == 0 && a.C1 % 4 == 0 && C <= 4096, "gn_apply: channels must be a multiple of 128 (got %d)", C);
   DPIR_REQUIRE(a.resample != RS_DOWN || (a.H % 2 == 0 && a.W % 2 == 0), "gn_apply: downsample needs even H, W");
   DPIR_REQUIRE(!a.src_half || (a.C2 == 0 && a.out_half), "gn_apply: fp16 source only for a single-source fp16 pipeline");
-  GnDev d{a.src1, a.C1, a.src2, a.C2, a.q1, a.q2, a.gamma, a.beta, a.film, a.film_stride, a.silu, a.H, a.W, a.raw32};
+  GnDev d{a.src1, a.C1, a.src2, a.C2, a.q1, a.q2, a.gamma, a.beta, a.film, a.film_stride, a.tsteps, a.silu, a.H, a.W, a.raw32};
   int nwork = (a.resample == RS_DOWN) ? (a.H / 2) * (a.W / 2) : a.H * a.W;
   dim3 grid(cdiv(nwork, GN_APPLY_PIX), a.B);
   int threads = gn_threads(C);

@@ -14,7 +14,8 @@ struct GnApplyArgs {
   int src_half;                       // 1: src1 is __half (single source)
   const double *q1, *q2;              // per-tensor quad statistics [B][C/4][2] (sum, sumsq) of src1 / src2
   const float *gamma, *beta;          // [C]
-  const float *film; int film_stride; // per-sample (scale[C], shift[C]) at film + b*film_stride, or null
+  const float *film; int film_stride; // per-sample (scale[C], shift[C]) at film + idx*film_stride, or null;
+  const int64_t *tsteps;              // idx = tsteps[b] (film is the per-timestep table) when non-null, else idx = b
   int silu;                           // apply SiLU after the affine/FiLM
   int resample;                       // Resample
   int B, H, W;                        // input spatial size

@@ -121,6 +121,11 @@ class UNetModel:
     def set_graph_mode(self, enable=True):
         _lib.check(self._lib.dpir_set_graph_mode(self._h, int(enable)), "dpir_set_graph_mode")
 
+    def set_film_table(self, enable=True):
+        """True (default): per-timestep FiLM table (integer timesteps in [0, diffusion_steps)); False: evaluate the embedding
+        MLPs per call (arbitrary timesteps)."""
+        _lib.check(self._lib.dpir_set_film_table(self._h, int(enable)), "dpir_set_film_table")
+
     def _prep(self, x, timesteps):
         _lib.require_cuda(x)
         if x.dtype != torch.float32:

@@ -100,6 +100,11 @@ int dpir_unet_x0(dpir_engine *e, const float *x, const int64_t *t, float *x0,
                  int32_t B, int32_t H, int32_t W, void *stream);
 /* workspace bytes currently held for activations (diagnostics) */
 int64_t dpir_workspace_bytes(dpir_engine *e);
+/* 1 (default) => the FiLM (scale, shift) vectors of all ResBlocks are tabulated once for every integer timestep
+ * 0..diffusion_steps-1 from the loaded weights, so a forward does no embedding work; timesteps must then be integers in
+ * that range (what DiffPIR passes: utils_model.py:215-217).  0 => evaluate timestep_embedding / time_embed / emb_layers
+ * (nn.py:103-121, unet.py:471-475, 199-205) per call for arbitrary timesteps. */
+int dpir_set_film_table(dpir_engine *e, int32_t enable);
 /* 1 => replay the forward from a captured CUDA graph (per batch shape) instead of stream launches */
 int dpir_set_graph_mode(dpir_engine *e, int32_t enable);
 

@@ -206,7 +206,34 @@ def gen_loops(iters=6):
     return res
 
 
-FILES = {"unet_small.npz": gen_unet_small, "unet_ffhq.npz": gen_unet_ffhq, "sisr.npz": gen_sisr,
+def fake_model_fn(x, noise_level, model_diffusion=None, vec_t=None, model_out_type="pred_xstart", diffusion=None,
+                  ddim_sample=False, alphas_cumprod=None, **kw):
+    """Deterministic, position-sensitive stand-in for utils_model.model_fn (an asymmetric 3x3 depthwise filter), used to
+    pin the test-time wrappers of utils_model.test_mode without a network."""
+    k = torch.tensor([[0.1, 0.3, -0.2], [0.5, 1.0, 0.05], [-0.4, 0.2, 0.15]]).view(1, 1, 3, 3).repeat(3, 1, 1, 1)
+    return torch.nn.functional.conv2d(x, k.to(x), padding=1, groups=3) * (1.0 + float(noise_level) / 255.0)
+
+
+TEST_MODE_CASES = [dict(mode=0), dict(mode=1, modulo=32), dict(mode=2, refield=16, min_size=48, modulo=16),
+                   dict(mode=3, modulo=16), dict(mode=4, refield=16, min_size=48, modulo=16),
+                   dict(mode=5, refield=16, min_size=48)]
+
+
+def test_mode_input():
+    return torch.rand(2, 3, 96, 80, generator=torch.Generator().manual_seed(15))
+
+
+def gen_test_mode():
+    ref_shim.install()
+    from utils import utils_model
+    x = test_mode_input()
+    res = {}
+    for i, kw in enumerate(TEST_MODE_CASES):
+        res[f"case{i}"] = utils_model.test_mode(fake_model_fn, None, x, noise_level=12.0, **kw).numpy()
+    return res
+
+
+FILES = {"test_mode.npz": gen_test_mode, "unet_small.npz": gen_unet_small, "unet_ffhq.npz": gen_unet_ffhq, "sisr.npz": gen_sisr,
          "misc.npz": gen_misc, "loops.npz": gen_loops}
 
 

@@ -78,3 +78,23 @@ def test_loop_matches_oracle(task, sf, hp, precision):
     assert abs(psnr(out, gt) - psnr(ref, gt)) < 0.01
     if precision == "fp32":
         assert worst < 5e-4, worst
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_sr_cubic_ibp_loop_matches_oracle(precision):
+    """sr_mode='cubic': iterative back-projection through the bicubic Resizer (main_ddpir.py:401-406)."""
+    from diffpir_b200.sampler import DiffPIRSampler
+    cfg = small_config()
+    sd = weights(cfg)
+    B, size, sf, iters = 2, 64, 4, 6
+    gt, _, _, _ = _setup("inpaint", B, size)
+    y = orc.resizer_forward(gt, 1.0 / sf)
+    init, zs = synth.predrawn_noise((B, 3, size, size), iters, seed=9)
+    x_init = torch.nn.functional.interpolate(y, scale_factor=sf, mode="bicubic", align_corners=False)
+    hp = dict(lambda_=6.0, zeta=0.25, sigma=0.05)
+    ref = orc.diffpir_loop(sd, cfg.as_dict(), "sr", y.double(), sf=sf, iter_num=iters, init_noise=init.double(),
+                           zeta_noise=[z.double() for z in zs], x_init=x_init.double(), sr_mode="cubic", gamma=0.01, **hp)
+    m = make_model(cfg, precision)
+    s = DiffPIRSampler(m, "sr", sf=sf, iter_num=iters, sr_mode="cubic", gamma=0.01, **hp)
+    out = s.run(y.cuda(), x_init=x_init.cuda(), init_noise=init.cuda(), zeta_noise=[z.cuda() for z in zs])
+    assert rel_l2(out, ref) < (1e-4 if precision == "fp32" else 1e-2)

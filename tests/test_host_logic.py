@@ -80,3 +80,28 @@ def test_masks():
     assert int((m[0, 0] == 0).sum()) == 64 * 64 // 2 and torch.equal(m[:, 0], m[:, 2])
     b = synth.box_mask(2, 256, 128, seed=2)
     assert int((b[0, 0] == 0).sum()) == 128 * 128
+
+
+def test_test_mode_wrappers_match_reference_golden():
+    """utils_model.test_mode modes 0-5 (pad / split / x8 / split+x8 / split once) against outputs of the reference's own
+    test_mode driven by the same deterministic stand-in model_fn (oracle/gen_golden.py::gen_test_mode)."""
+    import os
+    from diffpir_b200 import utils_model
+    from oracle import gen_golden
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "test_mode.npz"))
+    x = gen_golden.test_mode_input()
+    for i, kw in enumerate(gen_golden.TEST_MODE_CASES):
+        out = utils_model.test_mode(gen_golden.fake_model_fn, None, x, noise_level=12.0, **kw)
+        ref = torch.from_numpy(g[f"case{i}"])
+        assert out.shape == ref.shape, (i, out.shape, ref.shape)
+        assert float((out - ref).abs().max()) < 1e-6, i
+
+
+def test_find_nearest_and_model_fn_argument_errors():
+    from diffpir_b200 import utils_model
+    arr = torch.tensor([0.1, 0.5, 0.9])
+    assert utils_model.find_nearest(arr, 0.45) == 1 and utils_model.find_nearest(arr.numpy(), 2.0) == 2
+    import pytest
+    with pytest.raises(RuntimeError):
+        utils_model.model_fn(torch.zeros(1, 3, 8, 8), 10.0, model_diffusion=object(), model_out_type="pred_x_prev",
+                             diffusion=None, alphas_cumprod=torch.linspace(0.99, 0.01, 1000))
