@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libdiffpir_b200.so")
 
 PRECISION_FP32 = 0
 PRECISION_FP16 = 1
+PRECISION_FP16S = 2
 
 
 class UNetConfigC(ctypes.Structure):

@@ -186,7 +186,8 @@ __device__ __forceinline__ void epi_nhwc_chunk32(const ConvEpi &epi, const ConvT
   for (int j = 0; j < 8; ++j) { qs[j] = 0.f; qq[j] = 0.f; }
   if (valid) {
     const int64_t pix = ((int64_t)n * g.H + yh) * g.W + xw;
-    const float *rs = epi.residual ? epi.residual + pix * g.Cout + co : nullptr;
+    const float *rs = (epi.residual && !epi.res_half) ? epi.residual + pix * g.Cout + co : nullptr;
+    const __half *rsh = (epi.residual && epi.res_half) ? reinterpret_cast<const __half *>(epi.residual) + pix * g.Cout + co : nullptr;
     float v[32];
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
@@ -201,6 +202,10 @@ __device__ __forceinline__ void epi_nhwc_chunk32(const ConvEpi &epi, const ConvT
         if (rs) {
           float4 rv = *reinterpret_cast<const float4 *>(rs + j);
           v[j] += rv.x; v[j + 1] += rv.y; v[j + 2] += rv.z; v[j + 3] += rv.w;
+        } else if (rsh) {
+          uint2 u = *reinterpret_cast<const uint2 *>(rsh + j);
+          float2 f0 = __half22float2(*reinterpret_cast<__half2 *>(&u.x)), f1 = __half22float2(*reinterpret_cast<__half2 *>(&u.y));
+          v[j] += f0.x; v[j + 1] += f0.y; v[j + 2] += f1.x; v[j + 3] += f1.y;
         }
         qs[j >> 2] = (v[j] + v[j + 1]) + (v[j + 2] + v[j + 3]);
         qq[j >> 2] = (v[j] * v[j] + v[j + 1] * v[j + 1]) + (v[j + 2] * v[j + 2] + v[j + 3] * v[j + 3]);
@@ -570,9 +575,26 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_conv3x3_v2(const __grid_const
       } else {
         // fp16 output (conv1 -> GroupNorm -> conv2): 64 columns = 128 B per row per round
         __half *outh = reinterpret_cast<__half *>(epi.out);
+        const __half *resh = reinterpret_cast<const __half *>(epi.residual);   // fp16 residual stream (res_half) or null
 #pragma unroll 1
         for (int c = 0; c < 128; c += 64) {
           const int co = co0 + c;
+          float4 resp[8];      // this lane's residual row: 8 x (8 halves)
+          if (resh) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rr = 4 * i + tr;
+              bool ok;
+              const int64_t pix = pix_of(rr, ok);
+              float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (ok) v4 = *reinterpret_cast<const float4 *>(resh + pix * g.Cout + co + tcn * 8);
+              stg[rr * 8 + (tcn ^ (rr & 7))] = v4;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) resp[j] = stg[lane * 8 + (j ^ (lane & 7))];
+            __syncwarp();
+          }
 #pragma unroll
           for (int hlf = 0; hlf < 2; ++hlf) {
             uint32_t r[32];
@@ -582,13 +604,28 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_conv3x3_v2(const __grid_const
 #pragma unroll
             for (int j = 0; j < 8; j += 2) {
               float v[8];
+              float rv[8];
+              if (resh) {
+                const float4 pk = resp[4 * hlf + (j >> 1)];
+                uint32_t w0_ = __float_as_uint(pk.x), w1_ = __float_as_uint(pk.y), w2_ = __float_as_uint(pk.z), w3_ = __float_as_uint(pk.w);
+                float2 f0 = __half22float2(*reinterpret_cast<__half2 *>(&w0_)), f1 = __half22float2(*reinterpret_cast<__half2 *>(&w1_));
+                float2 f2 = __half22float2(*reinterpret_cast<__half2 *>(&w2_)), f3 = __half22float2(*reinterpret_cast<__half2 *>(&w3_));
+                rv[0] = f0.x; rv[1] = f0.y; rv[2] = f1.x; rv[3] = f1.y; rv[4] = f2.x; rv[5] = f2.y; rv[6] = f3.x; rv[7] = f3.y;
+              } else {
+#pragma unroll
+                for (int z = 0; z < 8; ++z) rv[z] = 0.f;
+              }
 #pragma unroll
               for (int u = 0; u < 2; ++u) {
                 float4 b4 = __ldg(reinterpret_cast<const float4 *>(epi.bias + co + 32 * hlf + 4 * (j + u)));
-                v[4 * u + 0] = __uint_as_float(r[4 * (j + u) + 0]) + b4.x;
-                v[4 * u + 1] = __uint_as_float(r[4 * (j + u) + 1]) + b4.y;
-                v[4 * u + 2] = __uint_as_float(r[4 * (j + u) + 2]) + b4.z;
-                v[4 * u + 3] = __uint_as_float(r[4 * (j + u) + 3]) + b4.w;
+                if (epi.bias2) {
+                  float4 c4 = __ldg(reinterpret_cast<const float4 *>(epi.bias2 + co + 32 * hlf + 4 * (j + u)));
+                  b4.x += c4.x; b4.y += c4.y; b4.z += c4.z; b4.w += c4.w;
+                }
+                v[4 * u + 0] = __uint_as_float(r[4 * (j + u) + 0]) + b4.x + rv[4 * u + 0];
+                v[4 * u + 1] = __uint_as_float(r[4 * (j + u) + 1]) + b4.y + rv[4 * u + 1];
+                v[4 * u + 2] = __uint_as_float(r[4 * (j + u) + 2]) + b4.z + rv[4 * u + 2];
+                v[4 * u + 3] = __uint_as_float(r[4 * (j + u) + 3]) + b4.w + rv[4 * u + 3];
                 qs[j + u] = my_ok ? (v[4 * u] + v[4 * u + 1]) + (v[4 * u + 2] + v[4 * u + 3]) : 0.f;
                 qq[j + u] = my_ok ? (v[4 * u] * v[4 * u] + v[4 * u + 1] * v[4 * u + 1]) +
                                         (v[4 * u + 2] * v[4 * u + 2] + v[4 * u + 3] * v[4 * u + 3]) : 0.f;
@@ -760,6 +797,8 @@ int launch_conv_tc(const ConvTcPlan *p, const ConvEpi &epi, int Cout, cudaStream
   DPIR_REQUIRE(Cout <= p->CoutPad, "conv_tc: Cout exceeds padded weight rows");
   DPIR_REQUIRE(epi.mode != EPI_NHWC || Cout % 4 == 0, "conv_tc: NHWC epilogue needs Cout %% 4 == 0");
   if (p->v2 && epi.mode == EPI_NHWC) {
+    DPIR_REQUIRE(!epi.residual || (epi.res_half != 0) == (epi.out_half != 0),
+                 "conv_tc: the persistent kernel needs residual and output of the same precision");
     static bool attr_set = false;
     if (!attr_set) {
       DPIR_CUDA_CHECK(cudaFuncSetAttribute(k_conv3x3_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, V2_SMEM));

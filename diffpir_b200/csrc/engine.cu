@@ -132,7 +132,8 @@ struct Pool {
 
 struct dpir_engine {
   dpir_unet_config cfg{};
-  bool half = false;
+  bool half = false;          // tensor-core path (fp16 operands)
+  bool stream_half = false;   // fp16s: the residual stream (block outputs, skip tensors) is stored in fp16 too
   int ted = 0, ch0 = 0;
   std::vector<std::vector<LayerDesc>> inputs, middle, outputs;
   std::map<std::string, ParamSlot> slots;
@@ -399,7 +400,7 @@ struct PlanBuilder {
     const Buf &t = bufs[id];
     Op st;
     st.kind = OP_GN_STATS;
-    st.p0 = bp<float>(id); st.C1 = t.C;
+    st.p0 = bp<float>(id); st.C1 = t.C; st.out_half = t.half ? 1 : 0;
     st.q0 = sp(id); st.B = B; st.HW = t.H * t.W;
     plan->ops.push_back(st);
   }
@@ -412,9 +413,12 @@ struct PlanBuilder {
     int Ho = resample == RS_DOWN ? Hin / 2 : (resample == RS_UP ? Hin * 2 : Hin);
     int Wo = resample == RS_DOWN ? Win / 2 : (resample == RS_UP ? Win * 2 : Win);
     n_norms++;
+    // fp16 stream: the raw (resampled / concatenated) residual copy is fp16 as well and is written through `rawact`
+    const bool raw_as_act = want_raw32 && e->stream_half;
     *act_id = new_buf(B, Ho, Wo, C, e->half);
-    *raw32_id = want_raw32 ? new_buf(B, Ho, Wo, C, false) : -1;
+    *raw32_id = (want_raw32 || raw_as_act) ? new_buf(B, Ho, Wo, C, raw_as_act) : -1;
     *rawact_id = want_rawact ? new_buf(B, Ho, Wo, C, e->half) : -1;
+    if (raw_as_act && want_rawact) { set_error("internal: raw copy requested twice"); err = DPIR_E_STATE; }
     Op ap;
     ap.kind = OP_GN_APPLY;
     GnApplyArgs &a = ap.gn;
@@ -429,8 +433,8 @@ struct PlanBuilder {
     ap.film_row = film_row;
     a.silu = silu; a.resample = resample; a.B = B; a.H = Hin; a.W = Win; a.out_half = e->half;
     a.act = bp<void>(*act_id);
-    a.raw32 = want_raw32 ? bp<float>(*raw32_id) : nullptr;
-    a.rawact = want_rawact ? bp<void>(*rawact_id) : nullptr;
+    a.raw32 = (want_raw32 && !raw_as_act) ? bp<float>(*raw32_id) : nullptr;
+    a.rawact = want_rawact ? bp<void>(*rawact_id) : (raw_as_act ? bp<void>(*raw32_id) : nullptr);
     plan->ops.push_back(ap);
     return DPIR_OK;
   }
@@ -448,6 +452,7 @@ struct PlanBuilder {
     const Buf &a = bufs[act];
     out_half = out_half && e->half;
     *out_id = new_buf(B, a.H, a.W, cw.cout, out_half, want_stats);
+    if (residual >= 0 && bufs[residual].half && !e->half) { set_error("internal: fp16 residual in fp32 mode"); err = DPIR_E_STATE; }
     Op op;
     op.kind = OP_CONV;
     op.p0 = bp<void>(act);
@@ -456,6 +461,7 @@ struct PlanBuilder {
     op.epi.mode = EPI_NHWC;
     op.epi.bias = e->ap<float>(cw.b_off);
     op.epi.residual = residual >= 0 ? bp<float>(residual) : nullptr;
+    op.epi.res_half = (residual >= 0 && bufs[residual].half) ? 1 : 0;
     op.epi.out = bp<float>(*out_id);
     op.epi.out_half = out_half ? 1 : 0;
     op.epi.qstats = (want_stats && e->half) ? sp(*out_id) : nullptr;
@@ -491,14 +497,14 @@ struct PlanBuilder {
     gn(h1, -1, rw.n2, rw.film_row, 1, RS_NONE, false, false, &a2, &d0, &d1);
     release(h1);
     if (rw.has_skip && v2_eligible(a2, rw.c2)) {
-      conv(a2, rw.c2, -1, out, /*want_stats=*/true, false, xraw, &rw.skip);
+      conv(a2, rw.c2, -1, out, /*want_stats=*/true, /*out_half=*/e->stream_half, xraw, &rw.skip);
       release(xraw);
     } else {
       if (rw.has_skip) {
         conv(xraw, rw.skip, -1, &residual);
         release(xraw);
       }
-      conv(a2, rw.c2, residual, out, /*want_stats=*/true);
+      conv(a2, rw.c2, residual, out, /*want_stats=*/true, /*out_half=*/e->stream_half);
       release(residual);
     }
     release(a2);
@@ -520,7 +526,7 @@ struct PlanBuilder {
     op.B = B; op.HW = xb.H * xb.W; op.Cin = l.cin; op.heads = l.heads; op.out_half = e->half;
     plan->ops.push_back(op);
     release(qkv);
-    conv(a, aw.proj, x, out, /*want_stats=*/true);
+    conv(a, aw.proj, x, out, /*want_stats=*/true, /*out_half=*/e->stream_half);
     release(a);
     release(x);
     return DPIR_OK;
@@ -563,8 +569,9 @@ struct PlanBuilder {
     plan->ops.push_back(fl);
 
     std::vector<int> hs;
-    int h = new_buf(B, H, W, e->ch0, false, /*want_stats=*/true);
+    int h = new_buf(B, H, W, e->ch0, e->stream_half, /*want_stats=*/true);
     Op ci; ci.kind = OP_CONV_IN; ci.bind_x = true; ci.q0 = bp<void>(h); ci.B = B; ci.H = H; ci.W = W;
+    ci.out_half = e->stream_half ? 1 : 0;
     plan->ops.push_back(ci);
     emit_stats(h);
     retain(h); hs.push_back(h);
@@ -685,11 +692,11 @@ int run_plan(dpir_engine *e, Plan *plan, const float *x, const int64_t *t, float
                                 e->ted, e->film_rows, 0, 0, st);
         break;
       case OP_CONV_IN:
-        rc = launch_conv_in(x, e->ap<float>(e->stem.w_off), e->ap<float>(e->stem.b_off), (float *)op.q0, op.B, op.H, op.W,
+        rc = launch_conv_in(x, e->ap<float>(e->stem.w_off), e->ap<float>(e->stem.b_off), op.q0, op.out_half, op.B, op.H, op.W,
                             e->stem.cin, e->stem.cout, st);
         break;
       case OP_GN_STATS:
-        rc = launch_gn_stats((const float *)op.p0, op.C1, (double *)op.q0, op.B, op.HW, st);
+        rc = launch_gn_stats(op.p0, op.out_half, op.C1, (double *)op.q0, op.B, op.HW, st);
         break;
       case OP_GN_APPLY:
         if (op.film_row >= 0 && e->use_film_table) {
@@ -838,7 +845,8 @@ extern "C" {
 
 int dpir_create(const dpir_unet_config *cfg, dpir_engine **out) {
   DPIR_REQUIRE(cfg && out, "dpir_create: null pointer");
-  DPIR_REQUIRE(cfg->precision == DPIR_PRECISION_FP32 || cfg->precision == DPIR_PRECISION_FP16, "dpir_create: bad precision");
+  DPIR_REQUIRE(cfg->precision == DPIR_PRECISION_FP32 || cfg->precision == DPIR_PRECISION_FP16 ||
+                   cfg->precision == DPIR_PRECISION_FP16S, "dpir_create: bad precision");
   DPIR_REQUIRE(cfg->diffusion_steps >= 1, "dpir_create: diffusion_steps must be >= 1");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -847,7 +855,8 @@ int dpir_create(const dpir_unet_config *cfg, dpir_engine **out) {
   }
   std::unique_ptr<dpir_engine> e(new dpir_engine());
   e->cfg = *cfg;
-  e->half = cfg->precision == DPIR_PRECISION_FP16;
+  e->half = cfg->precision == DPIR_PRECISION_FP16 || cfg->precision == DPIR_PRECISION_FP16S;
+  e->stream_half = cfg->precision == DPIR_PRECISION_FP16S;
   int rc = build_structure(e.get());
   if (rc) return rc;
   rc = build_params(e.get());

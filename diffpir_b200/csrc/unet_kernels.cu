@@ -13,6 +13,32 @@
 
 namespace dpir {
 
+// =========================================================================================== vector load/store helpers
+template <typename T> struct Store4;
+template <> struct Store4<float> {
+  static __device__ __forceinline__ void st(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
+};
+template <> struct Store4<__half> {
+  static __device__ __forceinline__ void st(__half *p, float4 v) {
+    __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t *>(&a);
+    u.y = *reinterpret_cast<uint32_t *>(&b);
+    *reinterpret_cast<uint2 *>(p) = u;
+  }
+};
+template <typename T> struct Load4;
+template <> struct Load4<float> {
+  static __device__ __forceinline__ float4 ld(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+};
+template <> struct Load4<__half> {
+  static __device__ __forceinline__ float4 ld(const __half *p) {
+    uint2 u = *reinterpret_cast<const uint2 *>(p);
+    float2 a = __half22float2(*reinterpret_cast<__half2 *>(&u.x)), b = __half22float2(*reinterpret_cast<__half2 *>(&u.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+};
+
 // =========================================================================================== input stem
 // input_blocks.0.0: Conv2d(Cin<=4, C, 3, padding=1) reading the caller's NCHW image and writing NHWC fp32.
 // w packed [tap*Cin + ci][Cout].  One CTA = an 8 x 32 pixel tile whose (10 x 34 x CIN) input patch is staged in shared
@@ -21,9 +47,9 @@ namespace dpir {
 // patch per input channel (shared-memory broadcasts, no predication in the inner loop); stores are 512 B contiguous.
 constexpr int CI_TH = 8, CI_TW = 32;
 
-template <int CIN>
+template <int CIN, typename TO>
 __global__ void __launch_bounds__(256) k_conv_in(const float *__restrict__ x, const float *__restrict__ w,
-                                                 const float *__restrict__ bias, float *__restrict__ out, int B, int H, int W,
+                                                 const float *__restrict__ bias, TO *__restrict__ out, int B, int H, int W,
                                                  int Cout) {
   __shared__ float patch[CIN][CI_TH + 2][CI_TW + 2];
   const int tiles_w = (W + CI_TW - 1) / CI_TW, tiles_h = (H + CI_TH - 1) / CI_TH;
@@ -74,22 +100,26 @@ __global__ void __launch_bounds__(256) k_conv_in(const float *__restrict__ x, co
       const int64_t p = ((int64_t)n * H + yh) * W + w0 + xs;
 #pragma unroll
       for (int pxl = 0; pxl < 4; ++pxl)
-        if (w0 + xs + pxl < W) reinterpret_cast<float4 *>(out + (p + pxl) * Cout)[c4] = acc[pxl];
+        if (w0 + xs + pxl < W) Store4<TO>::st(out + (p + pxl) * Cout + c4 * 4, acc[pxl]);
     }
   }
 }
 
-int launch_conv_in(const float *x, const float *w, const float *bias, float *out, int B, int H, int W, int Cin, int Cout,
-                   cudaStream_t st) {
+int launch_conv_in(const float *x, const float *w, const float *bias, void *out, int out_half, int B, int H, int W, int Cin,
+                   int Cout, cudaStream_t st) {
   DPIR_REQUIRE(Cout % 4 == 0, "conv_in: Cout must be a multiple of 4");
   DPIR_REQUIRE(Cin >= 1 && Cin <= 4, "conv_in: Cin must be 1..4");
   int grid = B * cdiv(H, CI_TH) * cdiv(W, CI_TW);
+#define CI_LAUNCH(N)                                                                                      \
+  if (out_half) k_conv_in<N, __half><<<grid, 256, 0, st>>>(x, w, bias, (__half *)out, B, H, W, Cout);     \
+  else k_conv_in<N, float><<<grid, 256, 0, st>>>(x, w, bias, (float *)out, B, H, W, Cout)
   switch (Cin) {
-    case 1: k_conv_in<1><<<grid, 256, 0, st>>>(x, w, bias, out, B, H, W, Cout); break;
-    case 2: k_conv_in<2><<<grid, 256, 0, st>>>(x, w, bias, out, B, H, W, Cout); break;
-    case 3: k_conv_in<3><<<grid, 256, 0, st>>>(x, w, bias, out, B, H, W, Cout); break;
-    default: k_conv_in<4><<<grid, 256, 0, st>>>(x, w, bias, out, B, H, W, Cout); break;
+    case 1: CI_LAUNCH(1); break;
+    case 2: CI_LAUNCH(2); break;
+    case 3: CI_LAUNCH(3); break;
+    default: CI_LAUNCH(4); break;
   }
+#undef CI_LAUNCH
   DPIR_LAUNCH_CHECK();
   return DPIR_OK;
 }
@@ -101,28 +131,29 @@ int launch_conv_in(const float *x, const float *w, const float *bias, float *out
 // straddle the two sources (e.g. 768 = 512 + 256 -> 24 channels per group), folds the quads of its 32 groups on the fly.
 constexpr int GN_PIX_PER_BLOCK = 512;
 
-__global__ void k_gn_stats(const float *__restrict__ src, int C, double *__restrict__ qstats, int HW) {
+template <typename TI>
+__global__ void k_gn_stats(const TI *__restrict__ src, int C, double *__restrict__ qstats, int HW) {
   int C4 = C / 4;
   int ppb = blockDim.x / C4;
   int lane_p = threadIdx.x / C4, c4 = threadIdx.x % C4;
   int b = blockIdx.y;
   int p0 = blockIdx.x * GN_PIX_PER_BLOCK;
   int p1 = min(p0 + GN_PIX_PER_BLOCK, HW);
-  const float *base = src + (int64_t)b * HW * C + c4 * 4;
+  const TI *base = src + (int64_t)b * HW * C + c4 * 4;
   float s = 0.f, ss = 0.f;
   int p = p0 + lane_p;
   for (; p + 3 * ppb < p1; p += 4 * ppb) {
-    float4 v0 = *reinterpret_cast<const float4 *>(base + (int64_t)p * C);
-    float4 v1 = *reinterpret_cast<const float4 *>(base + (int64_t)(p + ppb) * C);
-    float4 v2 = *reinterpret_cast<const float4 *>(base + (int64_t)(p + 2 * ppb) * C);
-    float4 v3 = *reinterpret_cast<const float4 *>(base + (int64_t)(p + 3 * ppb) * C);
+    float4 v0 = Load4<TI>::ld(base + (int64_t)(p + 0 * ppb) * C);
+    float4 v1 = Load4<TI>::ld(base + (int64_t)(p + 1 * ppb) * C);
+    float4 v2 = Load4<TI>::ld(base + (int64_t)(p + 2 * ppb) * C);
+    float4 v3 = Load4<TI>::ld(base + (int64_t)(p + 3 * ppb) * C);
     s += ((v0.x + v0.y) + (v0.z + v0.w)) + ((v1.x + v1.y) + (v1.z + v1.w)) + ((v2.x + v2.y) + (v2.z + v2.w)) +
          ((v3.x + v3.y) + (v3.z + v3.w));
     ss += ((v0.x * v0.x + v0.y * v0.y) + (v0.z * v0.z + v0.w * v0.w)) + ((v1.x * v1.x + v1.y * v1.y) + (v1.z * v1.z + v1.w * v1.w)) +
           ((v2.x * v2.x + v2.y * v2.y) + (v2.z * v2.z + v2.w * v2.w)) + ((v3.x * v3.x + v3.y * v3.y) + (v3.z * v3.z + v3.w * v3.w));
   }
   for (; p < p1; p += ppb) {
-    float4 v = *reinterpret_cast<const float4 *>(base + (int64_t)p * C);
+    float4 v = Load4<TI>::ld(base + (int64_t)p * C);
     s += (v.x + v.y) + (v.z + v.w);
     ss += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
   }
@@ -147,41 +178,18 @@ static inline int gn_threads(int C) {
   return C4 * ppb;
 }
 
-int launch_gn_stats(const float *src, int C, double *qstats, int B, int HW, cudaStream_t st) {
+int launch_gn_stats(const void *src, int src_half, int C, double *qstats, int B, int HW, cudaStream_t st) {
   DPIR_REQUIRE(C % 4 == 0 && C <= 4096, "gn_stats: channels must be a multiple of 4 (got %d)", C);
   dim3 grid(cdiv(HW, GN_PIX_PER_BLOCK), B);
   int threads = gn_threads(C);
-  k_gn_stats<<<grid, threads, (size_t)threads * 2 * sizeof(float), st>>>(src, C, qstats, HW);
+  size_t smem = (size_t)threads * 2 * sizeof(float);
+  if (src_half) k_gn_stats<__half><<<grid, threads, smem, st>>>((const __half *)src, C, qstats, HW);
+  else k_gn_stats<float><<<grid, threads, smem, st>>>((const float *)src, C, qstats, HW);
   DPIR_LAUNCH_CHECK();
   return DPIR_OK;
 }
 
 // =========================================================================================== GroupNorm apply
-template <typename T> struct Store4;
-template <> struct Store4<float> {
-  static __device__ __forceinline__ void st(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
-};
-template <> struct Store4<__half> {
-  static __device__ __forceinline__ void st(__half *p, float4 v) {
-    __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
-    uint2 u;
-    u.x = *reinterpret_cast<uint32_t *>(&a);
-    u.y = *reinterpret_cast<uint32_t *>(&b);
-    *reinterpret_cast<uint2 *>(p) = u;
-  }
-};
-template <typename T> struct Load4;
-template <> struct Load4<float> {
-  static __device__ __forceinline__ float4 ld(const float *p) { return *reinterpret_cast<const float4 *>(p); }
-};
-template <> struct Load4<__half> {
-  static __device__ __forceinline__ float4 ld(const __half *p) {
-    uint2 u = *reinterpret_cast<const uint2 *>(p);
-    float2 a = __half22float2(*reinterpret_cast<__half2 *>(&u.x)), b = __half22float2(*reinterpret_cast<__half2 *>(&u.y));
-    return make_float4(a.x, a.y, b.x, b.y);
-  }
-};
-
 struct GnDev {
   const void *s1; int C1; const void *s2; int C2;
   const double *q1, *q2;             // quad statistics of the two sources
@@ -326,7 +334,8 @@ int launch_gn_apply(const GnApplyArgs &a, cudaStream_t st) {
   int C = a.C1 + a.C2;
   DPIR_REQUIRE(C % 128 == 0 && a.C1 % 4 == 0 && C <= 4096, "gn_apply: channels must be a multiple of 128 (got %d)", C);
   DPIR_REQUIRE(a.resample != RS_DOWN || (a.H % 2 == 0 && a.W % 2 == 0), "gn_apply: downsample needs even H, W");
-  DPIR_REQUIRE(!a.src_half || (a.C2 == 0 && a.out_half), "gn_apply: fp16 source only for a single-source fp16 pipeline");
+  DPIR_REQUIRE(!a.src_half || a.out_half, "gn_apply: fp16 sources only in an fp16 pipeline");
+  DPIR_REQUIRE(!a.src_half || !a.raw32, "gn_apply: fp16 sources produce their raw copy through rawact");
   GnDev d{a.src1, a.C1, a.src2, a.C2, a.q1, a.q2, a.gamma, a.beta, a.film, a.film_stride, a.tsteps, a.silu, a.H, a.W, a.raw32};
   int nwork = (a.resample == RS_DOWN) ? (a.H / 2) * (a.W / 2) : a.H * a.W;
   dim3 grid(cdiv(nwork, GN_APPLY_PIX), a.B);

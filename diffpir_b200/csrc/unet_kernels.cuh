@@ -10,8 +10,8 @@ enum EpiMode { EPI_NHWC = 0, EPI_NCHW = 1, EPI_X0 = 2 };
 
 struct GnApplyArgs {
   const void *src1; int C1;           // fp32 (or fp16 when src_half) NHWC
-  const void *src2; int C2;           // may be null / 0 (fp32 only)
-  int src_half;                       // 1: src1 is __half (single source)
+  const void *src2; int C2;           // may be null / 0; same dtype as src1
+  int src_half;                       // 1: the sources are __half
   const double *q1, *q2;              // per-tensor quad statistics [B][C/4][2] (sum, sumsq) of src1 / src2
   const float *gamma, *beta;          // [C]
   const float *film; int film_stride; // per-sample (scale[C], shift[C]) at film + idx*film_stride, or null;
@@ -29,7 +29,8 @@ struct ConvEpi {
   int mode;                 // EpiMode
   const float *bias;        // [Cout]
   const float *bias2;       // second bias (fused 1x1 skip convolution) or null; tensor-core NHWC epilogue only
-  const float *residual;    // NHWC fp32 [B,H,W,Cout] or null (EPI_NHWC only)
+  const float *residual;    // NHWC [B,H,W,Cout] fp32 (or fp16 when res_half) or null (EPI_NHWC only)
+  int res_half;             // 1: residual is __half (tensor-core epilogues only)
   float *out;               // NHWC [B,H,W,Cout] | NCHW [B,Cout,H,W] | x0 NCHW [B,3,H,W]
   int out_half;             // EPI_NHWC on tensor cores: store __half instead of float (out is then a __half*)
   double *qstats;           // EPI_NHWC on tensor cores: accumulate quad statistics [B][Cout/4][2] of the stored tensor, or null
@@ -73,9 +74,9 @@ __device__ __forceinline__ void conv_epilogue_store(const ConvEpi &e, int n, int
 }
 #endif
 
-int launch_conv_in(const float *x_nchw, const float *w, const float *bias, float *out, int B, int H, int W, int Cin, int Cout,
-                   cudaStream_t st);
-int launch_gn_stats(const float *src, int C, double *qstats, int B, int HW, cudaStream_t st);
+int launch_conv_in(const float *x_nchw, const float *w, const float *bias, void *out, int out_half, int B, int H, int W, int Cin,
+                   int Cout, cudaStream_t st);
+int launch_gn_stats(const void *src, int src_half, int C, double *qstats, int B, int HW, cudaStream_t st);
 int launch_gn_apply(const GnApplyArgs &a, cudaStream_t st);
 int launch_conv_simt(const float *act, const float *w, int ldw, const ConvEpi &epi, int B, int H, int W, int Cin, int Cout,
                      int ksize, cudaStream_t st);

@@ -56,7 +56,7 @@ class UNetModel:
             c.attention_ds[i] = a
         c.num_heads, c.num_head_channels, c.num_heads_upsample = cfg.num_heads, cfg.num_head_channels, cfg.num_heads_upsample
         c.use_new_attention_order = int(cfg.use_new_attention_order)
-        c.precision = {"fp32": _lib.PRECISION_FP32, "fp16": _lib.PRECISION_FP16}[precision]
+        c.precision = {"fp32": _lib.PRECISION_FP32, "fp16": _lib.PRECISION_FP16, "fp16s": _lib.PRECISION_FP16S}[precision]
         c.diffusion_steps = diffusion_steps
         h = ctypes.c_void_p()
         _lib.check(lib.dpir_create(ctypes.byref(c), ctypes.byref(h)), "dpir_create")

@@ -37,7 +37,10 @@ extern "C" {
 #define DPIR_E_NOMEM (-5)
 
 #define DPIR_PRECISION_FP32 0  /* fp32 CUDA-core convolutions: parity mode (<=1e-4 rel-L2 vs reference) */
-#define DPIR_PRECISION_FP16 1  /* fp16 operands, fp32 accumulate on tcgen05 tensor cores: throughput mode */
+#define DPIR_PRECISION_FP16 1  /* fp16 operands, fp32 accumulate on tcgen05 tensor cores; fp32 residual stream */
+#define DPIR_PRECISION_FP16S 2 /* as FP16, and the residual stream / skip tensors are stored in fp16 as well (what the
+                                  reference's own use_fp16=True mode does, unet.py:620-632); GroupNorm statistics, softmax and
+                                  all accumulation stay fp32/fp64: throughput mode */
 
 const char *dpir_last_error(void);
 int dpir_version(void);

@@ -8,7 +8,7 @@ from dpir_testutil import make_model, rel_l2, small_config, weights
 
 pytestmark = pytest.mark.gpu
 
-TOL = {"fp32": 1e-4, "fp16": 4e-3}   # rel-L2 of the eps prediction; fp16 = operand rounding of ~60 chained GEMMs
+TOL = {"fp32": 1e-4, "fp16": 4e-3, "fp16s": 6e-3}   # rel-L2 of the eps prediction; fp16 = operand rounding of ~60 chained GEMMs
 
 
 def _inputs(B, size, seed=0):
@@ -16,7 +16,7 @@ def _inputs(B, size, seed=0):
     return torch.randn(B, 3, size, size, generator=g), torch.randint(0, 1000, (B,), generator=g)
 
 
-@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+@pytest.mark.parametrize("precision", ["fp32", "fp16", "fp16s"])
 def test_small_unet_forward_matches_oracle(precision):
     cfg = small_config()
     sd = weights(cfg)
@@ -26,6 +26,7 @@ def test_small_unet_forward_matches_oracle(precision):
     out = m(x.cuda(), t.cuda())
     assert tuple(out.shape) == (3, 6, 64, 64)
     err = rel_l2(out, ref)
+    print(f"small unet {precision}: rel-L2 {err:.3e}")
     assert err < TOL[precision], err
     # a second batch shape re-plans the workspace; results must not depend on the plan
     out1 = m(x[:1].cuda(), t[:1].cuda())
@@ -34,7 +35,7 @@ def test_small_unet_forward_matches_oracle(precision):
     assert torch.equal(out3, out)
 
 
-@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+@pytest.mark.parametrize("precision", ["fp32", "fp16", "fp16s"])
 def test_small_unet_x0_matches_oracle(precision):
     cfg = small_config()
     sd = weights(cfg)
@@ -46,7 +47,7 @@ def test_small_unet_x0_matches_oracle(precision):
     x0 = m.x0(x.cuda(), t.cuda())
     # before the clamp the error of eps is amplified by sqrt(1/abar - 1) (157 at t=999): compare where not saturated too
     assert float(x0.max()) <= 1 and float(x0.min()) >= -1
-    assert rel_l2(x0, ref) < (2e-4 if precision == "fp32" else 2e-2)
+    assert rel_l2(x0, ref) < (2e-4 if precision == "fp32" else 3e-2)
     # the fused epilogue must agree with the unfused route on the same engine
     from diffpir_b200 import ops
     tabs = orc.diffusion_tables()
@@ -71,7 +72,7 @@ def test_graph_mode_matches_stream_mode():
     assert torch.equal(d, m(x2.cuda(), t2.cuda()))
 
 
-@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+@pytest.mark.parametrize("precision", ["fp32", "fp16", "fp16s"])
 def test_ffhq_unet_forward_matches_oracle(precision):
     """The real diffusion_ffhq_10m architecture at 256x256, one image."""
     from diffpir_b200 import arch
@@ -83,7 +84,18 @@ def test_ffhq_unet_forward_matches_oracle(precision):
     m = make_model(cfg, precision)
     out = m(x.cuda(), t.cuda())
     err = rel_l2(out, ref)
+    print(f"ffhq unet {precision}: rel-L2 {err:.3e}")
     assert err < TOL[precision], err
+
+
+def test_film_table_matches_per_call_embedding():
+    cfg = small_config()
+    x, t = _inputs(3, 64, seed=6)
+    m = make_model(cfg, "fp16")
+    a = m(x.cuda(), t.cuda())
+    m.set_film_table(False)
+    b = m(x.cuda(), t.cuda())
+    assert rel_l2(a, b) < 1e-6
 
 
 def test_missing_weights_is_an_error():
@@ -103,7 +115,10 @@ def test_imagenet_unet_forward_matches_oracle():
     x, _ = _inputs(1, 256, seed=5)
     t = torch.tensor([77])
     ref = unet_oracle.unet_forward(sd, cfg.as_dict(), x, t)
-    m = make_model(cfg, "fp16")
-    out = m(x.cuda(), t.cuda())
-    err = rel_l2(out, ref)
-    assert err < TOL["fp16"], err
+    for precision in ("fp16", "fp16s"):
+        m = make_model(cfg, precision)
+        out = m(x.cuda(), t.cuda())
+        err = rel_l2(out, ref)
+        print(f"imagenet unet {precision}: rel-L2 {err:.3e}")
+        assert err < TOL[precision], err
+        del m
