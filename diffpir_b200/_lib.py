@@ -62,6 +62,11 @@ SIGNATURES = {
     "dpir_ibp_update": (c_int32, [c_void_p, c_void_p, c_void_p, c_float, c_float, c_int32, c_int32, c_int32, c_int32,
                                   c_void_p, c_void_p]),
     "dpir_blur_reflect": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
+    "dpir_tensor2uint": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    "dpir_sqdiff_batch": (c_int32, [c_void_p, c_void_p, c_float, c_float, c_float, c_float, c_int32, c_int32, c_int32, c_int32,
+                                    c_void_p, c_void_p]),
+    "dpir_measure_blur_u8": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
+                                       c_int32, c_int32, c_void_p]),
     "dpir_conv_tc": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
                                c_int32, c_int32, c_int32, c_void_p]),
     "dpir_conv_tc_variant": (c_int32, [c_int32]),

@@ -293,6 +293,100 @@ __global__ void k_blur_reflect(const float *__restrict__ x, const float *__restr
   }
 }
 
+
+// ------------------------------------------------------------------------------------------ output / metrics tail
+// tensor2uint_batch (utils/utils_image.py:238-242): clamp(0,1) * 255, round-half-even (np.round), uint8, NCHW -> NHWC
+__global__ void k_tensor2uint(const float *__restrict__ x, uint8_t *__restrict__ out, int B, int C, int H, int W) {
+  int64_t total = (int64_t)B * C * H * W;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    int64_t p = i / C;                    // output index order: (b, h, w, c)
+    int w = (int)(p % W);
+    int h = (int)((p / W) % H);
+    int b = (int)(p / ((int64_t)W * H));
+    float v = x[(((int64_t)b * C + c) * H + h) * W + w];
+    v = fminf(fmaxf(v, 0.f), 1.f) * 255.0f;
+    out[i] = (uint8_t)__float2int_rn(v);
+  }
+}
+
+// per-image sum of squared differences of (sa*a+ba) and (sb*b+bb); luma != 0: on Y = 0.299R+0.587G+0.114B only
+// (rgb2ycbcr_batch only_y, utils_image.py:470-490).  Block-level warp-shuffle reduction, one fp64 atomic per block.
+__global__ void k_sqdiff(const float *__restrict__ a, const float *__restrict__ b, float sa, float ba, float sb, float bb,
+                         int luma, int C, int HW, double *__restrict__ sse) {
+  int img = blockIdx.y;
+  const float *pa = a + (int64_t)img * C * HW, *pb = b + (int64_t)img * C * HW;
+  float acc = 0.f;
+  if (luma) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+      float ya = 0.299f * (sa * pa[i] + ba) + 0.587f * (sa * pa[HW + i] + ba) + 0.114f * (sa * pa[2 * HW + i] + ba);
+      float yb = 0.299f * (sb * pb[i] + bb) + 0.587f * (sb * pb[HW + i] + bb) + 0.114f * (sb * pb[2 * HW + i] + bb);
+      float d = ya - yb;
+      acc += d * d;
+    }
+  } else {
+    int n = C * HW;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+      float d = (sa * pa[i] + ba) - (sb * pb[i] + bb);
+      acc += d * d;
+    }
+  }
+  __shared__ float red[32];
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if (threadIdx.x == 0) atomicAdd(&sse[img], (double)v);
+  }
+}
+
+// measurement synthesis (main_ddpir.py:97-114): circular blur on the uint8 image exactly as
+// scipy.ndimage.convolve(img_H, k[..., None], mode='wrap') evaluates it - correlation with the flipped kernel, taps in
+// row-major order of the flipped kernel, fp64 multiply and add WITHOUT fma contraction, result truncated to uint8 - then
+// /255, *2-1, + noise (host-drawn AWGN, std 2*sigma), /2+.5, written as float NCHW.
+__global__ void k_measure_blur_u8(const uint8_t *__restrict__ img, const double *__restrict__ kf, const float *__restrict__ noise,
+                                  uint8_t *__restrict__ blur_u8, float *__restrict__ out, int B, int H, int W, int C, int kh,
+                                  int kw) {
+  extern __shared__ double skf[];
+  for (int i = threadIdx.x; i < kh * kw; i += blockDim.x) skf[i] = kf[(int64_t)blockIdx.y * kh * kw + i];
+  __syncthreads();
+  int b = blockIdx.y;
+  int64_t n = (int64_t)H * W * C;
+  const uint8_t *src = img + (int64_t)b * n;
+  // scipy: convolve == correlate with weights[::-1, ::-1], filter centre at size/2 (odd) or size/2 - 1 (even); taps with
+  // |w| <= DBL_EPSILON are dropped from the footprint (NI_Correlate)
+  const int sh = (kh & 1) ? kh / 2 : kh / 2 - 1, sw = (kw & 1) ? kw / 2 : kw / 2 - 1;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    int x = (int)((i / C) % W);
+    int y = (int)(i / ((int64_t)C * W));
+    double acc = 0.0;
+    for (int a = 0; a < kh; ++a) {
+      int yy = y + a - sh;
+      yy %= H; if (yy < 0) yy += H;
+      for (int bb = 0; bb < kw; ++bb) {
+        double wgt = skf[(kh - 1 - a) * kw + (kw - 1 - bb)];
+        if (fabs(wgt) <= 2.220446049250313e-16) continue;
+        int xx = x + bb - sw;
+        xx %= W; if (xx < 0) xx += W;
+        acc = __dadd_rn(acc, __dmul_rn((double)src[((int64_t)yy * W + xx) * C + c], wgt));
+      }
+    }
+    uint8_t q = (uint8_t)(int)acc;          // C cast: truncation
+    if (blur_u8) blur_u8[(int64_t)b * n + i] = q;
+    if (out) {
+      float v = (float)q / 255.0f;
+      float nz = noise ? noise[(int64_t)b * n + i] : 0.f;
+      v = (v * 2.f - 1.f + nz) / 2.f + 0.5f;
+      out[(((int64_t)b * C + c) * H + y) * W + x] = v;
+    }
+  }
+}
+
 static inline int grid_for(int64_t n, int block = 256, int max_blocks = 148 * 16) {
   int64_t g = (n + block - 1) / block;
   if (g < 1) g = 1;
@@ -479,6 +573,41 @@ int dpir_blur_reflect(const float *x, const float *k, int32_t planes, int32_t H,
   size_t smem = (size_t)kh * kw * sizeof(float);
   DPIR_REQUIRE(smem <= 48 * 1024, "dpir_blur_reflect: kernel too large");
   k_blur_reflect<<<grid_for((int64_t)planes * H * W), 256, smem, (cudaStream_t)stream>>>(x, k, planes, H, W, kh, kw, out);
+  DPIR_LAUNCH_CHECK();
+  return DPIR_OK;
+}
+
+int dpir_tensor2uint(const float *x, uint8_t *out_nhwc, int32_t B, int32_t C, int32_t H, int32_t W, void *stream) {
+  DPIR_REQUIRE(x && out_nhwc, "dpir_tensor2uint: null pointer");
+  k_tensor2uint<<<grid_for((int64_t)B * C * H * W), 256, 0, (cudaStream_t)stream>>>(x, out_nhwc, B, C, H, W);
+  DPIR_LAUNCH_CHECK();
+  return DPIR_OK;
+}
+
+int dpir_sqdiff_batch(const float *a, const float *b, float a_scale, float a_bias, float b_scale, float b_bias, int32_t luma,
+                      int32_t B, int32_t C, int32_t HW, double *sse, void *stream) {
+  DPIR_REQUIRE(a && b && sse, "dpir_sqdiff_batch: null pointer");
+  DPIR_REQUIRE(!luma || C == 3, "dpir_sqdiff_batch: luma needs 3 channels");
+  cudaStream_t st = (cudaStream_t)stream;
+  DPIR_CUDA_CHECK(cudaMemsetAsync(sse, 0, (size_t)B * sizeof(double), st));
+  int64_t n = luma ? HW : (int64_t)C * HW;
+  int gx = (int)((n + 256 * 8 - 1) / (256 * 8));
+  if (gx < 1) gx = 1;
+  if (gx > 64) gx = 64;
+  k_sqdiff<<<dim3(gx, B), 256, 0, st>>>(a, b, a_scale, a_bias, b_scale, b_bias, luma, C, HW, sse);
+  DPIR_LAUNCH_CHECK();
+  return DPIR_OK;
+}
+
+int dpir_measure_blur_u8(const uint8_t *img_nhwc, const double *k, const float *noise_nhwc, uint8_t *blur_u8, float *out_nchw,
+                         int32_t B, int32_t H, int32_t W, int32_t C, int32_t kh, int32_t kw, void *stream) {
+  DPIR_REQUIRE(img_nhwc && k && (blur_u8 || out_nchw), "dpir_measure_blur_u8: null pointer");
+  size_t smem = (size_t)kh * kw * sizeof(double);
+  DPIR_REQUIRE(smem <= 48 * 1024, "dpir_measure_blur_u8: kernel too large");
+  int64_t n = (int64_t)H * W * C;
+  int gx = (int)((n + 255) / 256);
+  if (gx > 148 * 8) gx = 148 * 8;
+  k_measure_blur_u8<<<dim3(gx, B), 256, smem, (cudaStream_t)stream>>>(img_nhwc, k, noise_nhwc, blur_u8, out_nchw, B, H, W, C, kh, kw);
   DPIR_LAUNCH_CHECK();
   return DPIR_OK;
 }

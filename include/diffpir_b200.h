@@ -197,6 +197,24 @@ int dpir_blur_reflect(const float *x, const float *k, int32_t planes, int32_t H,
                       float *out, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Edges of the loop ("next" rows of SURVEY.md section 8(f)).
+ * ------------------------------------------------------------------------------------------------ */
+/* tensor2uint_batch (utils/utils_image.py:238-242): x dev (B,C,H,W) float -> out dev (B,H,W,C) uint8 =
+ * round_half_even(clamp(x,0,1)*255). */
+int dpir_tensor2uint(const float *x, uint8_t *out_nhwc, int32_t B, int32_t C, int32_t H, int32_t W, void *stream);
+/* per-image sum of squared differences behind calculate_psnr_batch (utils_image.py:601-610):
+ * sse[i] = sum over image i of ((a_scale*a+a_bias) - (b_scale*b+b_bias))^2; luma != 0 compares only
+ * Y = 0.299R+0.587G+0.114B (rgb2ycbcr_batch only_y, :470-490).  a, b dev (B,C,HW) float; sse dev (B) double. */
+int dpir_sqdiff_batch(const float *a, const float *b, float a_scale, float a_bias, float b_scale, float b_bias, int32_t luma,
+                      int32_t B, int32_t C, int32_t HW, double *sse, void *stream);
+/* measurement synthesis for deblurring (main_ddpir.py:97-114, main_ddpir_deblur.py:193-199): circular blur of the uint8
+ * image exactly as scipy.ndimage.convolve(img, k[...,None], mode='wrap') computes it (fp64, same tap order, truncated to
+ * uint8), then /255, *2-1, + noise, /2+.5.  img dev (B,H,W,C) uint8; k dev (B,kh,kw) double; noise dev (B,H,W,C) float or
+ * NULL (AWGN drawn by the caller, std 2*sigma); blur_u8 dev (B,H,W,C) uint8 or NULL; out dev (B,C,H,W) float or NULL. */
+int dpir_measure_blur_u8(const uint8_t *img_nhwc, const double *k, const float *noise_nhwc, uint8_t *blur_u8, float *out_nchw,
+                         int32_t B, int32_t H, int32_t W, int32_t C, int32_t kh, int32_t kw, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Low-level entry points exposed for per-kernel parity tests and benchmarks (tests/ and bench.py).
  * NHWC activations.  act_dtype: 0 = fp32, 1 = fp16.
  * ------------------------------------------------------------------------------------------------ */

@@ -154,3 +154,43 @@ def test_blur_operator_forward_transpose_kernel():
     out = op.forward(x.cuda())
     assert rel_l2(out, ref) < 1e-5
     assert op.transpose(x) is x
+
+
+def test_tensor2uint_and_psnr_tail_match_reference_formulas():
+    """tensor2uint_batch / calculate_psnr_batch / Y-PSNR (utils_image.py:238-242, 601-610, 470-490; main_ddpir.py:482-515)."""
+    import numpy as np
+    from diffpir_b200 import utils_image as ui
+    g = torch.Generator().manual_seed(10)
+    x0 = torch.rand(3, 3, 64, 48, generator=g) * 1.2 - 0.1
+    ref_u8 = np.uint8((np.transpose(x0.clamp(0, 1).numpy(), (0, 2, 3, 1)) * 255.0).round())
+    assert np.array_equal(ui.tensor2uint_batch(x0.cuda()), ref_u8)             # byte output: bit-exact
+    a, b = x0 * 2 - 1, torch.rand(3, 3, 64, 48, generator=g) * 2 - 1
+    mse = torch.mean((a - b) ** 2, axis=(1, 2, 3))
+    ref = torch.mean(20 * torch.log10(2.0 / torch.sqrt(mse + 1e-10))).item()
+    assert abs(ui.calculate_psnr_batch(a.cuda(), b.cuda()) - ref) < 1e-4
+    ya = torch.zeros_like(a); yb = torch.zeros_like(b)
+    ya[:, 0] = 0.299 * a[:, 0] + 0.587 * a[:, 1] + 0.114 * a[:, 2]
+    yb[:, 0] = 0.299 * b[:, 0] + 0.587 * b[:, 1] + 0.114 * b[:, 2]
+    mse = torch.mean((ya - yb) ** 2, axis=(1, 2, 3))
+    ref = torch.mean(20 * torch.log10(2.0 / torch.sqrt(mse + 1e-10))).item()
+    assert abs(ui.calculate_psnr_y_batch(a.cuda(), b.cuda()) - ref) < 1e-4
+    assert ui.calculate_psnr_batch(a.cuda(), a.cuda()) == float("inf")
+
+
+@pytest.mark.parametrize("ksz", [13, 27, 61, 24])
+def test_measurement_blur_uint8_bit_exact_vs_scipy(ksz):
+    """The uint8 circular blur of CustomDataset.__getitem__ (main_ddpir.py:99): bit-exact against scipy.ndimage.convolve."""
+    import numpy as np
+    from scipy import ndimage
+    from diffpir_b200 import synth, utils_image as ui
+    imgs = synth.synthetic_images(2, 96, seed=31)
+    ks = [synth.gaussian_kernel(ksz, 2.5, dtype=np.float64) if ksz != 27 else synth.motion_kernel(27, 0.6, 3).astype(np.float64),
+          synth.motion_kernel(ksz, 0.5, 4).astype(np.float64)]
+    rng = np.random.RandomState(0)
+    noise = rng.normal(0, 0.1, imgs.shape).astype(np.float32)
+    y, u8 = ui.blur_measurement_batch(imgs, np.stack(ks), noise=noise, return_u8=True)
+    for b in range(2):
+        ref = ndimage.convolve(imgs[b], np.expand_dims(ks[b], axis=2), mode="wrap")
+        assert np.array_equal(u8[b].cpu().numpy(), ref)
+        yl = (np.float32(ref / 255.0) * 2 - 1 + noise[b]) / 2 + 0.5
+        assert np.abs(y[b].cpu().numpy() - np.transpose(yl, (2, 0, 1))).max() < 1e-6
