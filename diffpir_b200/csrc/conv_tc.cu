@@ -661,17 +661,194 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_conv3x3_v2(const __grid_const
   if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
+// ------------------------------------------------------------------------------------------------ v3: swap-AB persistent kernel
+// Same tiling / TMA / pipeline as v2, but the GEMM is issued transposed: D^T[cout][pixel] = W[cout][k] * A[pixel][k]^T with
+// M = 128 output channels (weights are the A operand) and N = 256 pixels (the whole 16x16 tile is ONE B operand: rows
+// dy*16 .. dy*16+255 of the halo box).  Per 64-channel chunk and tap this is 4 MMAs of 128x256x16 reading 4 KB (W) + 8 KB
+// (pixels) of shared memory per 128 tensor cycles instead of 2 x (4 + 4) KB - 25 % less operand traffic on the
+// shared-memory port, which is what bounds the SS-mode 128x128 MMAs of v2 (ncu: ~65 % tensor pipe on 128->128 layers).
+// The accumulator then has CHANNELS on TMEM lanes and pixels on columns, so in the epilogue a warp instruction writes 32
+// consecutive channels of one pixel = one contiguous 128 B (fp32) / 64 B (fp16) segment: coalesced without any transpose,
+// bias is a per-lane constant, and the GroupNorm quad statistics reduce to a thread-local sum over pixels plus two shuffles.
+__global__ void __launch_bounds__(V2_THREADS, 1) k_conv3x3_v3(const __grid_constant__ CUtensorMap tmA,
+                                                               const __grid_constant__ CUtensorMap tmB,
+                                                               const __grid_constant__ CUtensorMap tmA2,
+                                                               const __grid_constant__ CUtensorMap tmB2, ConvV2Geom g,
+                                                               ConvEpi epi) {
+  // M = 128 (couts), N = 256 (pixels)
+  constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem + V2_STAGES * V2_STAGE_BYTES);
+  uint64_t *empty = full + V2_STAGES;
+  uint64_t *tmem_full = empty + V2_STAGES;     // [2]
+  uint64_t *tmem_empty = tmem_full + 2;        // [2]
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int chunks = g.Cin / TC_BK;
+  const int num_main = 3 * chunks;
+  const int num_k = num_main + g.skip_chunks;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    if (g.skip_chunks) { tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmB2); }
+    for (int s = 0; s < V2_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 8); }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto decode = [&](int tile, int &n, int &h0, int &w0, int &co0) {
+    int nt = tile % g.n_tiles;
+    int mt = tile / g.n_tiles;
+    co0 = nt * 128;
+    w0 = (mt % g.tiles_w) * 16;
+    h0 = ((mt / g.tiles_w) % g.tiles_h) * 16;
+    n = mt / (g.tiles_w * g.tiles_h);
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+        int n, h0, w0, co0;
+        decode(tile, n, h0, w0, co0);
+        for (int k = 0; k < num_k; ++k, ++it) {
+          const int s = it % V2_STAGES;
+          const uint32_t ph = (it / V2_STAGES) & 1u;
+          mbar_wait(&empty[s], ph ^ 1u);
+          uint8_t *sa = smem + s * V2_STAGE_BYTES;
+          if (k < num_main) {
+            const int ch = k / 3, dx = k - ch * 3;
+            mbar_expect_tx(&full[s], V2_STAGE_BYTES);
+            tma_load_4d(sa, &tmA, &full[s], ch * TC_BK, w0 + dx - 1, h0 - 1, n);
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy)
+              tma_load_3d(sa + V2_A_BYTES + dy * (128 * 128), &tmB, &full[s], ch * TC_BK, co0, dy * 3 + dx);
+          } else {
+            const int ch = k - num_main;
+            mbar_expect_tx(&full[s], V2_A_BYTES + 128 * 128);
+            tma_load_4d(sa, &tmA2, &full[s], ch * TC_BK, w0, h0 - 1, n);
+            tma_load_3d(sa + V2_A_BYTES + 1 * (128 * 128), &tmB2, &full[s], ch * TC_BK, co0, 0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t it = 0, tc = 0;
+      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++tc) {
+        const uint32_t ab = tc & 1u, aph = (tc >> 1) & 1u;
+        mbar_wait(&tmem_empty[ab], aph ^ 1u);
+        tc_fence_after();
+        const uint32_t d = tmem_base + ab * 256u;
+        for (int k = 0; k < num_k; ++k, ++it) {
+          const int s = it % V2_STAGES;
+          const uint32_t ph = (it / V2_STAGES) & 1u;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * V2_STAGE_BYTES);
+          const int dy_lo = k < num_main ? 0 : 1, dy_hi = k < num_main ? 3 : 2;
+          for (int dy = dy_lo; dy < dy_hi; ++dy) {
+            const uint64_t wdesc = make_sw128_desc(sa + V2_A_BYTES + dy * (128 * 128));   // A operand: 128 couts x 64 k
+            const uint64_t pdesc = make_sw128_desc(sa + (uint32_t)(dy * 16 * 128));       // B operand: 256 pixels x 64 k
+#pragma unroll
+            for (int kk = 0; kk < TC_BK / 16; ++kk)
+              umma_f16(d, wdesc + (uint64_t)(2 * kk), pdesc + (uint64_t)(2 * kk), IDESC, (k | (dy - dy_lo) | kk) ? 1u : 0u);
+          }
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&tmem_full[ab]);
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue: lane = output channel, column = pixel
+    const int ew = warp - 2;              // 0..7
+    const int q = warp & 3;               // TMEM lane quarter -> channels co0 + q*32 + lane
+    const int hv = ew >> 2;               // which half of the tile's 256 pixels (image rows hv*8 .. hv*8+7)
+    uint32_t tc = 0;
+    for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++tc) {
+      const uint32_t ab = tc & 1u, aph = (tc >> 1) & 1u;
+      int n, h0, w0, co0;
+      decode(tile, n, h0, w0, co0);
+      const int ch = co0 + q * 32 + lane;
+      float bch = __ldg(epi.bias + ch);
+      if (epi.bias2) bch += __ldg(epi.bias2 + ch);
+      float st_s = 0.f, st_q = 0.f;
+      mbar_wait(&tmem_full[ab], aph);
+      tc_fence_after();
+      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + ab * 256u + (uint32_t)hv * 128u;
+      const int64_t img_base = (int64_t)n * g.H * g.W;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {       // 32 pixels = image rows (hv*8 + 2c), (hv*8 + 2c + 1) of the tile
+        const int y0 = h0 + hv * 8 + 2 * c;
+        float res[32];
+        if (epi.residual) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int yh = y0 + (j >> 4), xw = w0 + (j & 15);
+            res[j] = 0.f;
+            if (yh < g.H && xw < g.W) {
+              const int64_t o = (img_base + (int64_t)yh * g.W + xw) * g.Cout + ch;
+              res[j] = epi.res_half ? __half2float(reinterpret_cast<const __half *>(epi.residual)[o]) : epi.residual[o];
+            }
+          }
+        }
+        uint32_t r[32];
+        tmem_ld32(tbase + (uint32_t)(c * 32), r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int yh = y0 + (j >> 4), xw = w0 + (j & 15);
+          if (yh < g.H && xw < g.W) {                   // warp-uniform
+            float v = __uint_as_float(r[j]) + bch;
+            if (epi.residual) v += res[j];
+            st_s += v;
+            st_q += v * v;
+            const int64_t o = (img_base + (int64_t)yh * g.W + xw) * g.Cout + ch;
+            if (epi.out_half) reinterpret_cast<__half *>(epi.out)[o] = __float2half_rn(v);
+            else epi.out[o] = v;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[ab]);
+      if (epi.qstats) {
+        st_s += __shfl_xor_sync(0xffffffffu, st_s, 1); st_q += __shfl_xor_sync(0xffffffffu, st_q, 1);
+        st_s += __shfl_xor_sync(0xffffffffu, st_s, 2); st_q += __shfl_xor_sync(0xffffffffu, st_q, 2);
+        if ((lane & 3) == 0) {
+          double *qp = epi.qstats + ((int64_t)n * (g.Cout >> 2) + (ch >> 2)) * 2;
+          atomicAdd(qp, (double)st_s);
+          atomicAdd(qp + 1, (double)st_q);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 struct ConvTcPlan {
   CUtensorMap tmA, tmB;
   ConvTcGeom g;
   int BN, CoutPad;
-  bool v2 = false;        // persistent 3x3 kernel (k_conv3x3_v2)
+  bool v2 = false;        // persistent 3x3 kernel (k_conv3x3_v2 / k_conv3x3_v3)
+  bool use_v3 = true;     // swap-AB variant
   ConvV2Geom g2;
   CUtensorMap tmA2, tmB2; // fused 1x1 skip operand / weights (v2 only; copies of tmA/tmB when unused)
 };
 
-static int g_force_v1 = 0;   // tests / A-B benchmarking: dpir_conv_tc_variant(1) forces the v1 kernel everywhere
+static int g_force_v1 = 0;   // dpir_conv_tc_variant: 0 = auto (persistent swap-AB v3), 1 = v1 everywhere, 2 = persistent v2
 static int g_num_sms = 0;
 
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
@@ -707,7 +884,8 @@ int conv_tc_plan_create(const void *act_half, const void *w_half, int B, int H, 
   g.tiles_w = cdiv(W, g.TW); g.tiles_h = cdiv(H, g.TH); g.tiles_n = cdiv(B, g.TN);
   p->BN = CoutPad == 16 ? 16 : 128;
   p->CoutPad = CoutPad;
-  p->v2 = !g_force_v1 && ksize == 3 && H >= 16 && W >= 16 && CoutPad % 128 == 0;
+  p->v2 = g_force_v1 != 1 && ksize == 3 && H >= 16 && W >= 16 && CoutPad % 128 == 0;
+  p->use_v3 = g_force_v1 == 0;
   if (p->v2) {
     ConvV2Geom &g2 = p->g2;
     g2.B = B; g2.H = H; g2.W = W; g2.Cin = Cin; g2.Cout = 0; g2.skip_chunks = 0;
@@ -791,17 +969,16 @@ static int launch_tc_impl(const ConvTcPlan *p, const ConvTcGeom &g, const ConvEp
 }
 
 void conv_tc_force_v1(int on) { g_force_v1 = on; }
-bool conv_tc_v2_enabled() { return !g_force_v1; }
+bool conv_tc_v2_enabled() { return g_force_v1 != 1; }
 
 int launch_conv_tc(const ConvTcPlan *p, const ConvEpi &epi, int Cout, cudaStream_t st) {
   DPIR_REQUIRE(Cout <= p->CoutPad, "conv_tc: Cout exceeds padded weight rows");
   DPIR_REQUIRE(epi.mode != EPI_NHWC || Cout % 4 == 0, "conv_tc: NHWC epilogue needs Cout %% 4 == 0");
   if (p->v2 && epi.mode == EPI_NHWC) {
-    DPIR_REQUIRE(!epi.residual || (epi.res_half != 0) == (epi.out_half != 0),
-                 "conv_tc: the persistent kernel needs residual and output of the same precision");
     static bool attr_set = false;
     if (!attr_set) {
       DPIR_CUDA_CHECK(cudaFuncSetAttribute(k_conv3x3_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, V2_SMEM));
+      DPIR_CUDA_CHECK(cudaFuncSetAttribute(k_conv3x3_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, V2_SMEM));
       int dev = 0;
       DPIR_CUDA_CHECK(cudaGetDevice(&dev));
       DPIR_CUDA_CHECK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -810,7 +987,13 @@ int launch_conv_tc(const ConvTcPlan *p, const ConvEpi &epi, int Cout, cudaStream
     ConvV2Geom g2 = p->g2;
     g2.Cout = Cout;
     int grid = g2.total_tiles < g_num_sms ? g2.total_tiles : g_num_sms;
-    k_conv3x3_v2<<<grid, V2_THREADS, V2_SMEM, st>>>(p->tmA, p->tmB, p->tmA2, p->tmB2, g2, epi);
+    if (p->use_v3) {
+      k_conv3x3_v3<<<grid, V2_THREADS, V2_SMEM, st>>>(p->tmA, p->tmB, p->tmA2, p->tmB2, g2, epi);
+    } else {
+      DPIR_REQUIRE(!epi.residual || (epi.res_half != 0) == (epi.out_half != 0),
+                   "conv_tc: the v2 persistent kernel needs residual and output of the same precision");
+      k_conv3x3_v2<<<grid, V2_THREADS, V2_SMEM, st>>>(p->tmA, p->tmB, p->tmA2, p->tmB2, g2, epi);
+    }
     DPIR_LAUNCH_CHECK();
     return DPIR_OK;
   }

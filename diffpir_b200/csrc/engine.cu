@@ -1055,8 +1055,9 @@ int dpir_conv_tc(const void *act, const void *w, const float *bias, const float 
   return rc;
 }
 
-int dpir_conv_tc_variant(int32_t force_v1) {
-  conv_tc_force_v1(force_v1 ? 1 : 0);
+int dpir_conv_tc_variant(int32_t variant) {
+  DPIR_REQUIRE(variant >= 0 && variant <= 2, "dpir_conv_tc_variant: 0 = auto, 1 = v1, 2 = v2");
+  conv_tc_force_v1(variant);
   return DPIR_OK;
 }
 

@@ -48,7 +48,7 @@ SHAPES = [
 ]
 
 
-@pytest.mark.parametrize("variant", ["auto", "v1"])
+@pytest.mark.parametrize("variant", ["auto", "v1", "v2"])
 @pytest.mark.parametrize("B,H,W,Cin,Cout,k,residual", SHAPES + [
     (5, 32, 32, 128, 256, 3, True),     # persistent kernel: 40 tiles, 2 cout tiles, odd batch
     (2, 48, 80, 128, 128, 3, True),     # H, W multiples of 16 but not powers of two
@@ -58,7 +58,7 @@ SHAPES = [
 def test_conv_tc_matches_torch(B, H, W, Cin, Cout, k, residual, variant):
     from diffpir_b200 import _lib
     lib = _lib.load()
-    lib.dpir_conv_tc_variant(1 if variant == "v1" else 0)
+    lib.dpir_conv_tc_variant({"auto": 0, "v1": 1, "v2": 2}[variant])
     x, w, b, r = _case(B, H, W, Cin, Cout, k, 0, residual)
     # reference: fp32 conv of the fp16-rounded operands (isolates kernel correctness from operand rounding)
     xh, wh = x.half().float(), w.half().float()
