@@ -679,7 +679,8 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_conv3x3_v3(const __grid_const
   constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t *full = reinterpret_cast<uint64_t *>(smem + V2_STAGES * V2_STAGE_BYTES);
+  uint8_t *stg_base = smem + V2_STAGES * V2_STAGE_BYTES;
+  uint64_t *full = reinterpret_cast<uint64_t *>(stg_base + V2_STG_BYTES);
   uint64_t *empty = full + V2_STAGES;
   uint64_t *tmem_full = empty + V2_STAGES;     // [2]
   uint64_t *tmem_empty = tmem_full + 2;        // [2]
@@ -770,17 +771,26 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_conv3x3_v3(const __grid_const
     }
   } else {
     // ---------------------------------------------------------------- epilogue: lane = output channel, column = pixel
+    // A warp owns 32 channels x 128 pixels of the accumulator.  Per 32-pixel chunk it transposes 32 ch x 32 px through a
+    // private 4 KB buffer: a lane (channel) writes its 32 pixel values as 8 float4 into row `lane`, 16-byte column c4
+    // stored at c4 ^ ((lane >> 2) & 7); the warp then reads (pixel, 4 consecutive channels) vectors - 4 LDS.32 from 4 rows,
+    // conflict-free under that swizzle - so that 8 lanes write one pixel's 32 channels as one contiguous 128 B (fp32) /
+    // 64 B (fp16) segment, 4 pixels per instruction.  The residual takes the same route backwards.
     const int ew = warp - 2;              // 0..7
     const int q = warp & 3;               // TMEM lane quarter -> channels co0 + q*32 + lane
     const int hv = ew >> 2;               // which half of the tile's 256 pixels (image rows hv*8 .. hv*8+7)
+    float *stg = reinterpret_cast<float *>(stg_base + ew * 4096);     // [32 ch][32 px] floats, swizzled
+    const int pl = lane >> 3;             // transposed role: pixel (4k + pl) of the chunk ...
+    const int cq = lane & 7;              // ... channels 4*cq .. 4*cq+3 of this warp's 32
+    const int swz_own = (lane >> 2) & 7;
     uint32_t tc = 0;
     for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++tc) {
       const uint32_t ab = tc & 1u, aph = (tc >> 1) & 1u;
       int n, h0, w0, co0;
       decode(tile, n, h0, w0, co0);
-      const int ch = co0 + q * 32 + lane;
-      float bch = __ldg(epi.bias + ch);
-      if (epi.bias2) bch += __ldg(epi.bias2 + ch);
+      const int cbase = co0 + q * 32;
+      float bch = __ldg(epi.bias + cbase + lane);
+      if (epi.bias2) bch += __ldg(epi.bias2 + cbase + lane);
       float st_s = 0.f, st_q = 0.f;
       mbar_wait(&tmem_full[ab], aph);
       tc_fence_after();
@@ -792,31 +802,72 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_conv3x3_v3(const __grid_const
         float res[32];
         if (epi.residual) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
+          for (int k = 0; k < 8; ++k) {
+            const int j = 4 * k + pl;                              // pixel inside the chunk
             const int yh = y0 + (j >> 4), xw = w0 + (j & 15);
-            res[j] = 0.f;
+            float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
             if (yh < g.H && xw < g.W) {
-              const int64_t o = (img_base + (int64_t)yh * g.W + xw) * g.Cout + ch;
-              res[j] = epi.res_half ? __half2float(reinterpret_cast<const __half *>(epi.residual)[o]) : epi.residual[o];
+              const int64_t o = (img_base + (int64_t)yh * g.W + xw) * g.Cout + cbase + 4 * cq;
+              if (epi.res_half) {
+                uint2 u = *reinterpret_cast<const uint2 *>(reinterpret_cast<const __half *>(epi.residual) + o);
+                float2 f0 = __half22float2(*reinterpret_cast<__half2 *>(&u.x)), f1 = __half22float2(*reinterpret_cast<__half2 *>(&u.y));
+                rv = make_float4(f0.x, f0.y, f1.x, f1.y);
+              } else {
+                rv = *reinterpret_cast<const float4 *>(epi.residual + o);
+              }
             }
+            // element (channel row 4*cq + i, pixel column j): word = row*32 + (((j>>2) ^ ((row>>2)&7)) << 2) + (j&3), row>>2 == cq
+            const int col = (((j >> 2) ^ cq) << 2) + (j & 3);
+            stg[(4 * cq + 0) * 32 + col] = rv.x; stg[(4 * cq + 1) * 32 + col] = rv.y;
+            stg[(4 * cq + 2) * 32 + col] = rv.z; stg[(4 * cq + 3) * 32 + col] = rv.w;
           }
+          __syncwarp();
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4) {
+            float4 t4 = *reinterpret_cast<const float4 *>(stg + lane * 32 + ((c4 ^ swz_own) << 2));
+            res[4 * c4] = t4.x; res[4 * c4 + 1] = t4.y; res[4 * c4 + 2] = t4.z; res[4 * c4 + 3] = t4.w;
+          }
+          __syncwarp();
         }
         uint32_t r[32];
         tmem_ld32(tbase + (uint32_t)(c * 32), r);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int yh = y0 + (j >> 4), xw = w0 + (j & 15);
-          if (yh < g.H && xw < g.W) {                   // warp-uniform
+        for (int c4 = 0; c4 < 8; ++c4) {
+          float4 t4;
+          float *tp = reinterpret_cast<float *>(&t4);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int j = 4 * c4 + u;
             float v = __uint_as_float(r[j]) + bch;
             if (epi.residual) v += res[j];
-            st_s += v;
-            st_q += v * v;
-            const int64_t o = (img_base + (int64_t)yh * g.W + xw) * g.Cout + ch;
-            if (epi.out_half) reinterpret_cast<__half *>(epi.out)[o] = __float2half_rn(v);
-            else epi.out[o] = v;
+            const bool ok = (y0 + (j >> 4) < g.H) && (w0 + (j & 15) < g.W);      // warp-uniform
+            if (ok) { st_s += v; st_q += v * v; }
+            tp[u] = v;
+          }
+          *reinterpret_cast<float4 *>(stg + lane * 32 + ((c4 ^ swz_own) << 2)) = t4;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int j = 4 * k + pl;
+          const int yh = y0 + (j >> 4), xw = w0 + (j & 15);
+          const int col = (((j >> 2) ^ cq) << 2) + (j & 3);
+          float4 ov = make_float4(stg[(4 * cq + 0) * 32 + col], stg[(4 * cq + 1) * 32 + col], stg[(4 * cq + 2) * 32 + col],
+                                  stg[(4 * cq + 3) * 32 + col]);
+          if (yh < g.H && xw < g.W) {
+            const int64_t o = (img_base + (int64_t)yh * g.W + xw) * g.Cout + cbase + 4 * cq;
+            if (epi.out_half) {
+              __half2 h0 = __floats2half2_rn(ov.x, ov.y), h1 = __floats2half2_rn(ov.z, ov.w);
+              uint2 u;
+              u.x = *reinterpret_cast<uint32_t *>(&h0); u.y = *reinterpret_cast<uint32_t *>(&h1);
+              *reinterpret_cast<uint2 *>(reinterpret_cast<__half *>(epi.out) + o) = u;
+            } else {
+              *reinterpret_cast<float4 *>(epi.out + o) = ov;
+            }
           }
         }
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
@@ -825,7 +876,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_conv3x3_v3(const __grid_const
         st_s += __shfl_xor_sync(0xffffffffu, st_s, 1); st_q += __shfl_xor_sync(0xffffffffu, st_q, 1);
         st_s += __shfl_xor_sync(0xffffffffu, st_s, 2); st_q += __shfl_xor_sync(0xffffffffu, st_q, 2);
         if ((lane & 3) == 0) {
-          double *qp = epi.qstats + ((int64_t)n * (g.Cout >> 2) + (ch >> 2)) * 2;
+          double *qp = epi.qstats + ((int64_t)n * (g.Cout >> 2) + ((cbase + lane) >> 2)) * 2;
           atomicAdd(qp, (double)st_s);
           atomicAdd(qp + 1, (double)st_q);
         }

@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--model", default="ffhq")
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--json", default="")
+    ap.add_argument("--warmup", type=int, default=2)
     a = ap.parse_args()
     cfg = arch.ffhq_config() if a.model == "ffhq" else arch.imagenet_config()
     m = UNetModel(cfg, precision=a.precision)
@@ -28,7 +29,7 @@ def main():
     B = a.batch
     x = torch.randn(B, 3, a.size, a.size, device="cuda")
     t = torch.full((B,), 500, device="cuda", dtype=torch.int64)
-    for _ in range(2):
+    for _ in range(a.warmup):
         m.x0(x, t)
     torch.cuda.synchronize()
     m.profile_begin()
