@@ -19,6 +19,7 @@
 //   Two CTAs fit per SM (3 x 32 KB stages, 128 TMEM columns each) so one CTA's epilogue overlaps the other's main loop.
 #include "unet_kernels.cuh"
 
+#include <cstdlib>
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
@@ -380,6 +381,8 @@ constexpr int V2_SMEM = V2_STAGES * V2_STAGE_BYTES + V2_STG_BYTES + 1024 + 256;
 struct ConvV2Geom {
   int B, H, W, Cin, Cout;
   int skip_chunks;                    // extra K chunks of a fused 1x1 convolution on a second operand (ResBlock skip), or 0
+  int dbg;                            // timing diagnostics only (env DPIR_CONV_DEBUG): 1 = no epilogue memory traffic,
+                                      // 2 = no MMA issue, 4 = no TMA loads; results are garbage when non-zero
   int tiles_w, tiles_h, n_tiles;      // 16x16 pixel tiles per image, Cout/128 column tiles
   int total_tiles;                    // B * tiles_h * tiles_w * n_tiles
 };
@@ -726,6 +729,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_conv3x3_v3(const __grid_const
           const uint32_t ph = (it / V2_STAGES) & 1u;
           mbar_wait(&empty[s], ph ^ 1u);
           uint8_t *sa = smem + s * V2_STAGE_BYTES;
+          if (g.dbg & 4) { mbar_arrive(&full[s]); continue; }
           if (k < num_main) {
             const int ch = k / 3, dx = k - ch * 3;
             mbar_expect_tx(&full[s], V2_STAGE_BYTES);
@@ -757,7 +761,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_conv3x3_v3(const __grid_const
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * V2_STAGE_BYTES);
           const int dy_lo = k < num_main ? 0 : 1, dy_hi = k < num_main ? 3 : 2;
-          for (int dy = dy_lo; dy < dy_hi; ++dy) {
+          for (int dy = dy_lo; dy < dy_hi && !(g.dbg & 2); ++dy) {
             const uint64_t wdesc = make_sw128_desc(sa + V2_A_BYTES + dy * (128 * 128));   // A operand: 128 couts x 64 k
             const uint64_t pdesc = make_sw128_desc(sa + (uint32_t)(dy * 16 * 128));       // B operand: 256 pixels x 64 k
 #pragma unroll
@@ -771,18 +775,15 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_conv3x3_v3(const __grid_const
     }
   } else {
     // ---------------------------------------------------------------- epilogue: lane = output channel, column = pixel
-    // A warp owns 32 channels x 128 pixels of the accumulator.  Per 32-pixel chunk it transposes 32 ch x 32 px through a
-    // private 4 KB buffer: a lane (channel) writes its 32 pixel values as 8 float4 into row `lane`, 16-byte column c4
-    // stored at c4 ^ ((lane >> 2) & 7); the warp then reads (pixel, 4 consecutive channels) vectors - 4 LDS.32 from 4 rows,
-    // conflict-free under that swizzle - so that 8 lanes write one pixel's 32 channels as one contiguous 128 B (fp32) /
-    // 64 B (fp16) segment, 4 pixels per instruction.  The residual takes the same route backwards.
+    // The epilogue is instruction-issue bound (ncu: ~6 cycles per issued instruction with 2 warps per scheduler), so it is
+    // written for minimum instruction count and needs no shared memory: a warp instruction touches ONE pixel (fp32: 32 lanes x
+    // 4 B = 128 contiguous bytes) or TWO pixels (fp16: neighbouring channel lanes swap half of their pixels with one
+    // shuffle, then even lanes write pixel j and odd lanes pixel j+16 as 16 x half2 = 64 contiguous bytes each).  The
+    // residual takes the mirrored route.  Interior tiles (the vast majority) take a path without any bounds predicates.
     const int ew = warp - 2;              // 0..7
     const int q = warp & 3;               // TMEM lane quarter -> channels co0 + q*32 + lane
     const int hv = ew >> 2;               // which half of the tile's 256 pixels (image rows hv*8 .. hv*8+7)
-    float *stg = reinterpret_cast<float *>(stg_base + ew * 4096);     // [32 ch][32 px] floats, swizzled
-    const int pl = lane >> 3;             // transposed role: pixel (4k + pl) of the chunk ...
-    const int cq = lane & 7;              // ... channels 4*cq .. 4*cq+3 of this warp's 32
-    const int swz_own = (lane >> 2) & 7;
+    const bool odd = lane & 1;
     uint32_t tc = 0;
     for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++tc) {
       const uint32_t ab = tc & 1u, aph = (tc >> 1) & 1u;
@@ -792,87 +793,86 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_conv3x3_v3(const __grid_const
       float bch = __ldg(epi.bias + cbase + lane);
       if (epi.bias2) bch += __ldg(epi.bias2 + cbase + lane);
       float st_s = 0.f, st_q = 0.f;
+      const bool full = (h0 + 16 <= g.H) && (w0 + 16 <= g.W);
       mbar_wait(&tmem_full[ab], aph);
       tc_fence_after();
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + ab * 256u + (uint32_t)hv * 128u;
-      const int64_t img_base = (int64_t)n * g.H * g.W;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {       // 32 pixels = image rows (hv*8 + 2c), (hv*8 + 2c + 1) of the tile
+      for (int c = 0; c < 4 && !(g.dbg & 1); ++c) {       // 32 pixels = image rows y0, y0+1 of the tile
         const int y0 = h0 + hv * 8 + 2 * c;
-        float res[32];
+        // element offset of pixel (y0, w0) ; pixel j of the chunk is at + ((j>>4)*W + (j&15)) * Cout
+        const int64_t o00 = (((int64_t)n * g.H + y0) * g.W + w0) * g.Cout;
+        const int rowstep = g.W * g.Cout;
+        float v[32];
         if (epi.residual) {
+          if (epi.res_half) {
+            const __half *rp = reinterpret_cast<const __half *>(epi.residual) + o00 + cbase + (lane & ~1) + (odd ? rowstep : 0);
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const int j = 4 * k + pl;                              // pixel inside the chunk
-            const int yh = y0 + (j >> 4), xw = w0 + (j & 15);
-            float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (yh < g.H && xw < g.W) {
-              const int64_t o = (img_base + (int64_t)yh * g.W + xw) * g.Cout + cbase + 4 * cq;
-              if (epi.res_half) {
-                uint2 u = *reinterpret_cast<const uint2 *>(reinterpret_cast<const __half *>(epi.residual) + o);
-                float2 f0 = __half22float2(*reinterpret_cast<__half2 *>(&u.x)), f1 = __half22float2(*reinterpret_cast<__half2 *>(&u.y));
-                rv = make_float4(f0.x, f0.y, f1.x, f1.y);
-              } else {
-                rv = *reinterpret_cast<const float4 *>(epi.residual + o);
-              }
+            for (int i = 0; i < 16; ++i) {        // this lane loads (ch pair) of pixel i (even lanes: row y0, odd lanes: row y0+1)
+              __half2 h2 = __floats2half2_rn(0.f, 0.f);
+              const bool ok = full || ((y0 + (odd ? 1 : 0) < g.H) && (w0 + i < g.W));
+              if (ok) h2 = *reinterpret_cast<const __half2 *>(rp + (int64_t)i * g.Cout);
+              const float2 f = __half22float2(h2);
+              const float mine = odd ? f.y : f.x, theirs = odd ? f.x : f.y;
+              const float got = __shfl_xor_sync(0xffffffffu, theirs, 1);
+              // even lane: own pixel i (row y0) = mine, partner's pixel 16+i (row y0+1) value of MY channel = got
+              v[i] = odd ? got : mine;
+              v[16 + i] = odd ? mine : got;
             }
-            // element (channel row 4*cq + i, pixel column j): word = row*32 + (((j>>2) ^ ((row>>2)&7)) << 2) + (j&3), row>>2 == cq
-            const int col = (((j >> 2) ^ cq) << 2) + (j & 3);
-            stg[(4 * cq + 0) * 32 + col] = rv.x; stg[(4 * cq + 1) * 32 + col] = rv.y;
-            stg[(4 * cq + 2) * 32 + col] = rv.z; stg[(4 * cq + 3) * 32 + col] = rv.w;
-          }
-          __syncwarp();
+          } else {
+            const float *rp = epi.residual + o00 + cbase + lane;
 #pragma unroll
-          for (int c4 = 0; c4 < 8; ++c4) {
-            float4 t4 = *reinterpret_cast<const float4 *>(stg + lane * 32 + ((c4 ^ swz_own) << 2));
-            res[4 * c4] = t4.x; res[4 * c4 + 1] = t4.y; res[4 * c4 + 2] = t4.z; res[4 * c4 + 3] = t4.w;
+            for (int j = 0; j < 32; ++j) {
+              const bool ok = full || ((y0 + (j >> 4) < g.H) && (w0 + (j & 15) < g.W));
+              v[j] = ok ? rp[(int64_t)(j >> 4) * rowstep + (int64_t)(j & 15) * g.Cout] : 0.f;
+            }
           }
-          __syncwarp();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0.f;
         }
         uint32_t r[32];
         tmem_ld32(tbase + (uint32_t)(c * 32), r);
         tmem_ld_wait();
+        if (full) {
 #pragma unroll
-        for (int c4 = 0; c4 < 8; ++c4) {
-          float4 t4;
-          float *tp = reinterpret_cast<float *>(&t4);
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int j = 4 * c4 + u;
-            float v = __uint_as_float(r[j]) + bch;
-            if (epi.residual) v += res[j];
-            const bool ok = (y0 + (j >> 4) < g.H) && (w0 + (j & 15) < g.W);      // warp-uniform
-            if (ok) { st_s += v; st_q += v * v; }
-            tp[u] = v;
+          for (int j = 0; j < 32; ++j) {
+            v[j] += __uint_as_float(r[j]) + bch;
+            st_s += v[j];
+            st_q = fmaf(v[j], v[j], st_q);
           }
-          *reinterpret_cast<float4 *>(stg + lane * 32 + ((c4 ^ swz_own) << 2)) = t4;
-        }
-        __syncwarp();
+        } else {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const int j = 4 * k + pl;
-          const int yh = y0 + (j >> 4), xw = w0 + (j & 15);
-          const int col = (((j >> 2) ^ cq) << 2) + (j & 3);
-          float4 ov = make_float4(stg[(4 * cq + 0) * 32 + col], stg[(4 * cq + 1) * 32 + col], stg[(4 * cq + 2) * 32 + col],
-                                  stg[(4 * cq + 3) * 32 + col]);
-          if (yh < g.H && xw < g.W) {
-            const int64_t o = (img_base + (int64_t)yh * g.W + xw) * g.Cout + cbase + 4 * cq;
-            if (epi.out_half) {
-              __half2 h0 = __floats2half2_rn(ov.x, ov.y), h1 = __floats2half2_rn(ov.z, ov.w);
-              uint2 u;
-              u.x = *reinterpret_cast<uint32_t *>(&h0); u.y = *reinterpret_cast<uint32_t *>(&h1);
-              *reinterpret_cast<uint2 *>(reinterpret_cast<__half *>(epi.out) + o) = u;
-            } else {
-              *reinterpret_cast<float4 *>(epi.out + o) = ov;
-            }
+          for (int j = 0; j < 32; ++j) {
+            v[j] += __uint_as_float(r[j]) + bch;
+            if ((y0 + (j >> 4) < g.H) && (w0 + (j & 15) < g.W)) { st_s += v[j]; st_q = fmaf(v[j], v[j], st_q); }
           }
         }
-        __syncwarp();
+        if (g.dbg & 16) continue;
+        if (epi.out_half) {
+          __half *op = reinterpret_cast<__half *>(epi.out) + o00 + cbase + (lane & ~1) + (odd ? rowstep : 0);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float send = odd ? v[i] : v[16 + i];          // what the partner lane needs: my channel at ITS pixel
+            const float got = __shfl_xor_sync(0xffffffffu, send, 1);
+            const float mine = odd ? v[16 + i] : v[i];
+            const __half2 h2 = odd ? __floats2half2_rn(got, mine) : __floats2half2_rn(mine, got);   // (even ch, odd ch)
+            const bool ok = full || ((y0 + (odd ? 1 : 0) < g.H) && (w0 + i < g.W));
+            if (ok) *reinterpret_cast<__half2 *>(op + (int64_t)i * g.Cout) = h2;
+          }
+        } else {
+          float *op = epi.out + o00 + cbase + lane;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const bool ok = full || ((y0 + (j >> 4) < g.H) && (w0 + (j & 15) < g.W));
+            if (ok) op[(int64_t)(j >> 4) * rowstep + (int64_t)(j & 15) * g.Cout] = v[j];
+          }
+        }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[ab]);
-      if (epi.qstats) {
+      if (epi.qstats && !(g.dbg & 8)) {
         st_s += __shfl_xor_sync(0xffffffffu, st_s, 1); st_q += __shfl_xor_sync(0xffffffffu, st_q, 1);
         st_s += __shfl_xor_sync(0xffffffffu, st_s, 2); st_q += __shfl_xor_sync(0xffffffffu, st_q, 2);
         if ((lane & 3) == 0) {
@@ -939,7 +939,7 @@ int conv_tc_plan_create(const void *act_half, const void *w_half, int B, int H, 
   p->use_v3 = g_force_v1 == 0;
   if (p->v2) {
     ConvV2Geom &g2 = p->g2;
-    g2.B = B; g2.H = H; g2.W = W; g2.Cin = Cin; g2.Cout = 0; g2.skip_chunks = 0;
+    g2.B = B; g2.H = H; g2.W = W; g2.Cin = Cin; g2.Cout = 0; g2.skip_chunks = 0; g2.dbg = 0;
     g2.tiles_w = cdiv(W, 16); g2.tiles_h = cdiv(H, 16); g2.n_tiles = CoutPad / 128;
     g2.total_tiles = B * g2.tiles_w * g2.tiles_h * g2.n_tiles;
   }
@@ -1037,6 +1037,9 @@ int launch_conv_tc(const ConvTcPlan *p, const ConvEpi &epi, int Cout, cudaStream
     }
     ConvV2Geom g2 = p->g2;
     g2.Cout = Cout;
+    static int dbg = -1;
+    if (dbg < 0) { const char *e = getenv("DPIR_CONV_DEBUG"); dbg = e ? atoi(e) : 0; }
+    g2.dbg = dbg;
     int grid = g2.total_tiles < g_num_sms ? g2.total_tiles : g_num_sms;
     if (p->use_v3) {
       k_conv3x3_v3<<<grid, V2_THREADS, V2_SMEM, st>>>(p->tmA, p->tmB, p->tmA2, p->tmB2, g2, epi);

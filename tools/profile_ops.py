@@ -22,7 +22,10 @@ def main():
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--json", default="")
     ap.add_argument("--warmup", type=int, default=2)
+    ap.add_argument("--variant", type=int, default=0, help="dpir_conv_tc_variant: 0 auto (v3), 1 v1, 2 v2")
     a = ap.parse_args()
+    from diffpir_b200 import _lib
+    _lib.check(_lib.load().dpir_conv_tc_variant(a.variant), "dpir_conv_tc_variant")
     cfg = arch.ffhq_config() if a.model == "ffhq" else arch.imagenet_config()
     m = UNetModel(cfg, precision=a.precision)
     m.load_state_dict(synth.synthetic_state_dict(cfg, 0))
@@ -32,6 +35,10 @@ def main():
     for _ in range(a.warmup):
         m.x0(x, t)
     torch.cuda.synchronize()
+    if a.reps <= 0:
+        torch.cuda.synchronize()
+        print("warm-up forwards only (no per-op timing requested)")
+        return
     m.profile_begin()
     for _ in range(a.reps):
         m.x0(x, t)
