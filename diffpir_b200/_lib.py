@@ -69,6 +69,8 @@ SIGNATURES = {
                                        c_int32, c_int32, c_void_p]),
     "dpir_conv_tc": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
                                c_int32, c_int32, c_int32, c_void_p]),
+    "dpir_conv_tc_f16io": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
+                                     c_int32, c_int32, c_int32, c_void_p]),
     "dpir_conv_tc_variant": (c_int32, [c_int32]),
     "dpir_conv_simt": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
                                  c_int32, c_int32, c_void_p]),

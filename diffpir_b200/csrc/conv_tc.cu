@@ -78,6 +78,16 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *m, uin
       : "memory");
 }
 
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap *m, const void *src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 template <int COLS> __device__ __forceinline__ void tmem_alloc(uint32_t *slot) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "n"(COLS) : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -377,6 +387,8 @@ constexpr int V2_STAGES = 2;
 constexpr int V2_THREADS = 320;                       // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
 constexpr int V2_STG_BYTES = 8 * 4096;                // per-epilogue-warp 32 x 128 B transpose buffers
 constexpr int V2_SMEM = V2_STAGES * V2_STAGE_BYTES + V2_STG_BYTES + 1024 + 256;
+constexpr int V3_STG_BYTES = 8 * 6144;                // v3: per-epilogue-warp fp16 tiles OUT, RES0, RES1 (2 KB each)
+constexpr int V3_SMEM = V2_STAGES * V2_STAGE_BYTES + V3_STG_BYTES + 1024 + 512;
 
 struct ConvV2Geom {
   int B, H, W, Cin, Cout;
@@ -676,18 +688,21 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_conv3x3_v2(const __grid_const
 __global__ void __launch_bounds__(V2_THREADS, 1) k_conv3x3_v3(const __grid_constant__ CUtensorMap tmA,
                                                                const __grid_constant__ CUtensorMap tmB,
                                                                const __grid_constant__ CUtensorMap tmA2,
-                                                               const __grid_constant__ CUtensorMap tmB2, ConvV2Geom g,
+                                                               const __grid_constant__ CUtensorMap tmB2,
+                                                               const __grid_constant__ CUtensorMap tmOut,
+                                                               const __grid_constant__ CUtensorMap tmRes, ConvV2Geom g,
                                                                ConvEpi epi) {
   // M = 128 (couts), N = 256 (pixels)
   constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t *stg_base = smem + V2_STAGES * V2_STAGE_BYTES;
-  uint64_t *full = reinterpret_cast<uint64_t *>(stg_base + V2_STG_BYTES);
+  uint8_t *stg_base = smem + V2_STAGES * V2_STAGE_BYTES;     // per epilogue warp: OUT, RES0, RES1 (2 KB each)
+  uint64_t *full = reinterpret_cast<uint64_t *>(stg_base + V3_STG_BYTES);
   uint64_t *empty = full + V2_STAGES;
   uint64_t *tmem_full = empty + V2_STAGES;     // [2]
   uint64_t *tmem_empty = tmem_full + 2;        // [2]
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+  uint64_t *res_full = tmem_empty + 2;         // [8 warps][2 buffers]
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(res_full + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int chunks = g.Cin / TC_BK;
@@ -700,6 +715,9 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_conv3x3_v3(const __grid_const
     if (g.skip_chunks) { tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmB2); }
     for (int s = 0; s < V2_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 8); }
+    for (int a = 0; a < 16; ++a) mbar_init(&res_full[a], 1);
+    tma_prefetch_desc(&tmOut);
+    if (epi.residual) tma_prefetch_desc(&tmRes);
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -775,15 +793,21 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_conv3x3_v3(const __grid_const
     }
   } else {
     // ---------------------------------------------------------------- epilogue: lane = output channel, column = pixel
-    // The epilogue is instruction-issue bound (ncu: ~6 cycles per issued instruction with 2 warps per scheduler), so it is
-    // written for minimum instruction count and needs no shared memory: a warp instruction touches ONE pixel (fp32: 32 lanes x
-    // 4 B = 128 contiguous bytes) or TWO pixels (fp16: neighbouring channel lanes swap half of their pixels with one
-    // shuffle, then even lanes write pixel j and odd lanes pixel j+16 as 16 x half2 = 64 contiguous bytes each).  The
-    // residual takes the mirrored route.  Interior tiles (the vast majority) take a path without any bounds predicates.
+    // fp16 in / fp16 out only (the fp16-stream pipeline).  The epilogue is bound by per-warp instruction latency (ncu: ~6
+    // cycles per issued instruction, 2 warps per scheduler), so it is built for minimum instruction count: no global
+    // load/store instructions, no bounds logic.  Per 32-pixel chunk a warp adds bias (+ residual) to its 32 ch x 32 px
+    // accumulator slice, writes it as fp16 into a [pixel][channel] 2 KB tile of shared memory (32 x STS.U16, each one 64
+    // contiguous bytes) and ONE thread issues a TMA tensor store of the {32 ch, 16 px, 2 rows} box; the hardware clips boxes
+    // that stick out of the image.  The residual box arrives the same way (TMA load, double buffered, prefetched one chunk
+    // ahead) and is read back column-wise (32 x LDS.U16).
     const int ew = warp - 2;              // 0..7
     const int q = warp & 3;               // TMEM lane quarter -> channels co0 + q*32 + lane
     const int hv = ew >> 2;               // which half of the tile's 256 pixels (image rows hv*8 .. hv*8+7)
-    const bool odd = lane & 1;
+    __half *outb = reinterpret_cast<__half *>(stg_base + ew * 6144);
+    __half *resb0 = outb + 1024, *resb1 = outb + 2048;
+    uint64_t *rbar = res_full + ew * 2;
+    uint32_t rcount = 0;                  // residual boxes consumed so far by this warp (buffer = rcount & 1, parity = (rcount >> 1) & 1)
+    const bool has_res = epi.residual != nullptr;
     uint32_t tc = 0;
     for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++tc) {
       const uint32_t ab = tc & 1u, aph = (tc >> 1) & 1u;
@@ -793,40 +817,31 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_conv3x3_v3(const __grid_const
       float bch = __ldg(epi.bias + cbase + lane);
       if (epi.bias2) bch += __ldg(epi.bias2 + cbase + lane);
       float st_s = 0.f, st_q = 0.f;
-      const bool full = (h0 + 16 <= g.H) && (w0 + 16 <= g.W);
+      const bool full_tile = (h0 + 16 <= g.H) && (w0 + 16 <= g.W);
+      const int ybase = h0 + hv * 8;
+      if (has_res && lane == 0) {          // prefetch the residual box of chunk 0
+        uint64_t *bar = &rbar[rcount & 1];
+        mbar_expect_tx(bar, 2048);
+        tma_load_4d((rcount & 1) ? resb1 : resb0, &tmRes, bar, cbase, w0, ybase, n);
+      }
       mbar_wait(&tmem_full[ab], aph);
       tc_fence_after();
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + ab * 256u + (uint32_t)hv * 128u;
 #pragma unroll 1
       for (int c = 0; c < 4 && !(g.dbg & 1); ++c) {       // 32 pixels = image rows y0, y0+1 of the tile
-        const int y0 = h0 + hv * 8 + 2 * c;
-        // element offset of pixel (y0, w0) ; pixel j of the chunk is at + ((j>>4)*W + (j&15)) * Cout
-        const int64_t o00 = (((int64_t)n * g.H + y0) * g.W + w0) * g.Cout;
-        const int rowstep = g.W * g.Cout;
+        const int y0 = ybase + 2 * c;
         float v[32];
-        if (epi.residual) {
-          if (epi.res_half) {
-            const __half *rp = reinterpret_cast<const __half *>(epi.residual) + o00 + cbase + (lane & ~1) + (odd ? rowstep : 0);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {        // this lane loads (ch pair) of pixel i (even lanes: row y0, odd lanes: row y0+1)
-              __half2 h2 = __floats2half2_rn(0.f, 0.f);
-              const bool ok = full || ((y0 + (odd ? 1 : 0) < g.H) && (w0 + i < g.W));
-              if (ok) h2 = *reinterpret_cast<const __half2 *>(rp + (int64_t)i * g.Cout);
-              const float2 f = __half22float2(h2);
-              const float mine = odd ? f.y : f.x, theirs = odd ? f.x : f.y;
-              const float got = __shfl_xor_sync(0xffffffffu, theirs, 1);
-              // even lane: own pixel i (row y0) = mine, partner's pixel 16+i (row y0+1) value of MY channel = got
-              v[i] = odd ? got : mine;
-              v[16 + i] = odd ? mine : got;
-            }
-          } else {
-            const float *rp = epi.residual + o00 + cbase + lane;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const bool ok = full || ((y0 + (j >> 4) < g.H) && (w0 + (j & 15) < g.W));
-              v[j] = ok ? rp[(int64_t)(j >> 4) * rowstep + (int64_t)(j & 15) * g.Cout] : 0.f;
-            }
+        if (has_res) {
+          if (c < 3 && lane == 0) {        // prefetch the next chunk's box into the other buffer (freed one iteration ago)
+            uint64_t *bar = &rbar[(rcount + 1) & 1];
+            mbar_expect_tx(bar, 2048);
+            tma_load_4d(((rcount + 1) & 1) ? resb1 : resb0, &tmRes, bar, cbase, w0, y0 + 2, n);
           }
+          mbar_wait(&rbar[rcount & 1], (rcount >> 1) & 1u);
+          const __half *rb = (rcount & 1) ? resb1 : resb0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __half2float(rb[j * 32 + lane]);
+          ++rcount;
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = 0.f;
@@ -834,7 +849,12 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_conv3x3_v3(const __grid_const
         uint32_t r[32];
         tmem_ld32(tbase + (uint32_t)(c * 32), r);
         tmem_ld_wait();
-        if (full) {
+        if (c == 3) {                      // accumulator fully read: hand it back to the MMA warp before the tail work
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[ab]);
+        }
+        if (full_tile) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             v[j] += __uint_as_float(r[j]) + bch;
@@ -848,30 +868,23 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_conv3x3_v3(const __grid_const
             if ((y0 + (j >> 4) < g.H) && (w0 + (j & 15) < g.W)) { st_s += v[j]; st_q = fmaf(v[j], v[j], st_q); }
           }
         }
-        if (g.dbg & 16) continue;
-        if (epi.out_half) {
-          __half *op = reinterpret_cast<__half *>(epi.out) + o00 + cbase + (lane & ~1) + (odd ? rowstep : 0);
+        // the previous chunk's TMA store must have finished reading the staging tile before it is overwritten
+        if (lane == 0) tma_store_wait_read0();
+        __syncwarp();
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float send = odd ? v[i] : v[16 + i];          // what the partner lane needs: my channel at ITS pixel
-            const float got = __shfl_xor_sync(0xffffffffu, send, 1);
-            const float mine = odd ? v[16 + i] : v[i];
-            const __half2 h2 = odd ? __floats2half2_rn(got, mine) : __floats2half2_rn(mine, got);   // (even ch, odd ch)
-            const bool ok = full || ((y0 + (odd ? 1 : 0) < g.H) && (w0 + i < g.W));
-            if (ok) *reinterpret_cast<__half2 *>(op + (int64_t)i * g.Cout) = h2;
-          }
-        } else {
-          float *op = epi.out + o00 + cbase + lane;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const bool ok = full || ((y0 + (j >> 4) < g.H) && (w0 + (j & 15) < g.W));
-            if (ok) op[(int64_t)(j >> 4) * rowstep + (int64_t)(j & 15) * g.Cout] = v[j];
-          }
+        for (int j = 0; j < 32; ++j) outb[j * 32 + lane] = __float2half_rn(v[j]);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0 && !(g.dbg & 16)) {
+          tma_store_4d(&tmOut, outb, cbase, w0, y0, n);
+          tma_store_commit();
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[ab]);
+      if (g.dbg & 1) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[ab]);
+      }
       if (epi.qstats && !(g.dbg & 8)) {
         st_s += __shfl_xor_sync(0xffffffffu, st_s, 1); st_q += __shfl_xor_sync(0xffffffffu, st_q, 1);
         st_s += __shfl_xor_sync(0xffffffffu, st_s, 2); st_q += __shfl_xor_sync(0xffffffffu, st_q, 2);
@@ -882,6 +895,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_conv3x3_v3(const __grid_const
         }
       }
     }
+    if (lane == 0) tma_store_wait_all0();      // all tensor stores of this warp have landed before the CTA retires
   }
   tc_fence_before();
   __syncthreads();
@@ -897,6 +911,10 @@ struct ConvTcPlan {
   bool use_v3 = true;     // swap-AB variant
   ConvV2Geom g2;
   CUtensorMap tmA2, tmB2; // fused 1x1 skip operand / weights (v2 only; copies of tmA/tmB when unused)
+  CUtensorMap tmOut, tmRes;   // v3: fp16 output / residual tensors for the TMA-store epilogue
+  bool io_half = false;       // tmOut (and tmRes when has_res) are valid
+  bool has_res = false;
+  const void *io_out = nullptr, *io_res = nullptr;
 };
 
 static int g_force_v1 = 0;   // dpir_conv_tc_variant: 0 = auto (persistent swap-AB v3), 1 = v1 everywhere, 2 = persistent v2
@@ -972,6 +990,36 @@ int conv_tc_plan_create(const void *act_half, const void *w_half, int B, int H, 
 
 bool conv_tc_plan_is_v2(const ConvTcPlan *p) { return p->v2; }
 
+// register the (fp16) output / residual tensors of a persistent-kernel plan so that the swap-AB kernel can use its
+// TMA-store epilogue; without it (or with fp32 tensors) the launch falls back to k_conv3x3_v2
+int conv_tc_plan_set_io(ConvTcPlan *p, const void *out, int out_half, const void *residual, int res_half, int Cout) {
+  p->io_half = false;
+  if (!p->v2 || !out_half || (residual && !res_half) || Cout % 32 != 0) return DPIR_OK;
+  auto encode = get_encode_fn();
+  if (!encode) { set_error("conv_tc: cuTensorMapEncodeTiled entry point unavailable"); return DPIR_E_CUDA; }
+  const ConvTcGeom &g = p->g;
+  auto make = [&](CUtensorMap *tm, const void *ptr) -> int {
+    cuuint64_t gdim[4] = {(cuuint64_t)Cout, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.B};
+    cuuint64_t gstr[3] = {(cuuint64_t)Cout * 2, (cuuint64_t)g.W * Cout * 2, (cuuint64_t)g.H * g.W * Cout * 2};
+    cuuint32_t box[4] = {32, 16, 2, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(ptr), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled(io) failed: %d", (int)r); return DPIR_E_CUDA; }
+    return DPIR_OK;
+  };
+  int rc = make(&p->tmOut, out);
+  if (rc) return rc;
+  p->tmRes = p->tmOut;
+  if (residual) { rc = make(&p->tmRes, residual); if (rc) return rc; }
+  p->io_half = true;
+  p->has_res = residual != nullptr;
+  p->io_out = out;
+  p->io_res = residual;
+  return DPIR_OK;
+}
+
 // attach a fused 1x1 convolution on a second NHWC fp16 operand (same B,H,W; Cin2 channels; weights [1][CoutPad][Cin2])
 int conv_tc_plan_add_skip(ConvTcPlan *p, const void *act2_half, const void *w2_half, int Cin2) {
   DPIR_REQUIRE(p->v2, "conv_tc: skip fusion needs the persistent 3x3 kernel");
@@ -1029,7 +1077,7 @@ int launch_conv_tc(const ConvTcPlan *p, const ConvEpi &epi, int Cout, cudaStream
     static bool attr_set = false;
     if (!attr_set) {
       DPIR_CUDA_CHECK(cudaFuncSetAttribute(k_conv3x3_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, V2_SMEM));
-      DPIR_CUDA_CHECK(cudaFuncSetAttribute(k_conv3x3_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, V2_SMEM));
+      DPIR_CUDA_CHECK(cudaFuncSetAttribute(k_conv3x3_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM));
       int dev = 0;
       DPIR_CUDA_CHECK(cudaGetDevice(&dev));
       DPIR_CUDA_CHECK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -1041,8 +1089,10 @@ int launch_conv_tc(const ConvTcPlan *p, const ConvEpi &epi, int Cout, cudaStream
     if (dbg < 0) { const char *e = getenv("DPIR_CONV_DEBUG"); dbg = e ? atoi(e) : 0; }
     g2.dbg = dbg;
     int grid = g2.total_tiles < g_num_sms ? g2.total_tiles : g_num_sms;
-    if (p->use_v3) {
-      k_conv3x3_v3<<<grid, V2_THREADS, V2_SMEM, st>>>(p->tmA, p->tmB, p->tmA2, p->tmB2, g2, epi);
+    const bool v3_ok = p->use_v3 && p->io_half && epi.out_half && epi.out == p->io_out && epi.residual == p->io_res &&
+                       (!epi.residual || epi.res_half);
+    if (v3_ok) {
+      k_conv3x3_v3<<<grid, V2_THREADS, V3_SMEM, st>>>(p->tmA, p->tmB, p->tmA2, p->tmB2, p->tmOut, p->tmRes, g2, epi);
     } else {
       DPIR_REQUIRE(!epi.residual || (epi.res_half != 0) == (epi.out_half != 0),
                    "conv_tc: the v2 persistent kernel needs residual and output of the same precision");

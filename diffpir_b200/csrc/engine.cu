@@ -653,6 +653,10 @@ int get_plan(dpir_engine *e, int B, int H, int W, Plan **out) {
       if (rc) return rc;
       op.tc = tp;
       plan->tc_plans.push_back(tp);
+      if (conv_tc_plan_is_v2(tp) && !op.bind_out) {
+        rc = conv_tc_plan_set_io(tp, op.epi.out, op.epi.out_half, op.epi.residual, op.epi.res_half, op.Cout);
+        if (rc) return rc;
+      }
       if (op.p2) {
         if (!conv_tc_plan_is_v2(tp)) { set_error("internal: skip fusion planned for a non-persistent conv"); return DPIR_E_STATE; }
         rc = conv_tc_plan_add_skip(tp, op.p2, op.w2, op.Cin2);
@@ -1052,6 +1056,23 @@ int dpir_conv_tc(const void *act, const void *w, const float *bias, const float 
   epi.mode = EPI_NHWC; epi.bias = bias; epi.residual = residual; epi.out = out;
   rc = launch_conv_tc(p, epi, Cout, (cudaStream_t)stream);
   conv_tc_plan_destroy(p);   // the tensor maps were copied into the launch parameters
+  return rc;
+}
+
+/* test entry for the fp16-stream form of the same convolution: fp16 residual (or NULL), fp16 NHWC output (this is the
+ * combination the swap-AB persistent kernel serves with its TMA-store epilogue) */
+int dpir_conv_tc_f16io(const void *act, const void *w, const float *bias, const void *residual_half, void *out_half, int32_t B,
+                       int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t CoutPad, int32_t ksize, void *stream) {
+  DPIR_REQUIRE(act && w && bias && out_half, "dpir_conv_tc_f16io: null pointer");
+  ConvTcPlan *p = nullptr;
+  int rc = conv_tc_plan_create(act, w, B, H, W, Cin, CoutPad, ksize, &p);
+  if (rc) return rc;
+  ConvEpi epi{};
+  epi.mode = EPI_NHWC; epi.bias = bias; epi.residual = reinterpret_cast<const float *>(residual_half);
+  epi.res_half = residual_half ? 1 : 0; epi.out = reinterpret_cast<float *>(out_half); epi.out_half = 1;
+  rc = conv_tc_plan_set_io(p, out_half, 1, residual_half, 1, Cout);
+  if (!rc) rc = launch_conv_tc(p, epi, Cout, (cudaStream_t)stream);
+  conv_tc_plan_destroy(p);
   return rc;
 }
 

@@ -224,6 +224,9 @@ int dpir_measure_blur_u8(const uint8_t *img_nhwc, const double *k, const float *
 int dpir_conv_tc(const void *act, const void *w, const float *bias, const float *residual, float *out,
                  int32_t B, int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t CoutPad, int32_t ksize,
                  void *stream);
+/* the same convolution in its fp16-stream form: residual fp16 NHWC (or NULL), output fp16 NHWC. */
+int dpir_conv_tc_f16io(const void *act, const void *w, const float *bias, const void *residual_half, void *out_half, int32_t B,
+                       int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t CoutPad, int32_t ksize, void *stream);
 /* A/B switch for tests and benchmarks.  0 (default): 3x3 convs on >=16x16 maps use the persistent swap-AB halo-reuse
  * kernel (k_conv3x3_v3), everything else the one-tile-per-CTA kernel (k_conv_tc); 1: k_conv_tc everywhere;
  * 2: the persistent kernel with pixels on the M side (k_conv3x3_v2).  Affects plans created afterwards. */

@@ -117,3 +117,31 @@ def test_conv_simt_matches_torch(B, H, W, Cin, Cout, k, residual):
                                   Cout, k, _lib.stream_ptr()), "dpir_conv_simt")
     torch.cuda.synchronize()
     assert rel_l2(out.permute(0, 3, 1, 2), ref) < 2e-6
+
+
+@pytest.mark.parametrize("variant", ["auto", "v2", "v1"])
+@pytest.mark.parametrize("B,H,W,Cin,Cout,residual", [
+    (2, 32, 32, 128, 128, True), (3, 64, 64, 128, 256, False), (1, 24, 40, 192, 128, True),
+    (5, 16, 16, 256, 512, True), (2, 48, 80, 128, 128, False), (1, 256, 256, 128, 128, True), (2, 8, 8, 256, 128, True),
+])
+def test_conv_tc_fp16_stream_io_matches_torch(B, H, W, Cin, Cout, residual, variant):
+    """fp16 residual + fp16 output (the fp16-stream pipeline; on >=16x16 maps the swap-AB kernel with TMA-store epilogue)."""
+    from diffpir_b200 import _lib
+    lib = _lib.load()
+    lib.dpir_conv_tc_variant({"auto": 0, "v1": 1, "v2": 2}[variant])
+    x, w, b, r = _case(B, H, W, Cin, Cout, 3, 5, residual)
+    rh = r.half() if r is not None else None
+    ref = F.conv2d(x.half().double(), w.half().double(), b.double(), padding=1)
+    if rh is not None:
+        ref = ref + rh.double()
+    act = x.permute(0, 2, 3, 1).contiguous().half().cuda()
+    wp = _pack_tc(w, Cout).cuda()
+    res = rh.permute(0, 2, 3, 1).contiguous().cuda() if rh is not None else None
+    out = torch.full((B, H, W, Cout), float("nan"), device="cuda", dtype=torch.float16)
+    _lib.check(lib.dpir_conv_tc_f16io(_lib.ptr(act), _lib.ptr(wp), _lib.ptr(b.cuda()), _lib.ptr(res), _lib.ptr(out), B, H, W, Cin,
+                                      Cout, Cout, 3, _lib.stream_ptr()), "dpir_conv_tc_f16io")
+    torch.cuda.synchronize()
+    lib.dpir_conv_tc_variant(0)
+    got = out.permute(0, 3, 1, 2).float()
+    assert not torch.isnan(got).any()
+    assert rel_l2(got, ref) < 6e-4      # fp16 rounding of the stored result
