@@ -226,7 +226,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--batch", type=int, default=32)
-    ap.add_argument("--precision", default="fp16", choices=["fp16", "fp16s", "fp32"])
+    ap.add_argument("--precision", default="fp16s", choices=["fp16", "fp16s", "fp32"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-steps", type=int, default=3)
