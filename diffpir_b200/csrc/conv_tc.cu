@@ -953,9 +953,9 @@ int conv_tc_plan_create(const void *act_half, const void *w_half, int B, int H, 
   g.tiles_w = cdiv(W, g.TW); g.tiles_h = cdiv(H, g.TH); g.tiles_n = cdiv(B, g.TN);
   p->BN = CoutPad == 16 ? 16 : 128;
   p->CoutPad = CoutPad;
-  // small maps (8x8, 16x16 1x1): 128-wide cout tiles would leave most of the 148 SMs idle -> 64-wide tiles
-  if (CoutPad != 16 && g.tiles_w * g.tiles_h * g.tiles_n * (CoutPad / 128) < 100) p->BN = 64;
   p->v2 = g_force_v1 != 1 && ksize == 3 && H >= 16 && W >= 16 && CoutPad % 128 == 0;
+  // one-tile-per-CTA kernel on small maps (8x8, 16x16 1x1): 128-wide cout tiles would leave most of the 148 SMs idle
+  if (!p->v2 && CoutPad != 16 && g.tiles_w * g.tiles_h * g.tiles_n * (CoutPad / 128) < 100) p->BN = 64;
   p->use_v3 = g_force_v1 == 0;
   if (p->v2) {
     ConvV2Geom &g2 = p->g2;

@@ -10,6 +10,7 @@
 // Layout: activations NHWC so that channels are the contiguous (coalesced, float4) dimension and so that the same
 // buffers feed the tcgen05 implicit-GEMM convolution (conv_tc.cu) as K-major operands.
 #include "unet_kernels.cuh"
+#include <mma.h>
 
 namespace dpir {
 
@@ -29,14 +30,21 @@ template <> struct Store4<__half> {
 };
 template <typename T> struct Load4;
 template <> struct Load4<float> {
+  typedef float4 raw_t;
+  static constexpr int UNROLL = 4;
+  static __device__ __forceinline__ raw_t raw(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+  static __device__ __forceinline__ float4 cvt(raw_t r) { return r; }
   static __device__ __forceinline__ float4 ld(const float *p) { return *reinterpret_cast<const float4 *>(p); }
 };
 template <> struct Load4<__half> {
-  static __device__ __forceinline__ float4 ld(const __half *p) {
-    uint2 u = *reinterpret_cast<const uint2 *>(p);
+  typedef uint2 raw_t;
+  static constexpr int UNROLL = 8;      // 8 x 8 B in flight per thread: the streaming passes need ~45 KB in flight per SM
+  static __device__ __forceinline__ raw_t raw(const __half *p) { return *reinterpret_cast<const uint2 *>(p); }
+  static __device__ __forceinline__ float4 cvt(raw_t u) {
     float2 a = __half22float2(*reinterpret_cast<__half2 *>(&u.x)), b = __half22float2(*reinterpret_cast<__half2 *>(&u.y));
     return make_float4(a.x, a.y, b.x, b.y);
   }
+  static __device__ __forceinline__ float4 ld(const __half *p) { return cvt(raw(p)); }
 };
 
 // =========================================================================================== input stem
@@ -221,7 +229,7 @@ __device__ __forceinline__ float4 gn_act(float4 v, float mean, float rstd, float
   return o;
 }
 
-constexpr int GN_APPLY_PIX = 128;  // work pixels per block
+constexpr int GN_APPLY_PIX = 256;  // work pixels per block
 constexpr int GN_UNROLL = 4;
 
 // MODE none: one work pixel = one pixel.  MODE down: work pixel = output pixel (reads 2x2 inputs, averages the
@@ -274,16 +282,18 @@ __global__ void k_gn_apply(GnDev a, T *__restrict__ act, T *__restrict__ rawact)
   int64_t obase = (int64_t)b * Ho * Wo;
   if (MODE == RS_NONE) {
     int p = p0 + lane_p;
-    for (; p + (GN_UNROLL - 1) * ppb < p1; p += GN_UNROLL * ppb) {
-      float4 v[GN_UNROLL];
+    constexpr int UN = Load4<TI>::UNROLL;
+    for (; p + (UN - 1) * ppb < p1; p += UN * ppb) {
+      typename Load4<TI>::raw_t rv[UN];
 #pragma unroll
-      for (int u = 0; u < GN_UNROLL; ++u) v[u] = Load4<TI>::ld(src + (int64_t)(p + u * ppb) * Cs + cc);
+      for (int u = 0; u < UN; ++u) rv[u] = Load4<TI>::raw(src + (int64_t)(p + u * ppb) * Cs + cc);
 #pragma unroll
-      for (int u = 0; u < GN_UNROLL; ++u) {
+      for (int u = 0; u < UN; ++u) {
+        const float4 v = Load4<TI>::cvt(rv[u]);
         int64_t o = (obase + p + u * ppb) * C + c4 * 4;
-        Store4<T>::st(act + o, gn_act<FAST>(v[u], mean, rstd, ga, be, has_film, sc, sh, a.silu));
-        if (a.raw32) *reinterpret_cast<float4 *>(a.raw32 + o) = v[u];
-        if (rawact) Store4<T>::st(rawact + o, v[u]);
+        Store4<T>::st(act + o, gn_act<FAST>(v, mean, rstd, ga, be, has_film, sc, sh, a.silu));
+        if (a.raw32) *reinterpret_cast<float4 *>(a.raw32 + o) = v;
+        if (rawact) Store4<T>::st(rawact + o, v);
       }
     }
     for (; p < p1; p += ppb) {
@@ -330,136 +340,6 @@ __global__ void k_gn_apply(GnDev a, T *__restrict__ act, T *__restrict__ rawact)
   }
 }
 
-// fp16 -> fp16 variant with 8 channels (16 bytes) per thread: twice the bytes in flight per thread of the generic kernel,
-// which is what this pure streaming pass needs to approach the HBM roofline.  An aligned channel quad never straddles a
-// group (C % 128 == 0), so the 8-vector is normalised as two quads with their own (mean, rstd).
-struct H8 { float4 lo, hi; };
-__device__ __forceinline__ H8 ld_h8(const __half *p) {
-  uint4 u = *reinterpret_cast<const uint4 *>(p);
-  float2 a = __half22float2(*reinterpret_cast<__half2 *>(&u.x)), b = __half22float2(*reinterpret_cast<__half2 *>(&u.y));
-  float2 c = __half22float2(*reinterpret_cast<__half2 *>(&u.z)), d = __half22float2(*reinterpret_cast<__half2 *>(&u.w));
-  return H8{make_float4(a.x, a.y, b.x, b.y), make_float4(c.x, c.y, d.x, d.y)};
-}
-__device__ __forceinline__ void st_h8(__half *p, float4 lo, float4 hi) {
-  __half2 a = __floats2half2_rn(lo.x, lo.y), b = __floats2half2_rn(lo.z, lo.w);
-  __half2 c = __floats2half2_rn(hi.x, hi.y), d = __floats2half2_rn(hi.z, hi.w);
-  uint4 u;
-  u.x = *reinterpret_cast<uint32_t *>(&a); u.y = *reinterpret_cast<uint32_t *>(&b);
-  u.z = *reinterpret_cast<uint32_t *>(&c); u.w = *reinterpret_cast<uint32_t *>(&d);
-  *reinterpret_cast<uint4 *>(p) = u;
-}
-
-template <int MODE>
-__global__ void k_gn_apply_h8(GnDev a, __half *__restrict__ act, __half *__restrict__ rawact) {
-  __shared__ float s_mean[32], s_rstd[32];
-  const int C = a.C1 + a.C2, C8 = C / 8, C4 = C / 4;
-  const int b = blockIdx.y;
-  const int H = a.H, W = a.W, HW = H * W;
-  if (threadIdx.x < 32) {
-    int qpg = C4 / 32, Q1 = a.C1 / 4;
-    double su = 0.0, sq = 0.0;
-    for (int j = 0; j < qpg; ++j) {
-      int q = threadIdx.x * qpg + j;
-      const double *src = q < Q1 ? a.q1 + ((int64_t)b * Q1 + q) * 2 : a.q2 + ((int64_t)b * (C4 - Q1) + (q - Q1)) * 2;
-      su += src[0];
-      sq += src[1];
-    }
-    double n = (double)HW * (double)(C / 32);
-    double mean = su / n;
-    double var = sq / n - mean * mean;
-    if (var < 0.0) var = 0.0;
-    s_mean[threadIdx.x] = (float)mean;
-    s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + 1e-5));
-  }
-  __syncthreads();
-  const int ppb = blockDim.x / C8;
-  const int lane_p = threadIdx.x / C8, c8 = threadIdx.x % C8;
-  if (lane_p >= ppb) return;
-  const int cg = C / 32;
-  const int g0 = (8 * c8) / cg, g1 = (8 * c8 + 4) / cg;
-  const float m0 = s_mean[g0], r0 = s_rstd[g0], m1 = s_mean[g1], r1 = s_rstd[g1];
-  const float4 ga0 = reinterpret_cast<const float4 *>(a.gamma)[2 * c8], ga1 = reinterpret_cast<const float4 *>(a.gamma)[2 * c8 + 1];
-  const float4 be0 = reinterpret_cast<const float4 *>(a.beta)[2 * c8], be1 = reinterpret_cast<const float4 *>(a.beta)[2 * c8 + 1];
-  const bool has_film = a.film != nullptr;
-  float4 sc0 = make_float4(0, 0, 0, 0), sc1 = sc0, sh0 = sc0, sh1 = sc0;
-  if (has_film) {
-    const float *f = a.film + (a.tsteps ? a.tsteps[b] : (int64_t)b) * a.film_stride;
-    sc0 = reinterpret_cast<const float4 *>(f)[2 * c8]; sc1 = reinterpret_cast<const float4 *>(f)[2 * c8 + 1];
-    sh0 = reinterpret_cast<const float4 *>(f + C)[2 * c8]; sh1 = reinterpret_cast<const float4 *>(f + C)[2 * c8 + 1];
-  }
-  const __half *src; int Cs, cc;
-  if (c8 * 8 < a.C1) { src = reinterpret_cast<const __half *>(a.s1) + (int64_t)b * HW * a.C1; Cs = a.C1; cc = c8 * 8; }
-  else               { src = reinterpret_cast<const __half *>(a.s2) + (int64_t)b * HW * a.C2; Cs = a.C2; cc = c8 * 8 - a.C1; }
-  const int Hw = (MODE == RS_DOWN) ? H / 2 : H, Ww = (MODE == RS_DOWN) ? W / 2 : W;
-  const int Ho = (MODE == RS_UP) ? H * 2 : Hw, Wo = (MODE == RS_UP) ? W * 2 : Ww;
-  const int nwork = Hw * Ww;
-  const int p0 = blockIdx.x * GN_APPLY_PIX;
-  const int p1 = min(p0 + GN_APPLY_PIX, nwork);
-  const int64_t obase = (int64_t)b * Ho * Wo;
-  auto act8 = [&](const H8 &v, float4 &olo, float4 &ohi) {
-    olo = gn_act<true>(v.lo, m0, r0, ga0, be0, has_film, sc0, sh0, a.silu);
-    ohi = gn_act<true>(v.hi, m1, r1, ga1, be1, has_film, sc1, sh1, a.silu);
-  };
-  if (MODE == RS_NONE) {
-    int p = p0 + lane_p;
-    for (; p + (GN_UNROLL - 1) * ppb < p1; p += GN_UNROLL * ppb) {
-      H8 v[GN_UNROLL];
-#pragma unroll
-      for (int u = 0; u < GN_UNROLL; ++u) v[u] = ld_h8(src + (int64_t)(p + u * ppb) * Cs + cc);
-#pragma unroll
-      for (int u = 0; u < GN_UNROLL; ++u) {
-        const int64_t o = (obase + p + u * ppb) * C + c8 * 8;
-        float4 lo, hi;
-        act8(v[u], lo, hi);
-        st_h8(act + o, lo, hi);
-        if (rawact) st_h8(rawact + o, v[u].lo, v[u].hi);
-      }
-    }
-    for (; p < p1; p += ppb) {
-      H8 v = ld_h8(src + (int64_t)p * Cs + cc);
-      const int64_t o = (obase + p) * C + c8 * 8;
-      float4 lo, hi;
-      act8(v, lo, hi);
-      st_h8(act + o, lo, hi);
-      if (rawact) st_h8(rawact + o, v.lo, v.hi);
-    }
-  } else if (MODE == RS_DOWN) {
-    for (int p = p0 + lane_p; p < p1; p += ppb) {
-      const int yo = p / Ww, xo = p % Ww;
-      H8 v[4];
-#pragma unroll
-      for (int d = 0; d < 4; ++d) v[d] = ld_h8(src + ((int64_t)(2 * yo + (d >> 1)) * W + 2 * xo + (d & 1)) * Cs + cc);
-      float4 al = make_float4(0, 0, 0, 0), ah = al, rl = al, rh = al;
-#pragma unroll
-      for (int d = 0; d < 4; ++d) {
-        float4 lo, hi;
-        act8(v[d], lo, hi);
-        al.x += lo.x; al.y += lo.y; al.z += lo.z; al.w += lo.w; ah.x += hi.x; ah.y += hi.y; ah.z += hi.z; ah.w += hi.w;
-        rl.x += v[d].lo.x; rl.y += v[d].lo.y; rl.z += v[d].lo.z; rl.w += v[d].lo.w;
-        rh.x += v[d].hi.x; rh.y += v[d].hi.y; rh.z += v[d].hi.z; rh.w += v[d].hi.w;
-      }
-      al.x *= .25f; al.y *= .25f; al.z *= .25f; al.w *= .25f; ah.x *= .25f; ah.y *= .25f; ah.z *= .25f; ah.w *= .25f;
-      rl.x *= .25f; rl.y *= .25f; rl.z *= .25f; rl.w *= .25f; rh.x *= .25f; rh.y *= .25f; rh.z *= .25f; rh.w *= .25f;
-      const int64_t o = (obase + p) * C + c8 * 8;
-      st_h8(act + o, al, ah);
-      if (rawact) st_h8(rawact + o, rl, rh);
-    }
-  } else {
-    for (int p = p0 + lane_p; p < p1; p += ppb) {
-      const int yi = p / W, xi = p % W;
-      H8 v = ld_h8(src + (int64_t)p * Cs + cc);
-      float4 lo, hi;
-      act8(v, lo, hi);
-#pragma unroll
-      for (int d = 0; d < 4; ++d) {
-        const int64_t q = (obase + (int64_t)(2 * yi + (d >> 1)) * Wo + 2 * xi + (d & 1)) * C + c8 * 8;
-        st_h8(act + q, lo, hi);
-        if (rawact) st_h8(rawact + q, v.lo, v.hi);
-      }
-    }
-  }
-}
-
 int launch_gn_apply(const GnApplyArgs &a, cudaStream_t st) {
   int C = a.C1 + a.C2;
   DPIR_REQUIRE(C % 128 == 0 && a.C1 % 4 == 0 && C <= 4096, "gn_apply: channels must be a multiple of 128 (got %d)", C);
@@ -471,14 +351,7 @@ int launch_gn_apply(const GnApplyArgs &a, cudaStream_t st) {
   dim3 grid(cdiv(nwork, GN_APPLY_PIX), a.B);
   int threads = gn_threads(C);
 #define GN_LAUNCH(T, TI, M) k_gn_apply<T, TI, M><<<grid, threads, 0, st>>>(d, (T *)a.act, (T *)a.rawact)
-  if (a.out_half && a.src_half && a.C1 % 8 == 0 && C / 8 <= 256) {
-    int C8 = C / 8;
-    int ppb = 256 / C8 > 0 ? 256 / C8 : 1;
-    int th8 = C8 * ppb;
-    if (a.resample == RS_NONE) k_gn_apply_h8<RS_NONE><<<grid, th8, 0, st>>>(d, (__half *)a.act, (__half *)a.rawact);
-    else if (a.resample == RS_DOWN) k_gn_apply_h8<RS_DOWN><<<grid, th8, 0, st>>>(d, (__half *)a.act, (__half *)a.rawact);
-    else k_gn_apply_h8<RS_UP><<<grid, th8, 0, st>>>(d, (__half *)a.act, (__half *)a.rawact);
-  } else if (a.out_half && a.src_half) {
+  if (a.out_half && a.src_half) {
     if (a.resample == RS_NONE) GN_LAUNCH(__half, __half, RS_NONE);
     else if (a.resample == RS_DOWN) GN_LAUNCH(__half, __half, RS_DOWN);
     else GN_LAUNCH(__half, __half, RS_UP);
@@ -683,6 +556,137 @@ __global__ void __launch_bounds__(256) k_attention(const float *__restrict__ qkv
   }
 }
 
+// fp16-operand / fp32-accumulate variant for the tensor-core pipelines (legacy warp-level HMMA via nvcuda::wmma: attention
+// is 0.1 % of the UNet FLOPs, so it gets tensor cores the cheap way; q, k, v are rounded to fp16 exactly like every other
+// GEMM operand of this mode, the softmax stays fp32).  One CTA = 64 queries of one (sample, head); 4 warps x 16 query rows.
+// Per 64-key tile: S = Q K^T (16 HMMA per warp) -> smem -> online softmax (fp32, 2 lanes per row) -> P (fp16) -> O += P V
+// with O kept in shared memory so that the per-row rescale needs no knowledge of the fragment layout.
+constexpr int ATW_LDH = 72;    // half row pitch (64 + 8: keeps 16-byte alignment, spreads banks)
+constexpr int ATW_LDF = 68;    // float row pitch
+
+template <typename T>
+__global__ void __launch_bounds__(128) k_attention_wmma(const float *__restrict__ qkv, T *__restrict__ out, int Tn, int C,
+                                                        int heads, int new_order) {
+  using namespace nvcuda;
+  extern __shared__ __align__(32) uint8_t smraw[];
+  __half *Qh = reinterpret_cast<__half *>(smraw);                 // [64][72]
+  __half *Kh = Qh + 64 * ATW_LDH;                                  // [64][72]
+  __half *Vh = Kh + 64 * ATW_LDH;                                  // [64][72]
+  __half *Ph = Vh + 64 * ATW_LDH;                                  // [64][72]
+  float *Sf = reinterpret_cast<float *>(Ph + 64 * ATW_LDH);        // [64][68]  scores of the current key tile
+  float *Of = Sf + 64 * ATW_LDF;                                   // [64][68]  running output
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q0 = blockIdx.x * 64, h = blockIdx.y, b = blockIdx.z;
+  const int C3 = 3 * C;
+  int qoff, koff, voff;
+  if (new_order) { qoff = h * 64; koff = C + h * 64; voff = 2 * C + h * 64; }
+  else           { qoff = h * 192; koff = qoff + 64; voff = qoff + 128; }
+  const float *base = qkv + (int64_t)b * Tn * C3;
+  // stage Q (scaled by ch^-1/4 like the reference: q * scale, k * scale) and zero O
+  const float sc = 0.35355339059327373f;   // 64^-0.25
+  for (int i = tid; i < 64 * 16; i += 128) {
+    int r = i >> 4, d4 = (i & 15) * 4;
+    float4 v = *reinterpret_cast<const float4 *>(base + (int64_t)(q0 + r) * C3 + qoff + d4);
+    __half2 a = __floats2half2_rn(v.x * sc, v.y * sc), c = __floats2half2_rn(v.z * sc, v.w * sc);
+    *reinterpret_cast<__half2 *>(Qh + r * ATW_LDH + d4) = a;
+    *reinterpret_cast<__half2 *>(Qh + r * ATW_LDH + d4 + 2) = c;
+    *reinterpret_cast<float4 *>(Of + r * ATW_LDF + d4) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  // each row is owned by 2 lanes of its warp: row = warp*16 + lane/2, columns (lane&1)*32 .. +31
+  const int myrow = warp * 16 + (lane >> 1), mycol = (lane & 1) * 32;
+  float m_run = -INFINITY, l_run = 0.f;
+  for (int k0 = 0; k0 < Tn; k0 += 64) {
+    __syncthreads();
+    for (int i = tid; i < 64 * 16; i += 128) {
+      int r = i >> 4, d4 = (i & 15) * 4;
+      const float *rowp = base + (int64_t)(k0 + r) * C3;
+      float4 kv = *reinterpret_cast<const float4 *>(rowp + koff + d4);
+      float4 vv = *reinterpret_cast<const float4 *>(rowp + voff + d4);
+      *reinterpret_cast<__half2 *>(Kh + r * ATW_LDH + d4) = __floats2half2_rn(kv.x * sc, kv.y * sc);
+      *reinterpret_cast<__half2 *>(Kh + r * ATW_LDH + d4 + 2) = __floats2half2_rn(kv.z * sc, kv.w * sc);
+      *reinterpret_cast<__half2 *>(Vh + r * ATW_LDH + d4) = __floats2half2_rn(vv.x, vv.y);
+      *reinterpret_cast<__half2 *>(Vh + r * ATW_LDH + d4 + 2) = __floats2half2_rn(vv.z, vv.w);
+    }
+    __syncthreads();
+    // S[16 x 64] = Q[16 x 64] K^T
+    {
+      wmma::fragment<wmma::accumulator, 16, 16, 16, float> acc[4];
+#pragma unroll
+      for (int n = 0; n < 4; ++n) wmma::fill_fragment(acc[n], 0.f);
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        wmma::fragment<wmma::matrix_a, 16, 16, 16, __half, wmma::row_major> a;
+        wmma::load_matrix_sync(a, Qh + warp * 16 * ATW_LDH + kk * 16, ATW_LDH);
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+          wmma::fragment<wmma::matrix_b, 16, 16, 16, __half, wmma::col_major> bf;   // B[k=d][n=key] = Kh[key][d]
+          wmma::load_matrix_sync(bf, Kh + n * 16 * ATW_LDH + kk * 16, ATW_LDH);
+          wmma::mma_sync(acc[n], a, bf, acc[n]);
+        }
+      }
+#pragma unroll
+      for (int n = 0; n < 4; ++n) wmma::store_matrix_sync(Sf + warp * 16 * ATW_LDF + n * 16, acc[n], ATW_LDF, wmma::mem_row_major);
+    }
+    __syncwarp();
+    // online softmax on this warp's 16 rows (2 lanes per row)
+    {
+      float *srow = Sf + myrow * ATW_LDF + mycol;
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) mx = fmaxf(mx, srow[j]);
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      const float m_new = fmaxf(m_run, mx);
+      const float corr = expf(m_run - m_new);
+      float ps = 0.f;
+      __half *prow = Ph + myrow * ATW_LDH + mycol;
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) {
+        float e0 = expf(srow[j] - m_new), e1 = expf(srow[j + 1] - m_new);
+        __half2 hp = __floats2half2_rn(e0, e1);
+        // sum what is actually multiplied into V (the fp16-rounded probabilities) so that rows stay normalised
+        float2 back = __half22float2(hp);
+        ps += back.x + back.y;
+        *reinterpret_cast<__half2 *>(prow + j) = hp;
+      }
+      ps += __shfl_xor_sync(0xffffffffu, ps, 1);
+      l_run = l_run * corr + ps;
+      m_run = m_new;
+      float *orow = Of + myrow * ATW_LDF + mycol;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) orow[j] *= corr;
+    }
+    __syncwarp();
+    // O[16 x 64] += P[16 x 64] V[64 x 64]
+    {
+      wmma::fragment<wmma::accumulator, 16, 16, 16, float> acc[4];
+#pragma unroll
+      for (int n = 0; n < 4; ++n) wmma::load_matrix_sync(acc[n], Of + warp * 16 * ATW_LDF + n * 16, ATW_LDF, wmma::mem_row_major);
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        wmma::fragment<wmma::matrix_a, 16, 16, 16, __half, wmma::row_major> a;
+        wmma::load_matrix_sync(a, Ph + warp * 16 * ATW_LDH + kk * 16, ATW_LDH);
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+          wmma::fragment<wmma::matrix_b, 16, 16, 16, __half, wmma::row_major> bf;   // B[k=key][n=ch] = Vh[key][ch]
+          wmma::load_matrix_sync(bf, Vh + kk * 16 * ATW_LDH + n * 16, ATW_LDH);
+          wmma::mma_sync(acc[n], a, bf, acc[n]);
+        }
+      }
+#pragma unroll
+      for (int n = 0; n < 4; ++n) wmma::store_matrix_sync(Of + warp * 16 * ATW_LDF + n * 16, acc[n], ATW_LDF, wmma::mem_row_major);
+    }
+  }
+  __syncwarp();
+  {
+    const float inv = 1.f / l_run;
+    const float *orow = Of + myrow * ATW_LDF + mycol;
+    T *dst = out + ((int64_t)b * Tn + q0 + myrow) * C + h * 64 + mycol;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4)
+      Store4<T>::st(dst + j, make_float4(orow[j] * inv, orow[j + 1] * inv, orow[j + 2] * inv, orow[j + 3] * inv));
+  }
+}
+
 int launch_attention(const float *qkv, void *out, int out_half, int B, int T, int C, int heads, int new_order, cudaStream_t st) {
   DPIR_REQUIRE(C == heads * AT_D, "attention: head dim must be 64 (C=%d heads=%d)", C, heads);
   DPIR_REQUIRE(T % AT_Q == 0, "attention: token count must be a multiple of 64 (got %d)", T);
@@ -694,8 +698,18 @@ int launch_attention(const float *qkv, void *out, int out_half, int B, int T, in
     DPIR_CUDA_CHECK(cudaFuncSetAttribute(k_attention<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  if (out_half) k_attention<__half><<<grid, 256, smem, st>>>(qkv, (__half *)out, T, C, heads, new_order);
-  else k_attention<float><<<grid, 256, smem, st>>>(qkv, (float *)out, T, C, heads, new_order);
+  if (out_half) {
+    // tensor-core pipelines: fp16 operands on HMMA; the fp32 parity mode below keeps the fp32 CUDA-core kernel
+    constexpr size_t smem_w = (size_t)4 * 64 * ATW_LDH * sizeof(__half) + (size_t)2 * 64 * ATW_LDF * sizeof(float);
+    static bool attr_w = false;
+    if (!attr_w) {
+      DPIR_CUDA_CHECK(cudaFuncSetAttribute(k_attention_wmma<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
+      attr_w = true;
+    }
+    k_attention_wmma<__half><<<grid, 128, smem_w, st>>>(qkv, (__half *)out, T, C, heads, new_order);
+  } else {
+    k_attention<float><<<grid, 256, smem, st>>>(qkv, (float *)out, T, C, heads, new_order);
+  }
   DPIR_LAUNCH_CHECK();
   return DPIR_OK;
 }
