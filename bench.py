@@ -230,6 +230,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-steps", type=int, default=3)
+    ap.add_argument("--gn-fusion", type=int, default=1, choices=[0, 1, 2],
+                    help="ResBlock GroupNorm+SiLU inside the convolutions: 1 (default, fp32 operand arithmetic), 2 (packed half), 0 separate passes")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -269,6 +271,7 @@ def main():
         torch.cuda.synchronize()
         t_bcast_ms = e0.elapsed_time(e1)
         model.mark_weights_loaded()
+    model.set_gn_fusion(args.gn_fusion)
     if not args.no_graph:
         model.set_graph_mode(True)
 
@@ -384,6 +387,35 @@ def main():
                     "algorithmic_gflop_per_step": conv_flops / 1e9,
                     "whole_step_tflops": world * B * arch.flops_per_image(cfg) / (ms_step * 1e-3) / 1e12}
 
+    # ------------------------------------------------------------------ HBM roofline of the prox / re-noise kernels
+    prox = None
+    if rank == 0:
+        peaks = load_peaks()
+        hbm = peaks.get("hbm_gbs", FALLBACK_PEAKS["hbm_gbs"])
+        st = steps_tab[10]
+        reps = 20
+
+        def timed(fn):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / reps
+
+        ms_fft = timed(lambda: utils_sisr.data_solution_fused(x0, FB, F2B, FBFy, st["rho"], 1, 0.5, 0.5, 2.0, -1.0, 1.0, out=x0, spec=spec))
+        ms_rn = timed(lambda: ops.renoise(x, x0, noise, st["sa_t"], st["s1_t"], st["sa_p"], st["c_eps"], st["c_zeta"], out=x))
+        by_fft, by_rn = 2497536 * B, 3145728 * B          # algorithmic bytes per image per step, SURVEY.md section 8(d)
+        prox = {"bound": "hbm", "peak": hbm, "unit": "GB/s", "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peaks['_source']})",
+                "fft_data_solution": {"ms": ms_fft, "algorithmic_bytes": by_fft, "achieved": by_fft / ms_fft / 1e6,
+                                      "frac": by_fft / ms_fft / 1e6 / hbm,
+                                      "note": "cuFFT R2C + k_solve_sf1 + cuFFT C2R (3 launches); compulsory traffic only"},
+                "renoise": {"ms": ms_rn, "algorithmic_bytes": by_rn, "achieved": by_rn / ms_rn / 1e6, "frac": by_rn / ms_rn / 1e6 / hbm},
+                "share_of_step": (ms_fft + ms_rn) / ms_step}
+
     if rank == 0:
         cpu = None if (args.no_cpu_baseline or world > 1) else cpu_baseline_sample()
         line = {"metric": "images/sec @100-NFE 256x256 deblur", "value": value, "unit": "images/s", "n_gpus": world,
@@ -392,8 +424,8 @@ def main():
                 "data": "synthetic", "config": workload_config(B, args.precision),
                 "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": 2 * img_bytes,
                         "d2h_bytes_per_step": img_bytes, "ms_per_step": ms_e2e},
-                "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-                "weight_broadcast_ms": t_bcast_ms, "graph": not args.no_graph}
+                "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_prox": prox, "cpu_baseline": cpu,
+                "weight_broadcast_ms": t_bcast_ms, "graph": not args.no_graph, "gn_fusion": args.gn_fusion}
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()

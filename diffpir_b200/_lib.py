@@ -72,6 +72,11 @@ SIGNATURES = {
     "dpir_conv_tc_f16io": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
                                      c_int32, c_int32, c_int32, c_void_p]),
     "dpir_conv_tc_variant": (c_int32, [c_int32]),
+    "dpir_gn_coef": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
+                               c_void_p, c_void_p]),
+    "dpir_conv_gnfuse_f16io": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                         c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    "dpir_set_gn_fusion": (c_int32, [c_void_p, c_int32]),
     "dpir_conv_simt": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
                                  c_int32, c_int32, c_void_p]),
 }

@@ -385,6 +385,10 @@ constexpr int V2_B_BYTES = 3 * 128 * 128;            // 3 vertical taps x (128 c
 constexpr int V2_STAGE_BYTES = V2_A_BYTES + V2_B_BYTES;   // 86,016 B
 constexpr int V2_STAGES = 2;
 constexpr int V2_THREADS = 320;                       // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
+// v4 (fused GroupNorm+SiLU operand): 5 warpgroups - {TMA, MMA, 2 idle warps}, 2 x epilogue (warps 4-11), 2 x operand
+// producers (warps 12-19).  5 warps per SM sub-partition leave 96 registers per thread, fewer than the epilogue (117) and the
+// double-buffered producers need, so the warpgroups re-balance the register file with setmaxnreg: 40 / 120 / 112.
+constexpr int V4_THREADS = 640;
 constexpr int V2_STG_BYTES = 8 * 4096;                // per-epilogue-warp 32 x 128 B transpose buffers
 constexpr int V2_SMEM = V2_STAGES * V2_STAGE_BYTES + V2_STG_BYTES + 1024 + 256;
 constexpr int V3_STG_BYTES = 8 * 6144;                // v3: per-epilogue-warp fp16 tiles OUT, RES0, RES1 (2 KB each)
@@ -393,11 +397,26 @@ constexpr int V3_SMEM = V2_STAGES * V2_STAGE_BYTES + V3_STG_BYTES + 1024 + 512;
 struct ConvV2Geom {
   int B, H, W, Cin, Cout;
   int skip_chunks;                    // extra K chunks of a fused 1x1 convolution on a second operand (ResBlock skip), or 0
+  int skip_chunks_a;                  // of which the first skip_chunks_a come from tmA2, the rest from tmA2b (concat skip input)
   int dbg;                            // timing diagnostics only (env DPIR_CONV_DEBUG): 1 = no epilogue memory traffic,
                                       // 2 = no MMA issue, 4 = no TMA loads; results are garbage when non-zero
   int tiles_w, tiles_h, n_tiles;      // 16x16 pixel tiles per image, Cout/128 column tiles
   int total_tiles;                    // B * tiles_h * tiles_w * n_tiles
 };
+
+__device__ __forceinline__ float tanh_approx_f(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ __half2 tanh_approx_h2(__half2 x) {
+  uint32_t y;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(y) : "r"(*reinterpret_cast<const uint32_t *>(&x)));
+  return *reinterpret_cast<const __half2 *>(&y);
+}
+
+template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -685,13 +704,27 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_conv3x3_v2(const __grid_const
 // The accumulator then has CHANNELS on TMEM lanes and pixels on columns, so in the epilogue a warp instruction writes 32
 // consecutive channels of one pixel = one contiguous 128 B (fp32) / 64 B (fp16) segment: coalesced without any transpose,
 // bias is a per-lane constant, and the GroupNorm quad statistics reduce to a thread-local sum over pixels plus two shuffles.
-__global__ void __launch_bounds__(V2_THREADS, 1) k_conv3x3_v3(const __grid_constant__ CUtensorMap tmA,
+//
+// FUSE > 0 (v4): the GroupNorm (+FiLM) + SiLU that precedes the convolution in every ResBlock (unet.py:199-200, 205-212,
+// nn.py:17-19) is applied on the fly to the activation operand, so the HBM-bound k_gn_apply pass (read + write of the whole
+// tensor) and its output buffer disappear.  The normalisation is a per-(image, channel) affine map (k_gn_coef folds
+// mean / rstd / gamma / beta / FiLM scale+shift into hs = 0.5*scale, ho = 0.5*offset), so 8 extra producer warps replace the
+// activation TMA: they read the RAW fp16 tensor(s) - one or two sources = the virtual th.cat of unet.py:660 - with 16-byte
+// global loads (prefetched one pipeline stage ahead into registers), compute h = x*hs + ho, SiLU(2h) = h + h*tanh(h)
+// (one MUFU per element, fp32; FUSE == 2: packed-half arithmetic), write the result into the same K-major SWIZZLE_128B
+// layout the TMA would have produced (16-byte chunk j of pixel row r lands at r*128 + ((j ^ (r & 7)) << 4)), zero outside
+// the image (the conv pads the ACTIVATED tensor), and publish the stage through fence.proxy.async + the stage's mbarrier.
+// The weight tiles, the fused 1x1-skip stages (raw operand, TMA; two tensor maps when the skip input is a concat), the
+// MMA issue and the epilogue are unchanged.
+template <int FUSE>
+__global__ void __launch_bounds__(FUSE ? V4_THREADS : V2_THREADS, 1) k_conv3x3_v3(const __grid_constant__ CUtensorMap tmA,
                                                                const __grid_constant__ CUtensorMap tmB,
                                                                const __grid_constant__ CUtensorMap tmA2,
+                                                               const __grid_constant__ CUtensorMap tmA2b,
                                                                const __grid_constant__ CUtensorMap tmB2,
                                                                const __grid_constant__ CUtensorMap tmOut,
                                                                const __grid_constant__ CUtensorMap tmRes, ConvV2Geom g,
-                                                               ConvEpi epi) {
+                                                               ConvEpi epi, GnFuse gf) {
   // M = 128 (couts), N = 256 (pixels)
   constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   extern __shared__ uint8_t smem_raw[];
@@ -713,7 +746,8 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_conv3x3_v3(const __grid_const
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (g.skip_chunks) { tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmB2); }
-    for (int s = 0; s < V2_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    // FUSE: a stage is full once the TMA bytes (weights) have landed AND the 8 producer warps have published the operand
+    for (int s = 0; s < V2_STAGES; ++s) { mbar_init(&full[s], FUSE ? 9 : 1); mbar_init(&empty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 8); }
     for (int a = 0; a < 16; ++a) mbar_init(&res_full[a], 1);
     tma_prefetch_desc(&tmOut);
@@ -736,7 +770,8 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_conv3x3_v3(const __grid_const
     n = mt / (g.tiles_w * g.tiles_h);
   };
 
-  if (warp == 0) {
+  // warp roles as lambdas: the two thread layouts (v3: 10 warps; v4: 5 warpgroups with re-balanced registers) share them
+  auto role_tma = [&]() {
     if (lane == 0) {
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
@@ -750,21 +785,23 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_conv3x3_v3(const __grid_const
           if (g.dbg & 4) { mbar_arrive(&full[s]); continue; }
           if (k < num_main) {
             const int ch = k / 3, dx = k - ch * 3;
-            mbar_expect_tx(&full[s], V2_STAGE_BYTES);
-            tma_load_4d(sa, &tmA, &full[s], ch * TC_BK, w0 + dx - 1, h0 - 1, n);
+            mbar_expect_tx(&full[s], FUSE ? V2_B_BYTES : V2_STAGE_BYTES);
+            if (!FUSE) tma_load_4d(sa, &tmA, &full[s], ch * TC_BK, w0 + dx - 1, h0 - 1, n);
 #pragma unroll
             for (int dy = 0; dy < 3; ++dy)
               tma_load_3d(sa + V2_A_BYTES + dy * (128 * 128), &tmB, &full[s], ch * TC_BK, co0, dy * 3 + dx);
           } else {
             const int ch = k - num_main;
             mbar_expect_tx(&full[s], V2_A_BYTES + 128 * 128);
-            tma_load_4d(sa, &tmA2, &full[s], ch * TC_BK, w0, h0 - 1, n);
+            if (ch < g.skip_chunks_a) tma_load_4d(sa, &tmA2, &full[s], ch * TC_BK, w0, h0 - 1, n);
+            else tma_load_4d(sa, &tmA2b, &full[s], (ch - g.skip_chunks_a) * TC_BK, w0, h0 - 1, n);
             tma_load_3d(sa + V2_A_BYTES + 1 * (128 * 128), &tmB2, &full[s], ch * TC_BK, co0, 0);
           }
         }
       }
     }
-  } else if (warp == 1) {
+  };
+  auto role_mma = [&]() {
     if (lane == 0) {
       uint32_t it = 0, tc = 0;
       for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++tc) {
@@ -791,7 +828,107 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_conv3x3_v3(const __grid_const
         umma_commit(&tmem_full[ab]);
       }
     }
-  } else {
+  };
+  auto role_producer = [&]() {
+    // ---------------------------------------------------------------- v4 operand producers (8 warps, 256 threads)
+    // The 18 x 16 pixel halo box of a stage is 2304 16-byte units (pixel row r = yy*16 + xx, channel octet j); thread p owns
+    // j = p & 7, xx = (p >> 3) & 15 and the 9 rows yy = 2i + (p >> 7): the channel octet (hence the coefficients), the column
+    // validity and the swizzle term (r & 7 == xx & 7) are per-thread constants, and a warp reads 4 pixels x 128 contiguous B.
+    const int p = (int)threadIdx.x - 12 * 32;
+    const int j = p & 7, xx = (p >> 3) & 15, yh = p >> 7;
+    const uint32_t dst_off = (uint32_t)(yh * 2048 + xx * 128 + ((j ^ (xx & 7)) << 4));
+    const int Ctot = gf.C1 + gf.C2;
+    uint4 cur[9], nxt[9];
+    uint32_t mcur = 0, mnxt = 0;          // validity bits of the 9 units (outside the image -> exact zeros)
+    float hs[8], ho[8];
+    // issue the 9 global loads of main stage k of the tile at (n, h0, w0) into buf
+    auto issue = [&](int n, int h0, int w0, int k, uint4 (&buf)[9], uint32_t &mask) {
+      const int ch = k / 3, dx = k - ch * 3;
+      const int c = ch * TC_BK + j * 8;
+      const __half *src; int Cs, cc;
+      if (c < gf.C1) { src = gf.src1; Cs = gf.C1; cc = c; } else { src = gf.src2; Cs = gf.C2; cc = c - gf.C1; }
+      const int x = w0 + dx - 1 + xx;
+      const bool xok = (unsigned)x < (unsigned)g.W;
+      const int y0 = h0 - 1 + yh;
+      const __half *ptr = src + (((int64_t)n * g.H + y0) * g.W + x) * Cs + cc;
+      const int64_t rs = (int64_t)2 * g.W * Cs;
+      mask = 0;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) {
+        const bool ok = xok && (unsigned)(y0 + 2 * i) < (unsigned)g.H;
+        if (ok) { buf[i] = __ldg(reinterpret_cast<const uint4 *>(ptr + i * rs)); mask |= 1u << i; }   // invalid units: masked below
+      }
+    };
+    int tile = blockIdx.x;
+    int n = 0, h0 = 0, w0 = 0, co0 = 0;
+    if (tile < g.total_tiles) {
+      decode(tile, n, h0, w0, co0);
+      issue(n, h0, w0, 0, nxt, mnxt);
+    }
+    uint32_t it = 0;
+    for (; tile < g.total_tiles; tile += gridDim.x) {
+      int n2 = n, h2 = h0, w2 = w0;      // the tile after this one (decoded once, at its prefetch)
+      for (int k = 0; k < num_k; ++k, ++it) {
+        const int s = it % V2_STAGES;
+        const uint32_t ph = (it / V2_STAGES) & 1u;
+        if (k >= num_main) {               // fused 1x1-skip stage: operand comes by TMA, only keep the barrier count
+          mbar_wait(&empty[s], ph ^ 1u);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&full[s]);
+          continue;
+        }
+#pragma unroll
+        for (int i = 0; i < 9; ++i) cur[i] = nxt[i];
+        mcur = mnxt;
+        const int ch = k / 3;
+        if (k == ch * 3) {                 // new 64-channel chunk: this thread's 8 coefficient pairs
+          const float *cf = gf.coef + (int64_t)n * 2 * Ctot + ch * TC_BK + j * 8;
+          const float4 a0 = __ldg(reinterpret_cast<const float4 *>(cf)), a1 = __ldg(reinterpret_cast<const float4 *>(cf + 4));
+          const float4 b0 = __ldg(reinterpret_cast<const float4 *>(cf + Ctot)), b1 = __ldg(reinterpret_cast<const float4 *>(cf + Ctot + 4));
+          hs[0] = a0.x; hs[1] = a0.y; hs[2] = a0.z; hs[3] = a0.w; hs[4] = a1.x; hs[5] = a1.y; hs[6] = a1.z; hs[7] = a1.w;
+          ho[0] = b0.x; ho[1] = b0.y; ho[2] = b0.z; ho[3] = b0.w; ho[4] = b1.x; ho[5] = b1.y; ho[6] = b1.z; ho[7] = b1.w;
+        }
+        // prefetch the next main stage (same tile, or the first stage of this CTA's next tile)
+        if (k + 1 < num_main) {
+          issue(n, h0, w0, k + 1, nxt, mnxt);
+        } else if (tile + (int)gridDim.x < g.total_tiles) {
+          int co2;
+          decode(tile + (int)gridDim.x, n2, h2, w2, co2);
+          issue(n2, h2, w2, 0, nxt, mnxt);
+        }
+        mbar_wait(&empty[s], ph ^ 1u);
+        uint8_t *dst = smem + s * V2_STAGE_BYTES + dst_off;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+          uint4 v = make_uint4(0u, 0u, 0u, 0u);
+          if (mcur & (1u << i)) {
+            uint32_t w[4] = {cur[i].x, cur[i].y, cur[i].z, cur[i].w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const __half2 hv = *reinterpret_cast<const __half2 *>(&w[q]);
+              if (FUSE == 2) {
+                const __half2 h = __hfma2(hv, __floats2half2_rn(hs[2 * q], hs[2 * q + 1]), __floats2half2_rn(ho[2 * q], ho[2 * q + 1]));
+                const __half2 r = __hfma2(h, tanh_approx_h2(h), h);
+                w[q] = *reinterpret_cast<const uint32_t *>(&r);
+              } else {
+                const float2 f = __half22float2(hv);
+                const float ha = fmaf(f.x, hs[2 * q], ho[2 * q]), hb = fmaf(f.y, hs[2 * q + 1], ho[2 * q + 1]);
+                const __half2 r = __floats2half2_rn(fmaf(ha, tanh_approx_f(ha), ha), fmaf(hb, tanh_approx_f(hb), hb));
+                w[q] = *reinterpret_cast<const uint32_t *>(&r);
+              }
+            }
+            v = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+          *reinterpret_cast<uint4 *>(dst + i * 4096) = v;
+        }
+        fence_proxy_async();               // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full[s]);
+      }
+      n = n2; h0 = h2; w0 = w2;
+    }
+  };
+  auto role_epilogue = [&](const int ew) {
     // ---------------------------------------------------------------- epilogue: lane = output channel, column = pixel
     // fp16 in / fp16 out only (the fp16-stream pipeline).  The epilogue is bound by per-warp instruction latency (ncu: ~6
     // cycles per issued instruction, 2 warps per scheduler), so it is built for minimum instruction count: no global
@@ -800,7 +937,6 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_conv3x3_v3(const __grid_const
     // contiguous bytes) and ONE thread issues a TMA tensor store of the {32 ch, 16 px, 2 rows} box; the hardware clips boxes
     // that stick out of the image.  The residual box arrives the same way (TMA load, double buffered, prefetched one chunk
     // ahead) and is read back column-wise (32 x LDS.U16).
-    const int ew = warp - 2;              // 0..7
     const int q = warp & 3;               // TMEM lane quarter -> channels co0 + q*32 + lane
     const int hv = ew >> 2;               // which half of the tile's 256 pixels (image rows hv*8 .. hv*8+7)
     __half *outb = reinterpret_cast<__half *>(stg_base + ew * 6144);
@@ -896,6 +1032,24 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_conv3x3_v3(const __grid_const
       }
     }
     if (lane == 0) tma_store_wait_all0();      // all tensor stores of this warp have landed before the CTA retires
+  };
+  if constexpr (FUSE != 0) {
+    // setmaxnreg is executed once per warpgroup, at the top of the branch that dominates all of that group's code
+    if (warp < 4) {
+      setmaxnreg_dec<40>();
+      if (warp == 0) role_tma();
+      else if (warp == 1) role_mma();
+    } else if (warp < 12) {
+      setmaxnreg_inc<120>();
+      role_epilogue(warp - 4);
+    } else {
+      setmaxnreg_inc<112>();
+      role_producer();
+    }
+  } else {
+    if (warp == 0) role_tma();
+    else if (warp == 1) role_mma();
+    else role_epilogue(warp - 2);
   }
   tc_fence_before();
   __syncthreads();
@@ -911,6 +1065,8 @@ struct ConvTcPlan {
   bool use_v3 = true;     // swap-AB variant
   ConvV2Geom g2;
   CUtensorMap tmA2, tmB2; // fused 1x1 skip operand / weights (v2 only; copies of tmA/tmB when unused)
+  CUtensorMap tmA2b;      // second source of a concatenated skip operand (v3/v4)
+  GnFuse gf{};            // v4: fused GroupNorm+SiLU on the activation operand (gf.coef != null)
   CUtensorMap tmOut, tmRes;   // v3: fp16 output / residual tensors for the TMA-store epilogue
   bool io_half = false;       // tmOut (and tmRes when has_res) are valid
   bool has_res = false;
@@ -919,6 +1075,7 @@ struct ConvTcPlan {
 
 static int g_force_v1 = 0;   // dpir_conv_tc_variant: 0 = auto (persistent swap-AB v3), 1 = v1 everywhere, 2 = persistent v2
 static int g_num_sms = 0;
+static int g_gnfuse_math = 1; // fused-operand kernel arithmetic: 1 = fp32 (as k_gn_apply), 2 = packed half (tanh.approx.f16x2)
 
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
@@ -959,7 +1116,7 @@ int conv_tc_plan_create(const void *act_half, const void *w_half, int B, int H, 
   p->use_v3 = g_force_v1 == 0;
   if (p->v2) {
     ConvV2Geom &g2 = p->g2;
-    g2.B = B; g2.H = H; g2.W = W; g2.Cin = Cin; g2.Cout = 0; g2.skip_chunks = 0; g2.dbg = 0;
+    g2.B = B; g2.H = H; g2.W = W; g2.Cin = Cin; g2.Cout = 0; g2.skip_chunks = 0; g2.skip_chunks_a = 0; g2.dbg = 0;
     g2.tiles_w = cdiv(W, 16); g2.tiles_h = cdiv(H, 16); g2.n_tiles = CoutPad / 128;
     g2.total_tiles = B * g2.tiles_w * g2.tiles_h * g2.n_tiles;
   }
@@ -985,6 +1142,7 @@ int conv_tc_plan_create(const void *act_half, const void *w_half, int B, int H, 
     if (r != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled(B) failed: %d", (int)r); delete p; return DPIR_E_CUDA; }
   }
   p->tmA2 = p->tmA;
+  p->tmA2b = p->tmA;
   p->tmB2 = p->tmB;
   *out = p;
   return DPIR_OK;
@@ -1022,23 +1180,32 @@ int conv_tc_plan_set_io(ConvTcPlan *p, const void *out, int out_half, const void
   return DPIR_OK;
 }
 
-// attach a fused 1x1 convolution on a second NHWC fp16 operand (same B,H,W; Cin2 channels; weights [1][CoutPad][Cin2])
-int conv_tc_plan_add_skip(ConvTcPlan *p, const void *act2_half, const void *w2_half, int Cin2) {
+// attach a fused 1x1 convolution on a second NHWC fp16 operand (same B,H,W; weights [1][CoutPad][Cin2a + Cin2b]); the
+// operand may be the virtual concat of two tensors (act2b != null, Cin2b channels) - th.cat of unet.py:660 without a copy
+int conv_tc_plan_add_skip(ConvTcPlan *p, const void *act2_half, const void *w2_half, int Cin2a, const void *act2b_half,
+                          int Cin2b) {
   DPIR_REQUIRE(p->v2, "conv_tc: skip fusion needs the persistent 3x3 kernel");
-  DPIR_REQUIRE(Cin2 % TC_BK == 0, "conv_tc: fused skip Cin must be a multiple of 64");
+  DPIR_REQUIRE(Cin2a % TC_BK == 0 && Cin2b % TC_BK == 0, "conv_tc: fused skip Cin must be a multiple of 64");
+  DPIR_REQUIRE(!act2b_half || p->use_v3, "conv_tc: a concatenated skip operand needs the swap-AB kernel");
   auto encode = get_encode_fn();
   if (!encode) { set_error("conv_tc: cuTensorMapEncodeTiled entry point unavailable"); return DPIR_E_CUDA; }
   const ConvTcGeom &g = p->g;
-  {
-    cuuint64_t gdim[4] = {(cuuint64_t)Cin2, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.B};
-    cuuint64_t gstr[3] = {(cuuint64_t)Cin2 * 2, (cuuint64_t)g.W * Cin2 * 2, (cuuint64_t)g.H * g.W * Cin2 * 2};
+  const int Cin2 = Cin2a + (act2b_half ? Cin2b : 0);
+  auto make_a = [&](CUtensorMap *tm, const void *ptr, int C) -> int {
+    cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.B};
+    cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)g.W * C * 2, (cuuint64_t)g.H * g.W * C * 2};
     cuuint32_t box[4] = {(cuuint32_t)TC_BK, 16, 18, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = encode(&p->tmA2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(act2_half), gdim, gstr, box, estr,
+    CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(ptr), gdim, gstr, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled(A2) failed: %d", (int)r); return DPIR_E_CUDA; }
-  }
+    return DPIR_OK;
+  };
+  int rc = make_a(&p->tmA2, act2_half, Cin2a);
+  if (rc) return rc;
+  p->tmA2b = p->tmA2;
+  if (act2b_half) { rc = make_a(&p->tmA2b, act2b_half, Cin2b); if (rc) return rc; }
   {
     cuuint64_t gdim[3] = {(cuuint64_t)Cin2, (cuuint64_t)p->CoutPad, 1};
     cuuint64_t gstr[2] = {(cuuint64_t)Cin2 * 2, (cuuint64_t)p->CoutPad * Cin2 * 2};
@@ -1050,6 +1217,18 @@ int conv_tc_plan_add_skip(ConvTcPlan *p, const void *act2_half, const void *w2_h
     if (r != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled(B2) failed: %d", (int)r); return DPIR_E_CUDA; }
   }
   p->g2.skip_chunks = Cin2 / TC_BK;
+  p->g2.skip_chunks_a = Cin2a / TC_BK;
+  return DPIR_OK;
+}
+
+// v4: the activation operand is SiLU(GroupNorm(src)) computed inside the kernel from the raw fp16 source(s) and the
+// per-(image, channel) coefficient table of launch_gn_coef; needs the swap-AB kernel with its fp16 TMA-store epilogue
+int conv_tc_plan_set_gn_fuse(ConvTcPlan *p, const GnFuse &gf) {
+  DPIR_REQUIRE(p->v2 && p->use_v3, "conv_tc: GroupNorm fusion needs the persistent swap-AB 3x3 kernel");
+  DPIR_REQUIRE(gf.src1 && gf.coef && gf.C1 % TC_BK == 0 && gf.C2 % TC_BK == 0 && gf.C1 + gf.C2 == p->g2.Cin && (gf.C2 == 0 || gf.src2),
+               "conv_tc: bad GroupNorm fusion operands (C1 %d, C2 %d, Cin %d)", gf.C1, gf.C2, p->g2.Cin);
+  DPIR_REQUIRE((((uintptr_t)gf.src1 | (uintptr_t)gf.src2 | (uintptr_t)gf.coef) & 15) == 0, "conv_tc: fused operands must be 16-byte aligned");
+  p->gf = gf;
   return DPIR_OK;
 }
 
@@ -1071,6 +1250,8 @@ static int launch_tc_impl(const ConvTcPlan *p, const ConvTcGeom &g, const ConvEp
 
 void conv_tc_force_v1(int on) { g_force_v1 = on; }
 bool conv_tc_v2_enabled() { return g_force_v1 != 1; }
+bool conv_tc_swapab_enabled() { return g_force_v1 == 0; }
+void conv_tc_set_gnfuse_math(int m) { g_gnfuse_math = m == 2 ? 2 : 1; }
 
 int launch_conv_tc(const ConvTcPlan *p, const ConvEpi &epi, int Cout, cudaStream_t st) {
   DPIR_REQUIRE(Cout <= p->CoutPad, "conv_tc: Cout exceeds padded weight rows");
@@ -1079,7 +1260,9 @@ int launch_conv_tc(const ConvTcPlan *p, const ConvEpi &epi, int Cout, cudaStream
     static bool attr_set = false;
     if (!attr_set) {
       DPIR_CUDA_CHECK(cudaFuncSetAttribute(k_conv3x3_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, V2_SMEM));
-      DPIR_CUDA_CHECK(cudaFuncSetAttribute(k_conv3x3_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM));
+      DPIR_CUDA_CHECK(cudaFuncSetAttribute(k_conv3x3_v3<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM));
+      DPIR_CUDA_CHECK(cudaFuncSetAttribute(k_conv3x3_v3<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM));
+      DPIR_CUDA_CHECK(cudaFuncSetAttribute(k_conv3x3_v3<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM));
       int dev = 0;
       DPIR_CUDA_CHECK(cudaGetDevice(&dev));
       DPIR_CUDA_CHECK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -1093,8 +1276,15 @@ int launch_conv_tc(const ConvTcPlan *p, const ConvEpi &epi, int Cout, cudaStream
     int grid = g2.total_tiles < g_num_sms ? g2.total_tiles : g_num_sms;
     const bool v3_ok = p->use_v3 && p->io_half && epi.out_half && epi.out == p->io_out && epi.residual == p->io_res &&
                        (!epi.residual || epi.res_half);
-    if (v3_ok) {
-      k_conv3x3_v3<<<grid, V2_THREADS, V3_SMEM, st>>>(p->tmA, p->tmB, p->tmA2, p->tmB2, p->tmOut, p->tmRes, g2, epi);
+    DPIR_REQUIRE(v3_ok || (!p->gf.coef && g2.skip_chunks_a == g2.skip_chunks),
+                 "conv_tc: GroupNorm / concat-skip fusion planned for a conv the swap-AB kernel cannot run");
+    if (v3_ok && p->gf.coef) {
+      if (g_gnfuse_math == 2)
+        k_conv3x3_v3<2><<<grid, V4_THREADS, V3_SMEM, st>>>(p->tmA, p->tmB, p->tmA2, p->tmA2b, p->tmB2, p->tmOut, p->tmRes, g2, epi, p->gf);
+      else
+        k_conv3x3_v3<1><<<grid, V4_THREADS, V3_SMEM, st>>>(p->tmA, p->tmB, p->tmA2, p->tmA2b, p->tmB2, p->tmOut, p->tmRes, g2, epi, p->gf);
+    } else if (v3_ok) {
+      k_conv3x3_v3<0><<<grid, V2_THREADS, V3_SMEM, st>>>(p->tmA, p->tmB, p->tmA2, p->tmA2b, p->tmB2, p->tmOut, p->tmRes, g2, epi, p->gf);
     } else {
       DPIR_REQUIRE(!epi.residual || (epi.res_half != 0) == (epi.out_half != 0),
                    "conv_tc: the v2 persistent kernel needs residual and output of the same precision");

@@ -22,6 +22,8 @@ constexpr size_t ALIGN = 256;
 static inline size_t align_up(size_t v, size_t a = ALIGN) { return (v + a - 1) / a * a; }
 
 // ---------------------------------------------------------------------------------------------- structure
+static int g_gn_fuse = 1;    // dpir_set_gn_fusion: ResBlock GroupNorm+SiLU fused into the conv operand (v4 kernel) where eligible
+
 struct LayerDesc {
   int kind;  // 0 conv(stem), 1 res, 2 attn
   std::string prefix;
@@ -55,11 +57,14 @@ struct Buf {   // workspace tensor
   bool has_stats = false;
 };
 
-enum OpKind { OP_MEMSET, OP_TIME_EMBED, OP_FILM, OP_CONV_IN, OP_GN_STATS, OP_GN_APPLY, OP_CONV, OP_ATTN };
+enum OpKind { OP_MEMSET, OP_TIME_EMBED, OP_FILM, OP_CONV_IN, OP_GN_STATS, OP_GN_APPLY, OP_CONV, OP_ATTN, OP_GN_COEF };
 struct Op {
   OpKind kind;
   // generic pointers / ints, interpreted per kind
   GnApplyArgs gn{};
+  GnCoefArgs gc{};                                           // OP_GN_COEF
+  GnFuse gf{};                                               // OP_CONV with the GroupNorm+SiLU fused on its operand (v4 kernel)
+  const void *p2b = nullptr; int Cin2b = 0;                  // second source of a concatenated fused-skip operand
   ConvEpi epi{};
   const void *p0 = nullptr, *p1 = nullptr, *p2 = nullptr;   // workspace tensors (offset-encoded until the plan is rebased)
   void *q0 = nullptr;                                        // workspace tensor (output)
@@ -407,7 +412,7 @@ struct PlanBuilder {
 
   int gn(int src1, int src2, const NormW &nw, int film_row /*-1: none*/, int silu, int resample, bool want_raw32,
          bool want_rawact, int *act_id, int *raw32_id, int *rawact_id) {
-    const Buf &s1 = bufs[src1];
+    const Buf s1 = bufs[src1];   // by value: new_buf() below may reallocate `bufs`
     int C1 = s1.C, C2 = src2 >= 0 ? bufs[src2].C : 0, C = C1 + C2;
     int Hin = s1.H, Win = s1.W;
     int Ho = resample == RS_DOWN ? Hin / 2 : (resample == RS_UP ? Hin * 2 : Hin);
@@ -448,8 +453,8 @@ struct PlanBuilder {
   }
 
   int conv(int act, const ConvW &cw, int residual, int *out_id, bool want_stats = false, bool out_half = false,
-           int skip_act = -1, const ConvW *skip_w = nullptr) {
-    const Buf &a = bufs[act];
+           int skip_act = -1, const ConvW *skip_w = nullptr, int skip_act2 = -1) {
+    const Buf a = bufs[act];   // by value: new_buf() below may reallocate `bufs`
     out_half = out_half && e->half;
     *out_id = new_buf(B, a.H, a.W, cw.cout, out_half, want_stats);
     if (residual >= 0 && bufs[residual].half && !e->half) { set_error("internal: fp16 residual in fp32 mode"); err = DPIR_E_STATE; }
@@ -469,6 +474,11 @@ struct PlanBuilder {
       op.p2 = bp<void>(skip_act);
       op.w2 = e->arena + skip_w->w_off;
       op.Cin2 = skip_w->cin;
+      if (skip_act2 >= 0) {          // the skip operand is the virtual concat (skip_act | skip_act2)
+        op.p2b = bp<void>(skip_act2);
+        op.Cin2b = bufs[skip_act2].C;
+        if (bufs[skip_act].C + op.Cin2b != skip_w->cin) { set_error("internal: concat skip channels"); err = DPIR_E_STATE; }
+      }
       op.epi.bias2 = e->ap<float>(skip_w->b_off);
     }
     plan->ops.push_back(op);
@@ -476,8 +486,73 @@ struct PlanBuilder {
     return DPIR_OK;
   }
 
+  // v4: instead of a k_gn_apply pass, emit the tiny per-(image, channel) coefficient kernel; the conv applies
+  // GroupNorm(+FiLM)+SiLU to its operand on the fly.  Returns the coefficient buffer id (release it after the conv).
+  int gn_coef(int src1, int src2, const NormW &nw, int film_row) {
+    const Buf s1 = bufs[src1];
+    const int C1 = s1.C, C2 = src2 >= 0 ? bufs[src2].C : 0, C = C1 + C2;
+    n_norms++;
+    int cb = new_buf(B, 1, 1, 2 * C, false);
+    Op op;
+    op.kind = OP_GN_COEF;
+    GnCoefArgs &a = op.gc;
+    a.C1 = C1; a.C2 = C2;
+    a.q1 = sp(src1); a.q2 = src2 >= 0 ? sp(src2) : nullptr;
+    a.gamma = e->ap<float>(nw.g_off); a.beta = e->ap<float>(nw.b_off);
+    a.film = film_row >= 0 ? wp<float>(film_off + (size_t)film_row * 4) : nullptr;
+    a.film_stride = e->film_rows; a.tsteps = nullptr;
+    op.film_row = film_row;
+    a.B = B; a.HW = s1.H * s1.W;
+    a.coef = bp<float>(cb);
+    op.H = s1.H; op.W = s1.W; op.Cin = C;
+    plan->ops.push_back(op);
+    return cb;
+  }
+  // the conv just pushed reads SiLU(GroupNorm(src1|src2)) instead of a materialised activation
+  void fuse_last_conv(int src1, int src2, int coef_buf) {
+    Op &op = plan->ops.back();
+    op.gf.src1 = bp<__half>(src1); op.gf.C1 = bufs[src1].C;
+    op.gf.src2 = src2 >= 0 ? bp<__half>(src2) : nullptr; op.gf.C2 = src2 >= 0 ? bufs[src2].C : 0;
+    op.gf.coef = bp<float>(coef_buf);
+    op.p0 = op.gf.src1;
+  }
+  // ResBlock eligible for the fused-operand kernel: fp16 stream, no resampling, 3x3 convs on the persistent swap-AB kernel
+  bool gn_fusable(const LayerDesc &l, int x, int skip, const ResW &rw) const {
+    const Buf &a = bufs[x];
+    if (!(g_gn_fuse && e->stream_half && conv_tc_swapab_enabled() && l.updown == RS_NONE && a.H >= 16 && a.W >= 16)) return false;
+    if (!a.half || (skip >= 0 && !bufs[skip].half)) return false;
+    if (a.C % 64 || (skip >= 0 && bufs[skip].C % 64)) return false;
+    if (rw.c1.ksize != 3 || rw.c2.ksize != 3 || rw.c1.ldw % 128 || rw.c2.ldw % 128 || rw.c1.cout % 64) return false;
+    if (skip >= 0 && !rw.has_skip) return false;     // a concat input without a 1x1 skip would need the raw concat copy
+    return true;
+  }
+
+  int resblock_fused(const LayerDesc &l, int x, int skip, int *out) {
+    const ResW &rw = e->resw[l.prefix];
+    // in_layers: conv1(SiLU(GN(x | skip)))
+    int c1 = gn_coef(x, skip, rw.n1, -1);
+    int h1;
+    conv(x, rw.c1, -1, &h1, /*want_stats=*/true, /*out_half=*/true);
+    fuse_last_conv(x, skip, c1);
+    release(c1);
+    // out_layers: conv2(SiLU(FiLM(GN(h1)))) + skip_connection(x | skip)
+    int c2 = gn_coef(h1, -1, rw.n2, rw.film_row);
+    if (rw.has_skip) {
+      conv(h1, rw.c2, -1, out, /*want_stats=*/true, /*out_half=*/true, x, &rw.skip, skip);
+    } else {
+      conv(h1, rw.c2, x, out, /*want_stats=*/true, /*out_half=*/true);
+    }
+    fuse_last_conv(h1, -1, c2);
+    release(c2);
+    release(h1);
+    release(x);
+    if (skip >= 0) release(skip);
+    return DPIR_OK;
+  }
+
   int resblock(const LayerDesc &l, int x, int skip, int *out) {
     const ResW &rw = e->resw[l.prefix];
+    if (gn_fusable(l, x, skip, rw)) return resblock_fused(l, x, skip, out);
     bool concat = skip >= 0;
     bool need_raw32 = !rw.has_skip && (l.updown != RS_NONE || concat);
     int a1, xr, xraw;
@@ -643,7 +718,12 @@ int get_plan(dpir_engine *e, int B, int H, int W, Plan **out) {
       rebase(op.gn.film, base);
       rebase(op.gn.act, base); rebase(op.gn.raw32, base); rebase(op.gn.rawact, base);
     }
-    if (op.kind == OP_CONV) { rebase(op.epi.residual, base); rebase(op.epi.out, base); rebase(op.epi.qstats, base); }
+    if (op.kind == OP_CONV) {
+      rebase(op.epi.residual, base); rebase(op.epi.out, base); rebase(op.epi.qstats, base);
+      rebase_c(op.p2b, base);
+      rebase(op.gf.src1, base); rebase(op.gf.src2, base); rebase(op.gf.coef, base);
+    }
+    if (op.kind == OP_GN_COEF) { rebase(op.gc.q1, base); rebase(op.gc.q2, base); rebase(op.gc.film, base); rebase(op.gc.coef, base); }
   }
   if (e->half) {
     for (Op &op : plan->ops) {
@@ -659,7 +739,11 @@ int get_plan(dpir_engine *e, int B, int H, int W, Plan **out) {
       }
       if (op.p2) {
         if (!conv_tc_plan_is_v2(tp)) { set_error("internal: skip fusion planned for a non-persistent conv"); return DPIR_E_STATE; }
-        rc = conv_tc_plan_add_skip(tp, op.p2, op.w2, op.Cin2);
+        rc = conv_tc_plan_add_skip(tp, op.p2, op.w2, op.Cin2 - op.Cin2b, op.p2b, op.Cin2b);
+        if (rc) return rc;
+      }
+      if (op.gf.coef) {
+        rc = conv_tc_plan_set_gn_fuse(tp, op.gf);
         if (rc) return rc;
       }
     }
@@ -712,6 +796,12 @@ int run_plan(dpir_engine *e, Plan *plan, const float *x, const int64_t *t, float
           rc = launch_gn_apply(op.gn, st);
         }
         break;
+      case OP_GN_COEF: {
+        GnCoefArgs gc = op.gc;
+        if (op.film_row >= 0 && e->use_film_table) { gc.film = e->film_table + op.film_row; gc.tsteps = t; }
+        rc = launch_gn_coef(gc, st);
+        break;
+      }
       case OP_CONV: {
         ConvEpi epi = op.epi;
         if (op.bind_out) {
@@ -1037,7 +1127,7 @@ int dpir_profile_end(dpir_engine *e, int32_t *kind, int32_t *dims, float *ms, in
     if (op.kind == OP_GN_STATS) { H = op.HW; W = 1; Cin = op.C1 + op.C2; Cout = 0; }
     if (op.kind == OP_ATTN) { H = op.HW; W = 1; Cout = op.heads; }
     dims[6 * i] = H; dims[6 * i + 1] = W; dims[6 * i + 2] = Cin; dims[6 * i + 3] = Cout;
-    dims[6 * i + 4] = op.kind == OP_CONV ? op.ksize : 0;
+    dims[6 * i + 4] = op.kind == OP_CONV ? op.ksize + (op.gf.coef ? 10 : 0) : 0;   // 13 = 3x3 with the GroupNorm+SiLU fused on its operand
     dims[6 * i + 5] = op.kind == OP_CONV ? op.Cin2 : 0;
     ms[i] = acc[i];
   }
@@ -1071,6 +1161,48 @@ int dpir_conv_tc_f16io(const void *act, const void *w, const float *bias, const 
   epi.mode = EPI_NHWC; epi.bias = bias; epi.residual = reinterpret_cast<const float *>(residual_half);
   epi.res_half = residual_half ? 1 : 0; epi.out = reinterpret_cast<float *>(out_half); epi.out_half = 1;
   rc = conv_tc_plan_set_io(p, out_half, 1, residual_half, 1, Cout);
+  if (!rc) rc = launch_conv_tc(p, epi, Cout, (cudaStream_t)stream);
+  conv_tc_plan_destroy(p);
+  return rc;
+}
+
+/* 1 (default): ResBlocks whose 3x3 convs run on the persistent swap-AB kernel apply GroupNorm(+FiLM)+SiLU inside the conv
+ * (no k_gn_apply pass, fp16s pipeline only), fp32 operand arithmetic; 2: the same with packed-half arithmetic; 0: every norm
+ * is a separate pass.  Cached plans of `e` are dropped. */
+int dpir_set_gn_fusion(dpir_engine *e, int32_t enable) {
+  DPIR_REQUIRE(enable >= 0 && enable <= 2, "dpir_set_gn_fusion: 0 = off, 1 = on (fp32 operand arithmetic), 2 = on (packed half)");
+  g_gn_fuse = enable ? 1 : 0;
+  if (enable) conv_tc_set_gnfuse_math(enable);
+  if (e) { cudaDeviceSynchronize(); e->plans.clear(); }
+  return DPIR_OK;
+}
+
+/* test entries for the fused-operand (v4) convolution: dpir_gn_coef folds quad statistics + affine (+ per-sample FiLM rows
+ * film[b*film_stride + {c, C+c}]) into the [B][2][C] coefficient table; dpir_conv_gnfuse_f16io runs
+ * out = conv3x3(SiLU(2*(x*hs+ho))) (+ residual) with x = (src1 | src2) raw fp16 NHWC, fp16 NHWC output */
+int dpir_gn_coef(const double *q1, const double *q2, int32_t C1, int32_t C2, const float *gamma, const float *beta, const float *film,
+                 int32_t film_stride, int32_t B, int32_t HW, float *coef, void *stream) {
+  DPIR_REQUIRE(q1 && gamma && beta && coef, "dpir_gn_coef: null pointer");
+  GnCoefArgs a{};
+  a.C1 = C1; a.C2 = C2; a.q1 = q1; a.q2 = q2; a.gamma = gamma; a.beta = beta; a.film = film; a.film_stride = film_stride;
+  a.tsteps = nullptr; a.B = B; a.HW = HW; a.coef = coef;
+  return launch_gn_coef(a, (cudaStream_t)stream);
+}
+
+int dpir_conv_gnfuse_f16io(const void *src1, int32_t C1, const void *src2, int32_t C2, const float *coef, const void *w,
+                           const float *bias, const void *residual_half, void *out_half, int32_t B, int32_t H, int32_t W,
+                           int32_t Cout, int32_t CoutPad, void *stream) {
+  DPIR_REQUIRE(src1 && coef && w && bias && out_half, "dpir_conv_gnfuse_f16io: null pointer");
+  ConvTcPlan *p = nullptr;
+  int rc = conv_tc_plan_create(src1, w, B, H, W, C1 + C2, CoutPad, 3, &p);
+  if (rc) return rc;
+  ConvEpi epi{};
+  epi.mode = EPI_NHWC; epi.bias = bias; epi.residual = reinterpret_cast<const float *>(residual_half);
+  epi.res_half = residual_half ? 1 : 0; epi.out = reinterpret_cast<float *>(out_half); epi.out_half = 1;
+  rc = conv_tc_plan_set_io(p, out_half, 1, residual_half, 1, Cout);
+  GnFuse gf;
+  gf.src1 = (const __half *)src1; gf.C1 = C1; gf.src2 = (const __half *)src2; gf.C2 = C2; gf.coef = coef;
+  if (!rc) rc = conv_tc_plan_set_gn_fuse(p, gf);
   if (!rc) rc = launch_conv_tc(p, epi, Cout, (cudaStream_t)stream);
   conv_tc_plan_destroy(p);
   return rc;

@@ -377,6 +377,49 @@ int launch_gn_apply(const GnApplyArgs &a, cudaStream_t st) {
   return DPIR_OK;
 }
 
+// =========================================================================================== GroupNorm coefficients
+// For the v4 convolution (conv_tc.cu) GroupNorm(+FiLM) is folded into a per-(image, channel) affine map
+//   y = ((x - mean) * rstd * gamma + beta) * (1 + film_scale) + film_shift = scale * x + offset       (nn.py:17-19, unet.py:246-249)
+// and SiLU(y) = h + h * tanh(h) with h = y / 2, so the table holds hs = scale / 2 and ho = offset / 2: coef[b][0][c], coef[b][1][c].
+__global__ void k_gn_coef(GnCoefArgs a) {
+  __shared__ float s_mean[32], s_rstd[32];
+  const int C = a.C1 + a.C2, C4 = C / 4, b = blockIdx.x;
+  if (threadIdx.x < 32) {
+    const int qpg = C4 / 32, Q1 = a.C1 / 4;
+    double su = 0.0, sq = 0.0;
+    for (int j = 0; j < qpg; ++j) {
+      const int q = threadIdx.x * qpg + j;
+      const double *src = q < Q1 ? a.q1 + ((int64_t)b * Q1 + q) * 2 : a.q2 + ((int64_t)b * (C4 - Q1) + (q - Q1)) * 2;
+      su += src[0];
+      sq += src[1];
+    }
+    const double n = (double)a.HW * (double)(C / 32);
+    const double mean = su / n;
+    double var = sq / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_mean[threadIdx.x] = (float)mean;
+    s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + 1e-5));
+  }
+  __syncthreads();
+  const float *f = a.film ? a.film + (a.tsteps ? a.tsteps[b] : (int64_t)b) * a.film_stride : nullptr;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / (C / 32);
+    float sc = s_rstd[g] * a.gamma[c];
+    float of = a.beta[c] - s_mean[g] * sc;
+    if (f) { const float m = 1.f + f[c]; sc *= m; of = of * m + f[C + c]; }
+    a.coef[((int64_t)b * 2) * C + c] = 0.5f * sc;
+    a.coef[((int64_t)b * 2 + 1) * C + c] = 0.5f * of;
+  }
+}
+
+int launch_gn_coef(const GnCoefArgs &a, cudaStream_t st) {
+  const int C = a.C1 + a.C2;
+  DPIR_REQUIRE(C % 128 == 0 && a.C1 % 4 == 0, "gn_coef: channels must be a multiple of 128 (got %d)", C);
+  k_gn_coef<<<a.B, 256, 0, st>>>(a);
+  DPIR_LAUNCH_CHECK();
+  return DPIR_OK;
+}
+
 // =========================================================================================== fp32 implicit-GEMM conv
 // D[pixel][co] = sum_{tap, ci} act[pixel + tap][ci] * w[tap][ci][co]  on CUDA cores (parity mode / debugging aid).
 // Tile 64 pixels x 64 couts x 16 channels, 256 threads, 4x4 register micro-tile.

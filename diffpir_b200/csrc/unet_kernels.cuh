@@ -39,6 +39,24 @@ struct ConvEpi {
   const int64_t *t;         // EPI_X0: (B,) timesteps on device
 };
 
+// v4 convolution operand fusion: the activation operand is SiLU(GroupNorm(+FiLM)(src1|src2)) evaluated inside the kernel
+struct GnFuse {
+  const __half *src1 = nullptr, *src2 = nullptr;   // raw NHWC fp16 source(s); src2 = second half of a virtual concat or null
+  int C1 = 0, C2 = 0;
+  const float *coef = nullptr;                     // [B][2][C1+C2] from launch_gn_coef: 0.5*scale, 0.5*offset; null = no fusion
+};
+
+// per-(image, channel) affine form of GroupNorm(+FiLM): act = SiLU(scale*x + offset); writes 0.5*scale, 0.5*offset
+struct GnCoefArgs {
+  int C1, C2;                         // channels of the two sources (C2 = 0: one source)
+  const double *q1, *q2;              // quad statistics of the sources
+  const float *gamma, *beta;          // [C]
+  const float *film; int film_stride; const int64_t *tsteps;   // as GnApplyArgs
+  int B, HW;
+  float *coef;                        // [B][2][C]
+};
+int launch_gn_coef(const GnCoefArgs &a, cudaStream_t st);
+
 #ifdef __CUDACC__
 // shared conv epilogue (bias / residual / NCHW / fused eps->x0); acc[0..ncols) = channels co.. of pixel (n,y,x)
 __device__ __forceinline__ void conv_epilogue_store(const ConvEpi &e, int n, int y, int x, int H, int W, int Cout, int co,
@@ -95,10 +113,14 @@ int conv_tc_plan_create(const void *act_half, const void *w_half, int B, int H, 
                         ConvTcPlan **out);
 void conv_tc_plan_destroy(ConvTcPlan *p);
 bool conv_tc_plan_is_v2(const ConvTcPlan *p);
-int conv_tc_plan_add_skip(ConvTcPlan *p, const void *act2_half, const void *w2_half, int Cin2);
+int conv_tc_plan_add_skip(ConvTcPlan *p, const void *act2_half, const void *w2_half, int Cin2a, const void *act2b_half = nullptr,
+                          int Cin2b = 0);
+int conv_tc_plan_set_gn_fuse(ConvTcPlan *p, const GnFuse &gf);
 int conv_tc_plan_set_io(ConvTcPlan *p, const void *out, int out_half, const void *residual, int res_half, int Cout);
 int launch_conv_tc(const ConvTcPlan *p, const ConvEpi &epi, int Cout, cudaStream_t st);
 bool conv_tc_v2_enabled();
+void conv_tc_set_gnfuse_math(int m);   // 1: fp32 arithmetic in the fused GroupNorm+SiLU operand path, 2: packed half
+bool conv_tc_swapab_enabled();   // the swap-AB persistent kernel (v3 / fused-operand v4) is selectable
 void conv_tc_force_v1(int on);   // 1: use the one-tile-per-CTA kernel for every shape (A/B testing)
 
 }  // namespace dpir

@@ -180,7 +180,12 @@ class UNetModel:
         return int(self._lib.dpir_workspace_bytes(self._h))
 
     # ---- per-op device timing (CUDA events inside the engine)
-    OP_KINDS = ("memset", "time_embed", "film", "conv_in", "gn_stats", "gn_apply", "conv", "attention")
+    OP_KINDS = ("memset", "time_embed", "film", "conv_in", "gn_stats", "gn_apply", "conv", "attention", "gn_coef")
+
+    def set_gn_fusion(self, enable):
+        """A/B switch (process-wide): 1/True ResBlock GroupNorm+SiLU inside the convolutions (default, fp32 operand arithmetic),
+        2 the same with packed-half arithmetic, 0/False separate passes; drops this model's cached plans."""
+        _lib.check(self._lib.dpir_set_gn_fusion(self._h, int(enable)), "dpir_set_gn_fusion")
 
     def profile_begin(self):
         _lib.check(self._lib.dpir_profile_begin(self._h), "dpir_profile_begin")
@@ -196,7 +201,10 @@ class UNetModel:
             _lib.check(n, "dpir_profile_end")
         rows = []
         for i in range(min(n, cap)):
-            rows.append(dict(kind=self.OP_KINDS[kind[i]], dims=tuple(dims[6 * i:6 * i + 6]), ms=float(ms[i])))
+            d = list(dims[6 * i:6 * i + 6])
+            fused = d[4] >= 10          # conv with GroupNorm+SiLU applied inside the kernel (ksize reported + 10)
+            d[4] %= 10
+            rows.append(dict(kind=self.OP_KINDS[kind[i]], dims=tuple(d), ms=float(ms[i]), gn_fused=bool(fused)))
         return rows
 
     def __del__(self):

@@ -227,6 +227,22 @@ int dpir_conv_tc(const void *act, const void *w, const float *bias, const float 
 /* the same convolution in its fp16-stream form: residual fp16 NHWC (or NULL), output fp16 NHWC. */
 int dpir_conv_tc_f16io(const void *act, const void *w, const float *bias, const void *residual_half, void *out_half, int32_t B,
                        int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t CoutPad, int32_t ksize, void *stream);
+/* Fused-operand form (k_conv3x3_v3<FUSE>, "v4"): replaces GroupNorm32 + SiLU (+ FiLM) + conv3x3 of a ResBlock
+ * (guided_diffusion/unet.py:199-212, 246-251; nn.py:17-19) by ONE kernel.  dpir_gn_coef folds the per-tensor quad statistics
+ * q1/q2 ([B][C/4][2] sum, sumsq of the one or two concatenated sources), gamma/beta and optional per-sample FiLM rows
+ * (film[b*film_stride + c] = scale, [.. + C + c] = shift) into coef dev fp32 [B][2][C] = (0.5*scale_c, 0.5*offset_c);
+ * dpir_conv_gnfuse_f16io computes out = conv3x3(SiLU(scale*x + offset)) + bias (+ residual) with x = (src1 | src2) raw fp16
+ * NHWC (C1, C2 multiples of 64; src2 NULL / C2 0 for one source), zero padding applied AFTER the activation, fp16 NHWC
+ * residual/output. */
+int dpir_gn_coef(const double *q1, const double *q2, int32_t C1, int32_t C2, const float *gamma, const float *beta, const float *film,
+                 int32_t film_stride, int32_t B, int32_t HW, float *coef, void *stream);
+int dpir_conv_gnfuse_f16io(const void *src1, int32_t C1, const void *src2, int32_t C2, const float *coef, const void *w,
+                           const float *bias, const void *residual_half, void *out_half, int32_t B, int32_t H, int32_t W,
+                           int32_t Cout, int32_t CoutPad, void *stream);
+/* 1 (default): eligible ResBlocks of the fp16s pipeline run GroupNorm+SiLU inside their convolutions (above) with fp32
+ * operand arithmetic (bit-identical activation values to the separate pass); 2: packed-half arithmetic (tanh.approx.f16x2);
+ * 0: every norm is a separate k_gn_apply pass.  Process-wide; drops the cached plans of `e` (may be NULL). */
+int dpir_set_gn_fusion(dpir_engine *e, int32_t enable);
 /* A/B switch for tests and benchmarks.  0 (default): 3x3 convs on >=16x16 maps use the persistent swap-AB halo-reuse
  * kernel (k_conv3x3_v3), everything else the one-tile-per-CTA kernel (k_conv_tc); 1: k_conv_tc everywhere;
  * 2: the persistent kernel with pixels on the M side (k_conv3x3_v2).  Affects plans created afterwards. */

@@ -145,3 +145,71 @@ def test_conv_tc_fp16_stream_io_matches_torch(B, H, W, Cin, Cout, residual, vari
     got = out.permute(0, 3, 1, 2).float()
     assert not torch.isnan(got).any()
     assert rel_l2(got, ref) < 6e-4      # fp16 rounding of the stored result
+
+
+def _gn_reference(x, gamma, beta, film, eps=1e-5):
+    """GroupNorm32 (nn.py:17-19) + optional FiLM (unet.py:246-249) + SiLU in fp64 on (B,C,H,W)."""
+    y = F.group_norm(x.double(), 32, gamma.double(), beta.double(), eps)
+    if film is not None:
+        C = x.shape[1]
+        y = y * (1 + film[:, :C].double()[:, :, None, None]) + film[:, C:].double()[:, :, None, None]
+    return F.silu(y)
+
+
+def _quad_stats(xh):
+    """[B][C/4][2] fp64 (sum, sumsq) of an NHWC fp16 tensor - what the producing conv epilogue attaches to it."""
+    B, H, W, C = xh.shape
+    v = xh.double().reshape(B, H * W, C // 4, 4)
+    return torch.stack([v.sum(dim=(1, 3)), (v * v).sum(dim=(1, 3))], dim=-1).contiguous()
+
+
+@pytest.mark.parametrize("math", ["1", "2"])
+@pytest.mark.parametrize("B,H,W,C1,C2,Cout,residual,film", [
+    (2, 32, 32, 128, 0, 128, True, True),       # norm2 -> conv2 with FiLM and residual
+    (3, 64, 64, 128, 0, 256, False, False),     # two cout tiles
+    (1, 24, 40, 192, 0, 128, True, False),      # ragged tiles: zero padding must be applied AFTER the activation
+    (2, 16, 16, 256, 256, 512, False, False),   # virtual concat (norm1 of an output block), groups straddle nothing
+    (2, 32, 32, 512, 256, 256, False, True),    # concat 768: 24 channels per group straddle the two sources
+    (1, 256, 256, 128, 128, 128, False, False), # full-resolution concat
+    (5, 16, 16, 256, 0, 256, True, True),
+])
+def test_conv_gn_fused_matches_torch(B, H, W, C1, C2, Cout, residual, film, math):
+    """k_conv3x3_v3<FUSE>: out = conv3x3(SiLU(FiLM(GroupNorm(x1|x2)))) + bias (+ residual), the norm evaluated inside the conv."""
+    from diffpir_b200 import _lib
+    lib = _lib.load()
+    _lib.check(lib.dpir_set_gn_fusion(None, int(math)), "dpir_set_gn_fusion")     # 1: fp32 operand arithmetic, 2: packed half
+    C = C1 + C2
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(B, C, H, W, generator=g) * 1.7 + 0.6 * torch.randn(B, C, 1, 1, generator=g)
+    xh = x.half()
+    w = torch.randn(Cout, C, 3, 3, generator=g) / (C * 9) ** 0.5
+    b = torch.randn(Cout, generator=g) * 0.1
+    gamma = 1 + 0.3 * torch.randn(C, generator=g)
+    beta = 0.2 * torch.randn(C, generator=g)
+    fl = 0.3 * torch.randn(B, 2 * C, generator=g) if film else None
+    r = torch.randn(B, Cout, H, W, generator=g).half() if residual else None
+    act = _gn_reference(xh.float(), gamma, beta, fl)
+    ref = F.conv2d(act, w.half().double(), b.double(), padding=1)
+    if r is not None:
+        ref = ref + r.double()
+    x_nhwc = xh.permute(0, 2, 3, 1).contiguous()
+    s1 = x_nhwc[..., :C1].contiguous().cuda()
+    s2 = x_nhwc[..., C1:].contiguous().cuda() if C2 else None
+    q1 = _quad_stats(s1.cpu()).cuda()
+    q2 = _quad_stats(s2.cpu()).cuda() if C2 else None
+    coef = torch.empty(B, 2, C, device="cuda")
+    flc = fl.cuda().contiguous() if film else None
+    _lib.check(lib.dpir_gn_coef(_lib.ptr(q1), _lib.ptr(q2), C1, C2, _lib.ptr(gamma.cuda()), _lib.ptr(beta.cuda()), _lib.ptr(flc),
+                                2 * C, B, H * W, _lib.ptr(coef), _lib.stream_ptr()), "dpir_gn_coef")
+    wp = _pack_tc(w, Cout).cuda()
+    res = r.permute(0, 2, 3, 1).contiguous().cuda() if r is not None else None
+    out = torch.full((B, H, W, Cout), float("nan"), device="cuda", dtype=torch.float16)
+    _lib.check(lib.dpir_conv_gnfuse_f16io(_lib.ptr(s1), C1, _lib.ptr(s2), C2, _lib.ptr(coef), _lib.ptr(wp), _lib.ptr(b.cuda()),
+                                          _lib.ptr(res), _lib.ptr(out), B, H, W, Cout, Cout, _lib.stream_ptr()),
+               "dpir_conv_gnfuse_f16io")
+    torch.cuda.synchronize()
+    lib.dpir_set_gn_fusion(None, 1)
+    got = out.permute(0, 3, 1, 2).float()
+    assert not torch.isnan(got).any()
+    # fp16 rounding of the activated operand (+ of the stored result); packed-half arithmetic (math 2) rounds twice more
+    assert rel_l2(got, ref) < (1.2e-3 if math == "1" else 3e-3)

@@ -122,3 +122,32 @@ def test_imagenet_unet_forward_matches_oracle():
         print(f"imagenet unet {precision}: rel-L2 {err:.3e}")
         assert err < TOL[precision], err
         del m
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_gn_fusion_equivalence(mode):
+    """fp16s: ResBlock GroupNorm+SiLU evaluated inside the convolutions (v4 kernel) vs as separate passes - same network, the
+    only difference is where the activated operand is rounded to fp16 (mode 1: identical arithmetic) -> agreement far inside
+    the fp16 tolerance; both against the oracle."""
+    cfg = small_config()
+    sd = weights(cfg)
+    x, t = _inputs(3, 64, seed=8)
+    ref = unet_oracle.unet_forward(sd, cfg.as_dict(), x.double(), t)
+    m = make_model(cfg, "fp16s")
+    try:
+        m.set_gn_fusion(0)
+        a = m(x.cuda(), t.cuda())
+        m.set_gn_fusion(mode)
+        m.profile_begin()
+        b = m(x.cuda(), t.cuda())
+        rows = m.profile_end()
+        assert any(r["gn_fused"] for r in rows), "no convolution took the fused-operand path"
+        ea, eb, eab = rel_l2(a, ref), rel_l2(b, ref), rel_l2(b, a)
+        print(f"gn fusion mode {mode}: separate {ea:.3e} fused {eb:.3e} fused-vs-separate {eab:.3e}")
+        assert ea < TOL["fp16s"] and eb < TOL["fp16s"] * (1 if mode == 1 else 1.5)
+        assert eab < (5e-4 if mode == 1 else 4e-3)
+        m.set_graph_mode(True)
+        c = m(x.cuda(), t.cuda())
+        assert torch.equal(b, c)
+    finally:
+        m.set_gn_fusion(1)

@@ -23,12 +23,14 @@ def main():
     ap.add_argument("--json", default="")
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--variant", type=int, default=0, help="dpir_conv_tc_variant: 0 auto (v3), 1 v1, 2 v2")
+    ap.add_argument("--gn-fusion", type=int, default=1, help="0 separate GroupNorm passes, 1 fused into the convs (fp32 math), 2 (half math)")
     a = ap.parse_args()
     from diffpir_b200 import _lib
     _lib.check(_lib.load().dpir_conv_tc_variant(a.variant), "dpir_conv_tc_variant")
     cfg = arch.ffhq_config() if a.model == "ffhq" else arch.imagenet_config()
     m = UNetModel(cfg, precision=a.precision)
     m.load_state_dict(synth.synthetic_state_dict(cfg, 0))
+    m.set_gn_fusion(a.gn_fusion)
     B = a.batch
     x = torch.randn(B, 3, a.size, a.size, device="cuda")
     t = torch.full((B,), 500, device="cuda", dtype=torch.int64)
@@ -46,6 +48,7 @@ def main():
     tot = sum(r["ms"] for r in rows) / a.reps
     agg = {}
     print(f"{'kind':10s} {'dims':28s} {'ms':>8s} {'rate':>14s}")
+    by_kind = {}
     for r in rows:
         ms = r["ms"] / a.reps
         d = r["dims"]
@@ -53,11 +56,11 @@ def main():
         if r["kind"] == "conv":
             H, W, Cin, Cout, ks, Cin2 = d
             fl = 2.0 * B * H * W * (ks * ks * Cin + Cin2) * Cout
-            rate = f"{fl / ms / 1e9:8.1f} TF/s"
-            key = ("conv", H, Cin, Cout, ks, Cin2)
+            rate = f"{fl / ms / 1e9:8.1f} TF/s" + (" +gn" if r.get("gn_fused") else "")
+            key = ("conv+gn" if r.get("gn_fused") else "conv", H, Cin, Cout, ks, Cin2)
         elif r["kind"] == "gn_apply":
             H, W, C, rs = d[:4]
-            by = B * H * W * C * (4 + 2)
+            by = B * H * W * C * ((2 if a.precision == "fp16s" else 4) + 2)      # one read + one write of the tensor
             rate = f"{by / ms / 1e6:8.1f} GB/s~"
             key = ("gn_apply", H, C, rs, 0, 0)
         elif r["kind"] == "gn_stats":
@@ -67,11 +70,12 @@ def main():
             key = ("gn_stats", HW, C, 0, 0, 0)
         else:
             key = (r["kind"], 0, 0, 0, 0, 0)
+        by_kind[r["kind"]] = by_kind.get(r["kind"], 0.0) + ms
         agg.setdefault(key, [0.0, 0])
         agg[key][0] += ms
         agg[key][1] += 1
         print(f"{r['kind']:10s} {str(d):28s} {ms:8.4f} {rate:>14s}")
-    print(f"\ntotal serialised {tot:.3f} ms per forward (B={B})")
+    print(f"\ntotal serialised {tot:.3f} ms per forward (B={B}); by kind: " + ", ".join(f"{k} {v:.3f}" for k, v in sorted(by_kind.items())))
     print("\naggregated by shape (ms per forward, count):")
     for k, (ms, n) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:40]:
         print(f"  {str(k):40s} {ms:8.3f} ms  x{n}")
