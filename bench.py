@@ -378,7 +378,27 @@ def main():
         peak = peaks.get("bf16_tflops_sustained", FALLBACK_PEAKS["bf16_tflops_sustained"])
         achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
         unet_ms = sum(by_kind.values())
-        roofline = {"bound": "tensor", "kernel": "k_conv_tc (tcgen05 implicit-GEMM conv, all 3x3/1x1 layers of one forward)",
+        # A/B in the same process: the same forward with every GroupNorm as a separate pass (conv kernels do convolution only)
+        ab = None
+        if args.gn_fusion:
+            model.set_gn_fusion(0)
+            model.x0(x, ts[0], out=x0)                  # re-plan + warm-up
+            model.profile_begin()
+            for j in range(args.profile_steps):
+                model.x0(x, ts[(7 * j) % len(steps_tab)], out=x0)
+            rows_ab = model.profile_end()
+            model.set_gn_fusion(args.gn_fusion)
+            kind_ab = {}
+            for r in rows_ab:
+                kind_ab[r["kind"]] = kind_ab.get(r["kind"], 0.0) + r["ms"] / args.profile_steps
+            ach_ab = conv_flops / (kind_ab.get("conv", 0.0) * 1e-3) / 1e12 if kind_ab.get("conv") else 0.0
+            ab = {"note": "same forward with GroupNorm+SiLU as separate k_gn_apply passes (gn_fusion=0): convolution-only kernels",
+                  "achieved": ach_ab, "frac": ach_ab / peak if peak else None, "conv_ms_per_step": kind_ab.get("conv", 0.0),
+                  "unet_ms_per_step_serialised": sum(kind_ab.values()),
+                  "ms_by_kernel_kind": {k2: round(v, 4) for k2, v in sorted(kind_ab.items())}}
+        roofline = {"bound": "tensor", "kernel": "k_conv3x3_v3<FUSE> / k_conv_tc (tcgen05 implicit-GEMM conv, all 3x3/1x1 layers of one forward; "
+                                                 "with gn_fusion the ResBlock convs also evaluate GroupNorm+FiLM+SiLU on their operand)",
+                    "separate_norm_passes_ab": ab,
                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
                     "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['_source']})", "traffic": None,
                     "conv_ms_per_step": conv_ms, "unet_ms_per_step_serialised": unet_ms,

@@ -1,4 +1,5 @@
 """Build libdiffpir_b200.so in-tree with nvcc for sm_100a (no JIT cache: the .so travels with the repo snapshot)."""
+import hashlib
 import os
 import shutil
 import subprocess
@@ -7,6 +8,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdiffpir_b200.so")
+STAMP = os.path.join(HERE, "libdiffpir_b200.srchash")     # sha256 of the sources the shipped .so was built from
+LOCK = os.path.join(HERE, ".build.lock")
 SOURCES = ["prox.cu", "unet_kernels.cu", "conv_tc.cu", "engine.cu"]
 HEADERS = ["common.cuh", "unet_kernels.cuh", os.path.join("..", "..", "include", "diffpir_b200.h")]
 
@@ -18,40 +21,69 @@ def _nvcc():
     raise RuntimeError("nvcc not found")
 
 
+def _source_hash():
+    """Content hash of everything the library is built from (mtimes do not survive the copy to the GPU box)."""
+    h = hashlib.sha256()
+    for d in [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]:
+        with open(d, "rb") as f:
+            h.update(os.path.basename(d).encode() + b"\0" + f.read())
+    return h.hexdigest()
+
+
 def needs_build():
     if not os.path.exists(LIB):
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
-    return any(os.path.getmtime(d) > t for d in deps)
+    try:
+        return open(STAMP).read().strip() != _source_hash()
+    except OSError:
+        return True
 
 
 def build(force=False, verbose=False):
+    """Compile + link under an exclusive file lock (several ranks may import the package at once): objects go to a private
+    temporary directory and the finished library is moved into place atomically, then the source hash is stamped."""
     if not force and not needs_build():
         return LIB
-    objs = []
-    flags = ["-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
-             "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
-    if verbose:
-        flags += ["-Xptxas", "-v"]
-    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
-    procs = []
-    for s in SOURCES:
-        o = os.path.join(HERE, "build", s.replace(".cu", ".o"))
-        objs.append(o)
-        cmd = [_nvcc()] + flags + ["-c", os.path.join(CSRC, s), "-o", o]
-        procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-    for s, p in procs:
-        out, _ = p.communicate()
-        if verbose or p.returncode:
-            sys.stderr.write(out)
-        if p.returncode:
-            raise RuntimeError(f"nvcc failed on {s}")
-    cmd = [_nvcc(), "-shared", "-o", LIB] + objs + ["-lcufft", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
-    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    if r.returncode:
-        sys.stderr.write(r.stdout)
-        raise RuntimeError("link failed")
+    import fcntl
+    import tempfile
+    with open(LOCK, "w") as lk:
+        fcntl.flock(lk, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():      # another process built it while we waited
+                return LIB
+            flags = ["-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
+                     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
+            if verbose:
+                flags += ["-Xptxas", "-v"]
+            os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+            tmp = tempfile.mkdtemp(prefix="obj.", dir=os.path.join(HERE, "build"))
+            try:
+                objs, procs = [], []
+                for s in SOURCES:
+                    o = os.path.join(tmp, s.replace(".cu", ".o"))
+                    objs.append(o)
+                    cmd = [_nvcc()] + flags + ["-c", os.path.join(CSRC, s), "-o", o]
+                    procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+                for s, p in procs:
+                    out, _ = p.communicate()
+                    if verbose or p.returncode:
+                        sys.stderr.write(out)
+                    if p.returncode:
+                        raise RuntimeError(f"nvcc failed on {s}")
+                out_lib = os.path.join(tmp, "libdiffpir_b200.so")
+                cmd = [_nvcc(), "-shared", "-o", out_lib] + objs + ["-lcufft", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
+                r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+                if r.returncode:
+                    sys.stderr.write(r.stdout)
+                    raise RuntimeError("link failed")
+                os.replace(out_lib, LIB)
+                with open(STAMP + ".tmp", "w") as f:
+                    f.write(_source_hash() + "\n")
+                os.replace(STAMP + ".tmp", STAMP)
+            finally:
+                shutil.rmtree(tmp, ignore_errors=True)
+        finally:
+            fcntl.flock(lk, fcntl.LOCK_UN)
     return LIB
 
 

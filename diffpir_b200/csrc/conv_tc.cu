@@ -47,12 +47,41 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t *bar, uint32_t parity
       : "memory");
   return ok;
 }
-// bounded spin: a broken pipeline traps after ~2 s instead of hanging the GPU
+// try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes (or ~the hint elapses) instead of
+// returning after the short default time limit.  Without it a waiting warp re-issues the poll every ~70 cycles: ncu counted
+// 141 M of the 255 M epilogue warp-instructions of one 256x256 convolution in this loop - a fifth of the issue slots of
+// sub-partitions that are issue-bound once the operand producers of the fused kernel share them.
+__device__ __forceinline__ uint32_t mbar_try_wait_sleep(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(200000u)      // nanoseconds
+      : "memory");
+  return ok;
+}
+// bounded wait (latency-critical hand-offs): a broken pipeline traps after ~1-2 s instead of hanging the GPU.  The hardware
+// caps the suspend time of a try_wait at ~130 cycles (measured), so the loop body is kept to a counter: every poll of a
+// waiting warp takes issue slots from the warps that work.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) __trap();
+  uint32_t polls = 0;
+  while (!mbar_try_wait_sleep(bar, parity)) {
+    if (++polls > 20000000u) __trap();
+  }
+}
+// the same for long waits with slack (an epilogue warp waiting for the next accumulator, ~10 us): back off with nanosleep so
+// that the ~140 polls per wait (ncu: 89 M of the 436 M warp-instructions of a fused 256x256 convolution) become a handful
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  uint32_t polls = 0;
+  while (!mbar_try_wait_sleep(bar, parity)) {
+    __nanosleep(256);
+    if (++polls > 4000000u) __trap();
   }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -387,7 +416,8 @@ constexpr int V2_STAGES = 2;
 constexpr int V2_THREADS = 320;                       // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
 // v4 (fused GroupNorm+SiLU operand): 5 warpgroups - {TMA, MMA, 2 idle warps}, 2 x epilogue (warps 4-11), 2 x operand
 // producers (warps 12-19).  5 warps per SM sub-partition leave 96 registers per thread, fewer than the epilogue (117) and the
-// double-buffered producers need, so the warpgroups re-balance the register file with setmaxnreg: 40 / 120 / 112.
+// double-buffered producers need, so the warpgroups re-balance the CTA's register allocation (640 x 96) with setmaxnreg:
+// 32 / 120 / 104 per thread (128*32 + 256*120 + 256*104 = 640*96: the pool is what the launch allocated, no more).
 constexpr int V4_THREADS = 640;
 constexpr int V2_STG_BYTES = 8 * 4096;                // per-epilogue-warp 32 x 128 B transpose buffers
 constexpr int V2_SMEM = V2_STAGES * V2_STAGE_BYTES + V2_STG_BYTES + 1024 + 256;
@@ -399,7 +429,8 @@ struct ConvV2Geom {
   int skip_chunks;                    // extra K chunks of a fused 1x1 convolution on a second operand (ResBlock skip), or 0
   int skip_chunks_a;                  // of which the first skip_chunks_a come from tmA2, the rest from tmA2b (concat skip input)
   int dbg;                            // timing diagnostics only (env DPIR_CONV_DEBUG): 1 = no epilogue memory traffic,
-                                      // 2 = no MMA issue, 4 = no TMA loads; results are garbage when non-zero
+                                      // 2 = no MMA issue, 4 = no TMA loads; v4 producers: 32 = no global loads, 64 = no
+                                      // arithmetic, 128 = no proxy fence; results are garbage when non-zero
   int tiles_w, tiles_h, n_tiles;      // 16x16 pixel tiles per image, Cout/128 column tiles
   int total_tiles;                    // B * tiles_h * tiles_w * n_tiles
 };
@@ -832,42 +863,78 @@ __global__ void __launch_bounds__(FUSE ? V4_THREADS : V2_THREADS, 1) k_conv3x3_v
   auto role_producer = [&]() {
     // ---------------------------------------------------------------- v4 operand producers (8 warps, 256 threads)
     // The 18 x 16 pixel halo box of a stage is 2304 16-byte units (pixel row r = yy*16 + xx, channel octet j); thread p owns
-    // j = p & 7, xx = (p >> 3) & 15 and the 9 rows yy = 2i + (p >> 7): the channel octet (hence the coefficients), the column
-    // validity and the swizzle term (r & 7 == xx & 7) are per-thread constants, and a warp reads 4 pixels x 128 contiguous B.
+    // j = p & 7, xx = (p >> 3) & 15 and the 9 rows yy = 2i + (p >> 7): the channel octet (hence the 8 coefficient pairs), the
+    // column validity and the swizzle term (r & 7 == xx & 7) are per-thread constants; a warp reads 4 pixels x 128 contiguous B.
+    // Per stage: wait until the MMAs that read the slot have retired -> transform the 9 raw units held in registers -> st.shared
+    // -> fence.proxy.async -> arrive -> issue the global loads of the next stage into the same registers.  The loads come
+    // AFTER the fence on purpose: it compiles to MEMBAR.ALL.CTA, which waits for every load in flight.
+    // The SM sub-partitions are issue-bound in this kernel (2 producer + 2 epilogue warps each, ncu: ~0.9 IPC), so the stage
+    // is written for instruction count: branch-free (validity is a bit mask that predicates the loads and, only in tiles that
+    // touch the image border - warp-uniform test - selects zeros), one register buffer, addresses advanced incrementally.
     const int p = (int)threadIdx.x - 12 * 32;
     const int j = p & 7, xx = (p >> 3) & 15, yh = p >> 7;
     const uint32_t dst_off = (uint32_t)(yh * 2048 + xx * 128 + ((j ^ (xx & 7)) << 4));
     const int Ctot = gf.C1 + gf.C2;
-    uint4 cur[9], nxt[9];
-    uint32_t mcur = 0, mnxt = 0;          // validity bits of the 9 units (outside the image -> exact zeros)
+    uint4 buf[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) buf[i] = make_uint4(0u, 0u, 0u, 0u);
+    uint32_t mask = 0;                    // validity bits of the 9 units in buf (outside the image -> exact zeros)
     float hs[8], ho[8];
-    // issue the 9 global loads of main stage k of the tile at (n, h0, w0) into buf
-    auto issue = [&](int n, int h0, int w0, int k, uint4 (&buf)[9], uint32_t &mask) {
+    // state of the tile being LOADED (it runs one stage ahead of the tile being transformed)
+    int ln = 0, lw0 = 0;
+    uint32_t lym = 0;
+    int64_t lbase = 0;                    // pixel index of (n, h0 - 1 + yh, w0 - 1 + xx)
+    auto load_tile = [&](int tile) {
+      int h0, co0;
+      decode(tile, ln, h0, lw0, co0);
+      lym = 0;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) lym |= ((unsigned)(h0 - 1 + yh + 2 * i) < (unsigned)g.H) ? (1u << i) : 0u;
+      lbase = ((int64_t)ln * g.H + (h0 - 1 + yh)) * g.W + (lw0 - 1 + xx);
+    };
+    // issue the (up to) 9 global loads of main stage k of the tile described by (lbase, lym, lw0)
+    auto issue = [&](int k) {
       const int ch = k / 3, dx = k - ch * 3;
       const int c = ch * TC_BK + j * 8;
-      const __half *src; int Cs, cc;
-      if (c < gf.C1) { src = gf.src1; Cs = gf.C1; cc = c; } else { src = gf.src2; Cs = gf.C2; cc = c - gf.C1; }
-      const int x = w0 + dx - 1 + xx;
-      const bool xok = (unsigned)x < (unsigned)g.W;
-      const int y0 = h0 - 1 + yh;
-      const __half *ptr = src + (((int64_t)n * g.H + y0) * g.W + x) * Cs + cc;
-      const int64_t rs = (int64_t)2 * g.W * Cs;
-      mask = 0;
+      mask = ((unsigned)(lw0 + dx - 1 + xx) < (unsigned)g.W) ? lym : 0u;
+      if (g.dbg & 32) mask = 0u;          // timing diagnostic: no global loads
+      const __half *ptr;
+      int64_t rs;
+      if (c < gf.C1) { ptr = gf.src1 + (lbase + dx) * gf.C1 + c; rs = (int64_t)2 * g.W * gf.C1; }
+      else { ptr = gf.src2 + (lbase + dx) * gf.C2 + (c - gf.C1); rs = (int64_t)2 * g.W * gf.C2; }
 #pragma unroll
       for (int i = 0; i < 9; ++i) {
-        const bool ok = xok && (unsigned)(y0 + 2 * i) < (unsigned)g.H;
-        if (ok) { buf[i] = __ldg(reinterpret_cast<const uint4 *>(ptr + i * rs)); mask |= 1u << i; }   // invalid units: masked below
+        if (mask & (1u << i)) buf[i] = __ldg(reinterpret_cast<const uint4 *>(ptr));
+        ptr += rs;
       }
     };
+    // SiLU(GroupNorm(x)) of one 16-byte unit (8 channels)
+    auto act8 = [&](const uint4 &raw) {
+      uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const __half2 hv = *reinterpret_cast<const __half2 *>(&w[q]);
+        __half2 r;
+        if (FUSE == 2) {
+          const __half2 h = __hfma2(hv, __floats2half2_rn(hs[2 * q], hs[2 * q + 1]), __floats2half2_rn(ho[2 * q], ho[2 * q + 1]));
+          r = __hfma2(h, tanh_approx_h2(h), h);
+        } else {
+          const float2 f = __half22float2(hv);
+          const float ha = fmaf(f.x, hs[2 * q], ho[2 * q]), hb = fmaf(f.y, hs[2 * q + 1], ho[2 * q + 1]);
+          r = __floats2half2_rn(fmaf(ha, tanh_approx_f(ha), ha), fmaf(hb, tanh_approx_f(hb), hb));
+        }
+        w[q] = *reinterpret_cast<const uint32_t *>(&r);
+      }
+      return make_uint4(w[0], w[1], w[2], w[3]);
+    };
     int tile = blockIdx.x;
-    int n = 0, h0 = 0, w0 = 0, co0 = 0;
     if (tile < g.total_tiles) {
-      decode(tile, n, h0, w0, co0);
-      issue(n, h0, w0, 0, nxt, mnxt);
+      load_tile(tile);
+      issue(0);
     }
     uint32_t it = 0;
     for (; tile < g.total_tiles; tile += gridDim.x) {
-      int n2 = n, h2 = h0, w2 = w0;      // the tile after this one (decoded once, at its prefetch)
+      const int n = ln;                   // image of the tile being transformed (the loader moves on during its last stage)
       for (int k = 0; k < num_k; ++k, ++it) {
         const int s = it % V2_STAGES;
         const uint32_t ph = (it / V2_STAGES) & 1u;
@@ -877,9 +944,6 @@ __global__ void __launch_bounds__(FUSE ? V4_THREADS : V2_THREADS, 1) k_conv3x3_v
           if (lane == 0) mbar_arrive(&full[s]);
           continue;
         }
-#pragma unroll
-        for (int i = 0; i < 9; ++i) cur[i] = nxt[i];
-        mcur = mnxt;
         const int ch = k / 3;
         if (k == ch * 3) {                 // new 64-channel chunk: this thread's 8 coefficient pairs
           const float *cf = gf.coef + (int64_t)n * 2 * Ctot + ch * TC_BK + j * 8;
@@ -888,44 +952,33 @@ __global__ void __launch_bounds__(FUSE ? V4_THREADS : V2_THREADS, 1) k_conv3x3_v
           hs[0] = a0.x; hs[1] = a0.y; hs[2] = a0.z; hs[3] = a0.w; hs[4] = a1.x; hs[5] = a1.y; hs[6] = a1.z; hs[7] = a1.w;
           ho[0] = b0.x; ho[1] = b0.y; ho[2] = b0.z; ho[3] = b0.w; ho[4] = b1.x; ho[5] = b1.y; ho[6] = b1.z; ho[7] = b1.w;
         }
-        // prefetch the next main stage (same tile, or the first stage of this CTA's next tile)
-        if (k + 1 < num_main) {
-          issue(n, h0, w0, k + 1, nxt, mnxt);
-        } else if (tile + (int)gridDim.x < g.total_tiles) {
-          int co2;
-          decode(tile + (int)gridDim.x, n2, h2, w2, co2);
-          issue(n2, h2, w2, 0, nxt, mnxt);
-        }
         mbar_wait(&empty[s], ph ^ 1u);
         uint8_t *dst = smem + s * V2_STAGE_BYTES + dst_off;
+        if (g.dbg & 64) {                   // timing diagnostic: raw copy, no arithmetic
 #pragma unroll
-        for (int i = 0; i < 9; ++i) {
-          uint4 v = make_uint4(0u, 0u, 0u, 0u);
-          if (mcur & (1u << i)) {
-            uint32_t w[4] = {cur[i].x, cur[i].y, cur[i].z, cur[i].w};
+          for (int i = 0; i < 9; ++i) *reinterpret_cast<uint4 *>(dst + i * 4096) = buf[i];
+        } else if (__all_sync(0xffffffffu, mask == 0x1FFu)) {   // interior: every unit of the warp is inside the image
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const __half2 hv = *reinterpret_cast<const __half2 *>(&w[q]);
-              if (FUSE == 2) {
-                const __half2 h = __hfma2(hv, __floats2half2_rn(hs[2 * q], hs[2 * q + 1]), __floats2half2_rn(ho[2 * q], ho[2 * q + 1]));
-                const __half2 r = __hfma2(h, tanh_approx_h2(h), h);
-                w[q] = *reinterpret_cast<const uint32_t *>(&r);
-              } else {
-                const float2 f = __half22float2(hv);
-                const float ha = fmaf(f.x, hs[2 * q], ho[2 * q]), hb = fmaf(f.y, hs[2 * q + 1], ho[2 * q + 1]);
-                const __half2 r = __floats2half2_rn(fmaf(ha, tanh_approx_f(ha), ha), fmaf(hb, tanh_approx_f(hb), hb));
-                w[q] = *reinterpret_cast<const uint32_t *>(&r);
-              }
-            }
-            v = make_uint4(w[0], w[1], w[2], w[3]);
+          for (int i = 0; i < 9; ++i) *reinterpret_cast<uint4 *>(dst + i * 4096) = act8(buf[i]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 9; ++i) {
+            uint4 v = act8(buf[i]);
+            if (!(mask & (1u << i))) v = make_uint4(0u, 0u, 0u, 0u);    // select, not a branch
+            *reinterpret_cast<uint4 *>(dst + i * 4096) = v;
           }
-          *reinterpret_cast<uint4 *>(dst + i * 4096) = v;
         }
-        fence_proxy_async();               // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        if (!(g.dbg & 128)) fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive(&full[s]);
+        // the next main stage (same tile, or the first stage of this CTA's next tile)
+        if (k + 1 < num_main) {
+          issue(k + 1);
+        } else if (tile + (int)gridDim.x < g.total_tiles) {
+          load_tile(tile + (int)gridDim.x);
+          issue(0);
+        }
       }
-      n = n2; h0 = h2; w0 = w2;
     }
   };
   auto role_epilogue = [&](const int ew) {
@@ -960,7 +1013,7 @@ __global__ void __launch_bounds__(FUSE ? V4_THREADS : V2_THREADS, 1) k_conv3x3_v
         mbar_expect_tx(bar, 2048);
         tma_load_4d((rcount & 1) ? resb1 : resb0, &tmRes, bar, cbase, w0, ybase, n);
       }
-      mbar_wait(&tmem_full[ab], aph);
+      mbar_wait_relaxed(&tmem_full[ab], aph);
       tc_fence_after();
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + ab * 256u + (uint32_t)hv * 128u;
 #pragma unroll 1
@@ -1036,14 +1089,14 @@ __global__ void __launch_bounds__(FUSE ? V4_THREADS : V2_THREADS, 1) k_conv3x3_v
   if constexpr (FUSE != 0) {
     // setmaxnreg is executed once per warpgroup, at the top of the branch that dominates all of that group's code
     if (warp < 4) {
-      setmaxnreg_dec<40>();
+      setmaxnreg_dec<32>();
       if (warp == 0) role_tma();
       else if (warp == 1) role_mma();
     } else if (warp < 12) {
       setmaxnreg_inc<120>();
       role_epilogue(warp - 4);
     } else {
-      setmaxnreg_inc<112>();
+      setmaxnreg_inc<104>();
       role_producer();
     }
   } else {

@@ -167,7 +167,7 @@ def _quad_stats(xh):
 @pytest.mark.parametrize("B,H,W,C1,C2,Cout,residual,film", [
     (2, 32, 32, 128, 0, 128, True, True),       # norm2 -> conv2 with FiLM and residual
     (3, 64, 64, 128, 0, 256, False, False),     # two cout tiles
-    (1, 24, 40, 192, 0, 128, True, False),      # ragged tiles: zero padding must be applied AFTER the activation
+    (1, 24, 40, 128, 0, 128, True, False),      # ragged tiles: zero padding must be applied AFTER the activation
     (2, 16, 16, 256, 256, 512, False, False),   # virtual concat (norm1 of an output block), groups straddle nothing
     (2, 32, 32, 512, 256, 256, False, True),    # concat 768: 24 channels per group straddle the two sources
     (1, 256, 256, 128, 128, 128, False, False), # full-resolution concat
@@ -199,12 +199,13 @@ def test_conv_gn_fused_matches_torch(B, H, W, C1, C2, Cout, residual, film, math
     q2 = _quad_stats(s2.cpu()).cuda() if C2 else None
     coef = torch.empty(B, 2, C, device="cuda")
     flc = fl.cuda().contiguous() if film else None
-    _lib.check(lib.dpir_gn_coef(_lib.ptr(q1), _lib.ptr(q2), C1, C2, _lib.ptr(gamma.cuda()), _lib.ptr(beta.cuda()), _lib.ptr(flc),
+    gd, bd, biasd = gamma.cuda(), beta.cuda(), b.cuda()      # named: a temporary's block could be recycled before the launch
+    _lib.check(lib.dpir_gn_coef(_lib.ptr(q1), _lib.ptr(q2), C1, C2, _lib.ptr(gd), _lib.ptr(bd), _lib.ptr(flc),
                                 2 * C, B, H * W, _lib.ptr(coef), _lib.stream_ptr()), "dpir_gn_coef")
     wp = _pack_tc(w, Cout).cuda()
     res = r.permute(0, 2, 3, 1).contiguous().cuda() if r is not None else None
     out = torch.full((B, H, W, Cout), float("nan"), device="cuda", dtype=torch.float16)
-    _lib.check(lib.dpir_conv_gnfuse_f16io(_lib.ptr(s1), C1, _lib.ptr(s2), C2, _lib.ptr(coef), _lib.ptr(wp), _lib.ptr(b.cuda()),
+    _lib.check(lib.dpir_conv_gnfuse_f16io(_lib.ptr(s1), C1, _lib.ptr(s2), C2, _lib.ptr(coef), _lib.ptr(wp), _lib.ptr(biasd),
                                           _lib.ptr(res), _lib.ptr(out), B, H, W, Cout, Cout, _lib.stream_ptr()),
                "dpir_conv_gnfuse_f16io")
     torch.cuda.synchronize()
