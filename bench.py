@@ -182,6 +182,17 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def conv_traffic():
+    """DRAM bytes of the dominant kernel from the committed `ncu --set full` capture (cannot be measured live): the first
+    ResBlock convolution of the forward (256x256, 128->128, B=32, GroupNorm+SiLU fused), beside its algorithmic bytes."""
+    p = os.path.join(ROOT, "profiles", "r01_ncu_conv_v4_fused_full.md")
+    if not os.path.exists(p):
+        return None
+    return {"dram_bytes_per_launch": 1074328000 + 509015552, "algorithmic_bytes_per_launch": 2 * 32 * 256 * 256 * 128 * 2,
+            "launch": "k_conv3x3_v3<1> 256x256 128->128 B=32 fp16 in/out (read x once + write h once)",
+            "source": "profiles/r01_ncu_conv_v4_fused_full.md (dram__bytes_read.sum + dram__bytes_write.sum, launch 0)"}
+
+
 def workload_config(B, precision):
     return {"workload": f"Gaussian/motion deblur (Levin-size kernels), batch {B} synthetic FFHQ-shape 256x256 per GPU, 100 NFE "
                         f"quad schedule, diffusion_ffhq_10m architecture (random-init), sigma_n=12.75/255, lambda=7, zeta=0.3",
@@ -248,6 +259,9 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
+        # stdout carries exactly one JSON line: NCCL_DEBUG=VERSION (set on the GPU boxes) makes NCCL print its banner there
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     from diffpir_b200 import _lib, ops, utils_sisr
@@ -400,7 +414,7 @@ def main():
                                                  "with gn_fusion the ResBlock convs also evaluate GroupNorm+FiLM+SiLU on their operand)",
                     "separate_norm_passes_ab": ab,
                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
-                    "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['_source']})", "traffic": None,
+                    "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['_source']})", "traffic": conv_traffic(),
                     "conv_ms_per_step": conv_ms, "unet_ms_per_step_serialised": unet_ms,
                     "share_of_unet": conv_ms / unet_ms if unet_ms else None,
                     "ms_by_kernel_kind": {k2: round(v, 4) for k2, v in sorted(by_kind.items())},
