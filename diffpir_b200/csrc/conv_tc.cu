@@ -778,7 +778,8 @@ __global__ void __launch_bounds__(FUSE ? V4_THREADS : V2_THREADS, 1) k_conv3x3_v
     tma_prefetch_desc(&tmB);
     if (g.skip_chunks) { tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmB2); }
     // FUSE: a stage is full once the TMA bytes (weights) have landed AND the 8 producer warps have published the operand
-    for (int s = 0; s < V2_STAGES; ++s) { mbar_init(&full[s], FUSE ? 9 : 1); mbar_init(&empty[s], 1); }
+    // (FUSE == 3: 9 producer warps)
+    for (int s = 0; s < V2_STAGES; ++s) { mbar_init(&full[s], FUSE == 3 ? 10 : (FUSE ? 9 : 1)); mbar_init(&empty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 8); }
     for (int a = 0; a < 16; ++a) mbar_init(&res_full[a], 1);
     tma_prefetch_desc(&tmOut);
@@ -786,7 +787,8 @@ __global__ void __launch_bounds__(FUSE ? V4_THREADS : V2_THREADS, 1) k_conv3x3_v
     fence_barrier_init();
     fence_proxy_async();
   }
-  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  constexpr int MMA_WARP = FUSE == 3 ? 18 : 1;      // also owns the TMEM allocation
+  if (warp == MMA_WARP) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -981,6 +983,109 @@ __global__ void __launch_bounds__(FUSE ? V4_THREADS : V2_THREADS, 1) k_conv3x3_v
       }
     }
   };
+  auto role_producer_once = [&]() {
+    // ---------------------------------------------------------------- v5 operand producers (FUSE == 3; 9 warps, 288 threads)
+    // EXPERIMENTAL - compiles, not yet validated on hardware, not selected by default (dpir_set_gn_fusion(3)).
+    // k_conv3x3_v3<1> activates every input element once per horizontal tap box: 3 x 18/16 = 3.4 times.  Here a thread owns a
+    // column X of the 18-wide halo (instead of a column of one 16-wide box), a channel octet j and every second row (rg):
+    // 18 x 8 x 2 = 288 threads x 9 units.  The 9 raw units of a 64-channel chunk are loaded once, activated once in place,
+    // and kept in registers across the chunk's three stages: for tap column dx the thread stores them at box column
+    // xx = X - dx (threads whose xx falls outside [0,16) skip that stage's stores).  The loads of the NEXT chunk are issued
+    // after the dx = 2 stage has been published (never in flight at a proxy fence = MEMBAR.ALL.CTA); the producers then run
+    // up to two cheap stages ahead of the tensor core, which leaves ~2 MMA stages for load latency + activation.
+    const int t = (int)threadIdx.x - 8 * 32;      // 0..287
+    const int j = t & 7, Xl = t >> 3;             // Xl 0..35
+    const int X = Xl % 18, rg = Xl / 18;
+    const int Ctot = gf.C1 + gf.C2;
+    uint4 buf[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) buf[i] = make_uint4(0u, 0u, 0u, 0u);
+    uint32_t mask = 0, lmask = 0;          // validity of the units in buf / of the tile being loaded
+    int ln = 0;
+    int64_t lbase = 0;                     // pixel index of (n, h0 - 1 + rg, w0 - 1 + X) of the tile being loaded
+    auto load_tile = [&](int tile) {
+      int h0, w0, co0;
+      decode(tile, ln, h0, w0, co0);
+      lmask = 0;
+      if ((unsigned)(w0 - 1 + X) < (unsigned)g.W) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) lmask |= ((unsigned)(h0 - 1 + rg + 2 * i) < (unsigned)g.H) ? (1u << i) : 0u;
+      }
+      if (g.dbg & 32) lmask = 0u;
+      lbase = ((int64_t)ln * g.H + (h0 - 1 + rg)) * g.W + (w0 - 1 + X);
+    };
+    auto issue = [&](int ch) {             // raw units of chunk ch of the tile described by (lbase, lmask)
+      const int c = ch * TC_BK + j * 8;
+      const __half *ptr;
+      int64_t rs;
+      if (c < gf.C1) { ptr = gf.src1 + lbase * gf.C1 + c; rs = (int64_t)2 * g.W * gf.C1; }
+      else { ptr = gf.src2 + lbase * gf.C2 + (c - gf.C1); rs = (int64_t)2 * g.W * gf.C2; }
+#pragma unroll
+      for (int i = 0; i < 9; ++i) {
+        if (lmask & (1u << i)) buf[i] = __ldg(reinterpret_cast<const uint4 *>(ptr));
+        ptr += rs;
+      }
+    };
+    int tile = blockIdx.x;
+    if (tile < g.total_tiles) {
+      load_tile(tile);
+      issue(0);
+    }
+    uint32_t it = 0;
+    for (; tile < g.total_tiles; tile += gridDim.x) {
+      const int n = ln;
+      mask = lmask;
+      for (int k = 0; k < num_k; ++k, ++it) {
+        const int s = it % V2_STAGES;
+        const uint32_t ph = (it / V2_STAGES) & 1u;
+        if (k >= num_main) {               // fused 1x1-skip stage: operand comes by TMA, only keep the barrier count
+          mbar_wait(&empty[s], ph ^ 1u);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&full[s]);
+          continue;
+        }
+        const int ch = k / 3, dx = k - ch * 3;
+        if (dx == 0 && !(g.dbg & 64)) {    // new chunk: activate the 9 units in place (needs no pipeline slot)
+          const float *cf = gf.coef + (int64_t)n * 2 * Ctot + ch * TC_BK + j * 8;
+          const float4 a0 = __ldg(reinterpret_cast<const float4 *>(cf)), a1 = __ldg(reinterpret_cast<const float4 *>(cf + 4));
+          const float4 b0 = __ldg(reinterpret_cast<const float4 *>(cf + Ctot)), b1 = __ldg(reinterpret_cast<const float4 *>(cf + Ctot + 4));
+          const float hs[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+          const float ho[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+          for (int i = 0; i < 9; ++i) {
+            uint32_t w[4] = {buf[i].x, buf[i].y, buf[i].z, buf[i].w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&w[q]));
+              const float ha = fmaf(f.x, hs[2 * q], ho[2 * q]), hb = fmaf(f.y, hs[2 * q + 1], ho[2 * q + 1]);
+              const __half2 r = __floats2half2_rn(fmaf(ha, tanh_approx_f(ha), ha), fmaf(hb, tanh_approx_f(hb), hb));
+              w[q] = *reinterpret_cast<const uint32_t *>(&r);
+            }
+            const bool ok = (mask >> i) & 1u;              // outside the image: the conv pads the ACTIVATED tensor with zeros
+            buf[i] = make_uint4(ok ? w[0] : 0u, ok ? w[1] : 0u, ok ? w[2] : 0u, ok ? w[3] : 0u);
+          }
+        }
+        mbar_wait(&empty[s], ph ^ 1u);
+        const int xx = X - dx;
+        if ((unsigned)xx < 16u) {
+          uint8_t *dst = smem + s * V2_STAGE_BYTES + (rg * 2048 + xx * 128 + ((j ^ (xx & 7)) << 4));
+#pragma unroll
+          for (int i = 0; i < 9; ++i) *reinterpret_cast<uint4 *>(dst + i * 4096) = buf[i];
+        }
+        if (!(g.dbg & 128)) fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full[s]);
+        if (dx == 2) {                     // the chunk is published three times: fetch the next one into the same registers
+          if (ch + 1 < chunks) {
+            issue(ch + 1);
+          } else if (tile + (int)gridDim.x < g.total_tiles) {
+            load_tile(tile + (int)gridDim.x);
+            issue(0);
+          }
+        }
+      }
+    }
+  };
   auto role_epilogue = [&](const int ew) {
     // ---------------------------------------------------------------- epilogue: lane = output channel, column = pixel
     // fp16 in / fp16 out only (the fp16-stream pipeline).  The epilogue is bound by per-warp instruction latency (ncu: ~6
@@ -1086,7 +1191,19 @@ __global__ void __launch_bounds__(FUSE ? V4_THREADS : V2_THREADS, 1) k_conv3x3_v
     }
     if (lane == 0) tma_store_wait_all0();      // all tensor stores of this warp have landed before the CTA retires
   };
-  if constexpr (FUSE != 0) {
+  if constexpr (FUSE == 3) {
+    // v5 layout: warpgroups 0-1 = epilogue (120 registers), warpgroups 2-4 = 9 producer warps + TMA warp + MMA warp + one
+    // idle warp (80 registers): 2*128*120 + 3*128*80 = 640*96
+    if (warp < 8) {
+      setmaxnreg_inc<120>();
+      role_epilogue(warp);
+    } else {
+      setmaxnreg_dec<80>();
+      if (warp < 17) role_producer_once();
+      else if (warp == 17) role_tma();
+      else if (warp == 18) role_mma();
+    }
+  } else if constexpr (FUSE != 0) {
     // setmaxnreg is executed once per warpgroup, at the top of the branch that dominates all of that group's code
     if (warp < 4) {
       setmaxnreg_dec<32>();
@@ -1106,7 +1223,7 @@ __global__ void __launch_bounds__(FUSE ? V4_THREADS : V2_THREADS, 1) k_conv3x3_v
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<512>(tmem_base);
+  if (warp == MMA_WARP) tmem_dealloc<512>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -1128,7 +1245,8 @@ struct ConvTcPlan {
 
 static int g_force_v1 = 0;   // dpir_conv_tc_variant: 0 = auto (persistent swap-AB v3), 1 = v1 everywhere, 2 = persistent v2
 static int g_num_sms = 0;
-static int g_gnfuse_math = 1; // fused-operand kernel arithmetic: 1 = fp32 (as k_gn_apply), 2 = packed half (tanh.approx.f16x2)
+static int g_gnfuse_math = 1; // fused-operand kernel: 1 = fp32 arithmetic (as k_gn_apply), 2 = packed half (tanh.approx.f16x2),
+                              // 3 = experimental activate-once-per-chunk producers (k_conv3x3_v3<3>, not validated on hardware)
 
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
@@ -1304,7 +1422,7 @@ static int launch_tc_impl(const ConvTcPlan *p, const ConvTcGeom &g, const ConvEp
 void conv_tc_force_v1(int on) { g_force_v1 = on; }
 bool conv_tc_v2_enabled() { return g_force_v1 != 1; }
 bool conv_tc_swapab_enabled() { return g_force_v1 == 0; }
-void conv_tc_set_gnfuse_math(int m) { g_gnfuse_math = m == 2 ? 2 : 1; }
+void conv_tc_set_gnfuse_math(int m) { g_gnfuse_math = (m == 2 || m == 3) ? m : 1; }
 
 int launch_conv_tc(const ConvTcPlan *p, const ConvEpi &epi, int Cout, cudaStream_t st) {
   DPIR_REQUIRE(Cout <= p->CoutPad, "conv_tc: Cout exceeds padded weight rows");
@@ -1316,6 +1434,7 @@ int launch_conv_tc(const ConvTcPlan *p, const ConvEpi &epi, int Cout, cudaStream
       DPIR_CUDA_CHECK(cudaFuncSetAttribute(k_conv3x3_v3<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM));
       DPIR_CUDA_CHECK(cudaFuncSetAttribute(k_conv3x3_v3<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM));
       DPIR_CUDA_CHECK(cudaFuncSetAttribute(k_conv3x3_v3<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM));
+      DPIR_CUDA_CHECK(cudaFuncSetAttribute(k_conv3x3_v3<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM));
       int dev = 0;
       DPIR_CUDA_CHECK(cudaGetDevice(&dev));
       DPIR_CUDA_CHECK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -1332,7 +1451,9 @@ int launch_conv_tc(const ConvTcPlan *p, const ConvEpi &epi, int Cout, cudaStream
     DPIR_REQUIRE(v3_ok || (!p->gf.coef && g2.skip_chunks_a == g2.skip_chunks),
                  "conv_tc: GroupNorm / concat-skip fusion planned for a conv the swap-AB kernel cannot run");
     if (v3_ok && p->gf.coef) {
-      if (g_gnfuse_math == 2)
+      if (g_gnfuse_math == 3)
+        k_conv3x3_v3<3><<<grid, V4_THREADS, V3_SMEM, st>>>(p->tmA, p->tmB, p->tmA2, p->tmA2b, p->tmB2, p->tmOut, p->tmRes, g2, epi, p->gf);
+      else if (g_gnfuse_math == 2)
         k_conv3x3_v3<2><<<grid, V4_THREADS, V3_SMEM, st>>>(p->tmA, p->tmB, p->tmA2, p->tmA2b, p->tmB2, p->tmOut, p->tmRes, g2, epi, p->gf);
       else
         k_conv3x3_v3<1><<<grid, V4_THREADS, V3_SMEM, st>>>(p->tmA, p->tmB, p->tmA2, p->tmA2b, p->tmB2, p->tmOut, p->tmRes, g2, epi, p->gf);

@@ -1170,7 +1170,8 @@ int dpir_conv_tc_f16io(const void *act, const void *w, const float *bias, const 
  * (no k_gn_apply pass, fp16s pipeline only), fp32 operand arithmetic; 2: the same with packed-half arithmetic; 0: every norm
  * is a separate pass.  Cached plans of `e` are dropped. */
 int dpir_set_gn_fusion(dpir_engine *e, int32_t enable) {
-  DPIR_REQUIRE(enable >= 0 && enable <= 2, "dpir_set_gn_fusion: 0 = off, 1 = on (fp32 operand arithmetic), 2 = on (packed half)");
+  DPIR_REQUIRE(enable >= 0 && enable <= 3,
+               "dpir_set_gn_fusion: 0 = off, 1 = on (fp32 operand arithmetic), 2 = on (packed half), 3 = experimental v5 producers");
   g_gn_fuse = enable ? 1 : 0;
   if (enable) conv_tc_set_gnfuse_math(enable);
   if (e) { cudaDeviceSynchronize(); e->plans.clear(); }

@@ -241,7 +241,9 @@ int dpir_conv_gnfuse_f16io(const void *src1, int32_t C1, const void *src2, int32
                            int32_t Cout, int32_t CoutPad, void *stream);
 /* 1 (default): eligible ResBlocks of the fp16s pipeline run GroupNorm+SiLU inside their convolutions (above) with fp32
  * operand arithmetic (bit-identical activation values to the separate pass); 2: packed-half arithmetic (tanh.approx.f16x2);
- * 0: every norm is a separate k_gn_apply pass.  Process-wide; drops the cached plans of `e` (may be NULL). */
+ * 0: every norm is a separate k_gn_apply pass; 3: EXPERIMENTAL producers that activate each element once per 64-channel chunk
+ * (k_conv3x3_v3<3>; builds, not yet validated on hardware, never selected by default).  Process-wide; drops the cached plans
+ * of `e` (may be NULL). */
 int dpir_set_gn_fusion(dpir_engine *e, int32_t enable);
 /* A/B switch for tests and benchmarks.  0 (default): 3x3 convs on >=16x16 maps use the persistent swap-AB halo-reuse
  * kernel (k_conv3x3_v3), everything else the one-tile-per-CTA kernel (k_conv_tc); 1: k_conv_tc everywhere;
