@@ -8,6 +8,7 @@ What gets rebound (attributes are resolved at call time because the drivers bind
     utils.utils_sisr.pre_calculate / data_solution            -> diffpir_b200.utils_sisr
     utils.utils_model.model_fn / test_mode / find_nearest     -> diffpir_b200.utils_model
     utils.utils_resizer.Resizer                                -> diffpir_b200.utils_resizer.Resizer
+    utils.utils_inpaint.mask_generator                         -> diffpir_b200.utils_inpaint.mask_generator (same numpy draws)
     guided_diffusion.script_util.create_model_and_diffusion   -> returns (diffpir_b200.UNetModel, reference SpacedDiffusion)
 `create_model_and_diffusion` is imported by name in the drivers (main_ddpir.py:31-36), so install() must run before
 the driver module is imported.  uninstall() restores everything.
@@ -38,6 +39,12 @@ def install(precision="fp16", graph=True):
     _patch(ref_model, "test_mode", um.test_mode)
     _patch(ref_model, "find_nearest", um.find_nearest)
     _patch(ref_resizer, "Resizer", ur.Resizer)
+    try:        # data edges (host logic with the reference's numpy draws; utils_inpaint pulls in matplotlib through utils_image)
+        from . import utils_inpaint as ui
+        ref_inpaint = importlib.import_module("utils.utils_inpaint")
+        _patch(ref_inpaint, "mask_generator", ui.mask_generator)
+    except ImportError:
+        pass
     ref_create = _saved.get((ref_script.__name__, "create_model_and_diffusion"), (None, ref_script.create_model_and_diffusion))[1]
 
     def create_model_and_diffusion(**kw):

@@ -195,6 +195,63 @@ def resizer_forward(x, scale):
     return x
 
 
+def _matlab_cubic(x):
+    """utils/utils_image.py:672-677."""
+    ax = torch.abs(x)
+    ax2, ax3 = ax ** 2, ax ** 3
+    return (1.5 * ax3 - 2.5 * ax2 + 1) * (ax <= 1).type_as(ax) + \
+        (-0.5 * ax3 + 2.5 * ax2 - 4 * ax + 2) * ((ax > 1) * (ax <= 2)).type_as(ax)
+
+
+def imresize_weights_indices(in_length, out_length, scale, kernel_width=4, antialiasing=True):
+    """MATLAB-style bicubic taps, utils/utils_image.py:680-731 (calculate_weights_indices): float32 torch arithmetic as there.
+    Returns (weights [out, taps], first index into the symmetric-padded signal [out], sym_len_start, sym_len_end).
+    Note :721-726: the leading column is dropped when it contains ANY zero weight, and after that the trailing column is
+    only dropped if the leading one was not (the second narrow is then a no-op) - restated as is."""
+    if scale < 1 and antialiasing:
+        kernel_width = kernel_width / scale
+    x = torch.linspace(1, out_length, out_length)
+    u = x / scale + 0.5 * (1 - 1 / scale)
+    left = torch.floor(u - kernel_width / 2)
+    P = math.ceil(kernel_width) + 2
+    indices = left.view(out_length, 1).expand(out_length, P) + torch.linspace(0, P - 1, P).view(1, P).expand(out_length, P)
+    dist = u.view(out_length, 1).expand(out_length, P) - indices
+    weights = scale * _matlab_cubic(dist * scale) if (scale < 1 and antialiasing) else _matlab_cubic(dist)
+    weights = weights / torch.sum(weights, 1).view(out_length, 1).expand(out_length, P)
+    zeros = torch.sum((weights == 0), 0)
+    if int(zeros[0]) != 0:
+        indices = indices.narrow(1, 1, P - 2)
+        weights = weights.narrow(1, 1, P - 2)
+    if int(zeros[-1]) != 0:
+        indices = indices.narrow(1, 0, P - 2)
+        weights = weights.narrow(1, 0, P - 2)
+    sym_s = int(-indices.min() + 1)
+    sym_e = int(indices.max() - in_length)
+    first = (indices[:, 0] + sym_s - 1).long()
+    return weights.contiguous(), first, sym_s, sym_e
+
+
+def imresize_np(img, scale, antialiasing=True):
+    """utils/utils_image.py:811-881 on an (H,W,C) or (H,W) float array: symmetric padding, H pass, then W pass."""
+    x = torch.from_numpy(np.asarray(img, dtype=np.float32))
+    squeeze = x.dim() == 2
+    if squeeze:
+        x = x[:, :, None]
+    H, W, C = x.shape
+    oH, oW = math.ceil(H * scale), math.ceil(W * scale)
+
+    def one_axis(t, n_in, n_out):            # resize along dim 0 of (n_in, M)
+        w, first, ss, se = imresize_weights_indices(n_in, n_out, scale, 4, antialiasing)
+        aug = torch.cat([t[:ss].flip(0), t, t[n_in - se:].flip(0) if se > 0 else t[:0]], 0)
+        kw = w.shape[1]
+        return torch.stack([(aug[int(first[i]):int(first[i]) + kw] * w[i].view(kw, 1)).sum(0) for i in range(n_out)], 0)
+
+    y = one_axis(x.reshape(H, W * C), H, oH).reshape(oH, W, C)
+    y = one_axis(y.permute(1, 0, 2).reshape(W, oH * C), W, oW).reshape(oW, oH, C).permute(1, 0, 2)
+    y = y.contiguous().numpy()
+    return y[:, :, 0] if squeeze else y
+
+
 def ibp_step(x0, y, sf, gamma, rho, in_iter=1):
     """main_ddpir.py:401-406: x0 in [-1,1]; y in [0,1] at low resolution;
     up_sample = F.interpolate(scale_factor=sf) (default mode = nearest, :297)."""

@@ -233,7 +233,25 @@ def gen_test_mode():
     return res
 
 
-FILES = {"test_mode.npz": gen_test_mode, "unet_small.npz": gen_unet_small, "unet_ffhq.npz": gen_unet_ffhq, "sisr.npz": gen_sisr,
+def gen_imresize():
+    """utils_image.imresize_np (the SR measurement of main_ddpir.py:89 / main_ddpir_sisr.py:202) on small seeded images."""
+    ref_shim.install()
+    from utils import utils_image as util
+    rng = np.random.RandomState(5)
+    res = {}
+    a = rng.rand(48, 40, 3).astype(np.float32)
+    b = rng.rand(37, 52).astype(np.float32)          # odd sizes, single channel
+    res["a"], res["b"] = a, b
+    for sf in (2, 3, 4):
+        res[f"a_down{sf}"] = util.imresize_np(a.copy(), 1 / sf)
+    res["a_up2"] = util.imresize_np(a.copy(), 2)
+    res["b_down2"] = util.imresize_np(b.copy(), 1 / 2)
+    res["a_up3_noaa"] = util.imresize_np(a.copy(), 3, antialiasing=False)
+    # (a zero-length symmetric pad - e.g. b at 1/4 without antialiasing - raises inside the reference itself, :870)
+    return res
+
+
+FILES = {"imresize.npz": gen_imresize, "test_mode.npz": gen_test_mode, "unet_small.npz": gen_unet_small, "unet_ffhq.npz": gen_unet_ffhq, "sisr.npz": gen_sisr,
          "misc.npz": gen_misc, "loops.npz": gen_loops}
 
 

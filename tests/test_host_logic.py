@@ -105,3 +105,51 @@ def test_find_nearest_and_model_fn_argument_errors():
     with pytest.raises(RuntimeError):
         utils_model.model_fn(torch.zeros(1, 3, 8, 8), 10.0, model_diffusion=object(), model_out_type="pred_x_prev",
                              diffusion=None, alphas_cumprod=torch.linspace(0.99, 0.01, 1000))
+
+
+def test_mask_generator_matches_reference_goldens():
+    """diffpir_b200.utils_inpaint.mask_generator draws from the global numpy stream in the reference's order: bit-exact
+    against masks produced by the unmodified utils.utils_inpaint.mask_generator (tests/golden/misc.npz, oracle/gen_golden.py)."""
+    import os
+    from diffpir_b200.utils_inpaint import mask_generator
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "misc.npz"))
+    img = torch.zeros(1, 3, 64, 64)
+    np.random.seed(123)
+    m = mask_generator("random", mask_prob_range=(0.5, 0.5), image_size=64)(img)
+    assert m.shape == img.shape and m.dtype == torch.float32
+    assert np.array_equal(m.numpy().astype(np.uint8), g["mask_random"])
+    assert int((m[0, 0] == 0).sum()) == 64 * 64 // 2
+    np.random.seed(123)
+    b = mask_generator("box", mask_len_range=(16, 17), image_size=64, margin=(4, 4))(img)
+    assert np.array_equal(b.numpy().astype(np.uint8), g["mask_box"])
+    np.random.seed(123)
+    e = mask_generator("extreme", mask_len_range=(16, 17), image_size=64, margin=(4, 4))(img)
+    assert torch.equal(e, 1 - b)
+    assert set(torch.unique(m).tolist()) <= {0.0, 1.0}
+
+
+def test_imresize_tables_reproduce_reference_goldens():
+    """The gather tables diffpir_b200.utils_image.imresize_tables hands to the resize kernel, applied here with numpy, give
+    utils_image.imresize_np of the unmodified reference (tests/golden/imresize.npz) - including its symmetric padding."""
+    import os
+    from diffpir_b200.utils_image import imresize_tables
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "imresize.npz"))
+
+    def apply(x, scale, aa=True):
+        x = x if x.ndim == 3 else x[:, :, None]
+        H, W, _ = x.shape
+        wh, fh = imresize_tables(H, int(np.ceil(H * scale)), scale, aa)
+        ww, fw = imresize_tables(W, int(np.ceil(W * scale)), scale, aa)
+        y = np.einsum("to,tohc->ohc", wh, x[fh].astype(np.float32))                 # H pass first, as the reference
+        return np.einsum("to,htoc->hoc", ww, y[:, fw].astype(np.float32))
+    for key, scale, aa in (("a_down2", 1 / 2, True), ("a_down3", 1 / 3, True), ("a_down4", 1 / 4, True), ("a_up2", 2, True),
+                           ("b_down2", 1 / 2, True), ("a_up3_noaa", 3, False)):
+        src = g[key[0]]
+        out = apply(src, scale, aa)
+        ref = g[key] if g[key].ndim == 3 else g[key][:, :, None]
+        assert out.shape == ref.shape, key
+        assert np.abs(out - ref).max() < 2e-6, (key, np.abs(out - ref).max())
+        assert np.abs(orc.imresize_np(src, scale, aa).reshape(ref.shape) - ref).max() < 1e-6      # the oracle is pinned too
+    w, f = imresize_tables(256, 64, 0.25)
+    assert w.dtype == np.float32 and f.dtype == np.int32 and f.min() >= 0 and f.max() < 256
+    assert np.allclose(w.sum(0), 1, atol=1e-6)
