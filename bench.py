@@ -414,7 +414,8 @@ def main():
                                                  "with gn_fusion the ResBlock convs also evaluate GroupNorm+FiLM+SiLU on their operand)",
                     "separate_norm_passes_ab": ab,
                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
-                    "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['_source']})", "traffic": conv_traffic(),
+                    "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['_source']})",
+                    "traffic": (conv_traffic() or {}).get("dram_bytes_per_launch"), "traffic_detail": conv_traffic(),
                     "conv_ms_per_step": conv_ms, "unet_ms_per_step_serialised": unet_ms,
                     "share_of_unet": conv_ms / unet_ms if unet_ms else None,
                     "ms_by_kernel_kind": {k2: round(v, 4) for k2, v in sorted(by_kind.items())},

@@ -17,6 +17,14 @@
 //   warps 2-5 = epilogue (tcgen05.ld 32x32b -> registers -> bias / residual / NCHW / eps->x0 -> global).
 // * STAGES-deep smem ring with full/empty mbarriers; MMA completion releases a stage via tcgen05.commit.
 //   Two CTAs fit per SM (3 x 32 KB stages, 128 TMEM columns each) so one CTA's epilogue overlaps the other's main loop.
+//
+// Kernels in this file (all share the TMA / SWIZZLE_128B / tcgen05 scheme above; DESIGN.md section 4 has the measurements):
+//   k_conv_tc<BN,STAGES>    one 128-pixel x BN-cout tile per CTA: 1x1 convs, 8x8 maps, the 128->6 output conv (eps->x0 epilogue)
+//   k_conv3x3_v2            persistent halo-reuse 3x3 kernel, pixels on M (A/B variant, dpir_conv_tc_variant(2))
+//   k_conv3x3_v3<0>         persistent swap-AB 3x3 kernel (couts on M, 256 pixels on N), TMA-store epilogue: the default for
+//                           3x3 convs on >=16x16 maps in the fp16-stream pipeline
+//   k_conv3x3_v3<1|2>       the same with the preceding GroupNorm(+FiLM)+SiLU applied to the activation operand by 8 producer
+//                           warps ("v4", default for eligible ResBlocks); <3> is an unvalidated activate-once variant
 #include "unet_kernels.cuh"
 
 #include <cstdlib>

@@ -238,7 +238,6 @@ __device__ __forceinline__ float4 gn_act(float4 v, float mean, float rstd, float
 }
 
 constexpr int GN_APPLY_PIX = 256;  // work pixels per block
-constexpr int GN_UNROLL = 4;
 
 // MODE none: one work pixel = one pixel.  MODE down: work pixel = output pixel (reads 2x2 inputs, averages the
 // ACTIVATED values as unet.py:238-241 does: in_rest(x) then h_upd).  MODE up: work pixel = input pixel, written 2x2.
