@@ -60,3 +60,13 @@ def test_product_does_not_import_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), fn
+
+
+def test_shipped_library_matches_sources():
+    """The in-tree .so is the one the committed sources build (sha256 stamp written by diffpir_b200.build; file times do not
+    survive the copy to the GPU box, and two ranks importing at once must not both rebuild - build() takes a file lock)."""
+    from diffpir_b200 import _lib, build
+    _lib.load()
+    assert os.path.exists(build.LIB) and os.path.exists(build.STAMP)
+    assert not build.needs_build()
+    assert open(build.STAMP).read().strip() == build._source_hash()
