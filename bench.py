@@ -201,8 +201,9 @@ def workload_config(B, precision):
 
 
 # ----------------------------------------------------------------------------------------------- cpu baseline leg
-def cpu_baseline_sample():
-    """~10-30 s of the oracle's CPU evaluation of the same step, rank 0 / N=1 only."""
+def cpu_baseline_sample(keep=None):
+    """~10-30 s of the oracle's CPU evaluation of the same step, rank 0 / N=1 only.  With `keep` (a dict) the inputs, the
+    pre-drawn noise and the result of the short trajectory are recorded so that parity_sample() can replay it on the GPU."""
     from oracle import diffpir_oracle as orc
     from oracle import unet_oracle
     cores = host_cores()
@@ -214,19 +215,58 @@ def cpu_baseline_sample():
     sched = orc.driver_schedule()
     tabs = orc.diffusion_tables()
     FBt = orc.pre_calculate(y, k, 1)
-    x = torch.randn(B, 3, SIZE, SIZE, generator=torch.Generator().manual_seed(0))
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(B, 3, SIZE, SIZE, generator=g)
+    noises = [torch.randn(B, 3, SIZE, SIZE, generator=g) for _ in range(nsteps)]
+    x_init = x.clone()
     vec_t = torch.tensor([500] * B)
     with torch.no_grad():
         unet_oracle.unet_forward(sd, cfg.as_dict(), x, vec_t)      # warm-up
         t0 = time.perf_counter()
-        for _ in range(nsteps):
+        for i in range(nsteps):
             x0 = orc.pred_xstart(unet_oracle.unet_forward(sd, cfg.as_dict(), x, vec_t), x, vec_t, tabs)
             x0 = orc.data_solution(x0 / 2 + 0.5, *FBt, torch.tensor(0.01).view(1, 1, 1, 1), 1) * 2 - 1
-            x = orc.renoise(x, x0, 500, 480, sched, 0.0, ZETA, torch.zeros_like(x), torch.randn_like(x))
+            x = orc.renoise(x, x0, 500, 480, sched, 0.0, ZETA, torch.zeros_like(x), noises[i])
         dt = (time.perf_counter() - t0) / nsteps
+    if keep is not None:
+        keep.update(y=y, k=k, x_init=x_init, noises=noises, x_final=x, x0_last=x0, t_i=500, t_im1=480, rho=0.01, nsteps=nsteps)
     return {"value": B / (NFE * dt), "unit": "images/s", "cores": cores, "kind": "port",
             "sample": f"{nsteps} loop steps of B={B} image (FFHQ UNet + FFT prox + re-noise) with the CPU oracle on {cores} threads, "
                       f"scaled to 100 NFE ({dt:.2f} s/step)"}
+
+
+def parity_sample(model, keep, dev):
+    """The trajectory cpu_baseline_sample() just computed on the CPU (fp32 oracle), replayed through the product path on the
+    GPU with the same weights, measurement, start and pre-drawn noise: the "PSNR vs ref" half of the metric on a bounded
+    sample.  Never allowed to take the bench line down: any failure is reported in the result."""
+    try:
+        from diffpir_b200 import ops, utils_sisr
+        from diffpir_b200.sampler import driver_schedule
+        s = driver_schedule()
+        sa, s1 = s["sqrt_alphas_cumprod"], s["sqrt_1m_alphas_cumprod"]
+        t_i, t_im1 = keep["t_i"], keep["t_im1"]
+        c_eps = float(np.sqrt(1 - ZETA) * s1[t_im1])            # eta = 0
+        c_zeta = float(np.sqrt(ZETA) * s1[t_im1])
+        y, k = keep["y"].to(dev), keep["k"].to(dev)
+        FB, _, F2B, FBFy = utils_sisr.pre_calculate(y, k, 1)
+        x = keep["x_init"].to(dev).clone()
+        x0 = torch.empty_like(x)
+        spec = torch.empty(3 * SIZE * (SIZE // 2 + 1) * 2, device=dev, dtype=torch.float32)
+        t = torch.full((1,), t_i, device=dev, dtype=torch.int64)
+        for i in range(keep["nsteps"]):
+            model.x0(x, t, out=x0)
+            utils_sisr.data_solution_fused(x0, FB, F2B, FBFy, keep["rho"], 1, 0.5, 0.5, 2.0, -1.0, 1.0, out=x0, spec=spec)
+            ops.renoise(x, x0, keep["noises"][i].to(dev), float(sa[t_i]), float(s1[t_i]), float(sa[t_im1]), c_eps, c_zeta, out=x)
+        torch.cuda.synchronize()
+        xg, x0g = x.cpu().double(), x0.cpu().double()
+        xr, x0r = keep["x_final"].double(), keep["x0_last"].double()
+        mse = float((((x0g - x0r) / 2) ** 2).mean())               # images in [0,1]
+        return {"what": f"{keep['nsteps']}-step trajectory (UNet -> FFT prox -> re-noise at t={t_i}) of one 256x256 image, "
+                        f"GPU product path vs the fp32 CPU oracle, identical weights / measurement / noise",
+                "rel_l2_x": float((xg - xr).norm() / xr.norm()), "rel_l2_x0": float((x0g - x0r).norm() / x0r.norm()),
+                "psnr_db_gpu_vs_oracle_x0": float(10 * np.log10(1.0 / max(mse, 1e-30)))}
+    except Exception as exc:        # noqa: BLE001 - reported, not raised
+        return {"error": f"{type(exc).__name__}: {exc}"}
 
 
 # ----------------------------------------------------------------------------------------------- GPU arm
@@ -452,14 +492,16 @@ def main():
                 "share_of_step": (ms_fft + ms_rn) / ms_step}
 
     if rank == 0:
-        cpu = None if (args.no_cpu_baseline or world > 1) else cpu_baseline_sample()
+        keep = {}
+        cpu = None if (args.no_cpu_baseline or world > 1) else cpu_baseline_sample(keep)
+        parity = parity_sample(model, keep, dev) if keep else None
         line = {"metric": "images/sec @100-NFE 256x256 deblur", "value": value, "unit": "images/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "f16",
                 "data": "synthetic", "config": workload_config(B, args.precision),
                 "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": 2 * img_bytes,
                         "d2h_bytes_per_step": img_bytes, "ms_per_step": ms_e2e},
-                "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_prox": prox, "cpu_baseline": cpu,
+                "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_prox": prox, "cpu_baseline": cpu, "parity_sample": parity,
                 "weight_broadcast_ms": t_bcast_ms, "graph": not args.no_graph, "gn_fusion": args.gn_fusion}
         print(json.dumps(line))
     if dist is not None:
