@@ -1,5 +1,6 @@
 """Per-kernel parity of the two convolution kernels (tcgen05 fp16 and CUDA-core fp32) through the C-ABI."""
 import ctypes
+import os
 
 import pytest
 import torch
@@ -163,7 +164,12 @@ def _quad_stats(xh):
     return torch.stack([v.sum(dim=(1, 3)), (v * v).sum(dim=(1, 3))], dim=-1).contiguous()
 
 
-@pytest.mark.parametrize("math", ["1", "2"])
+# "3" = k_conv3x3_v3<3> (activate-once producers): written in round 1, not yet validated on hardware, never the default;
+# DPIR_TEST_EXPERIMENTAL=1 adds it to the parity runs
+_FUSE_MODES = ["1", "2"] + (["3"] if os.environ.get("DPIR_TEST_EXPERIMENTAL") == "1" else [])
+
+
+@pytest.mark.parametrize("math", _FUSE_MODES)
 @pytest.mark.parametrize("B,H,W,C1,C2,Cout,residual,film", [
     (2, 32, 32, 128, 0, 128, True, True),       # norm2 -> conv2 with FiLM and residual
     (3, 64, 64, 128, 0, 256, False, False),     # two cout tiles
@@ -213,4 +219,4 @@ def test_conv_gn_fused_matches_torch(B, H, W, C1, C2, Cout, residual, film, math
     got = out.permute(0, 3, 1, 2).float()
     assert not torch.isnan(got).any()
     # fp16 rounding of the activated operand (+ of the stored result); packed-half arithmetic (math 2) rounds twice more
-    assert rel_l2(got, ref) < (1.2e-3 if math == "1" else 3e-3)
+    assert rel_l2(got, ref) < (3e-3 if math == "2" else 1.2e-3)

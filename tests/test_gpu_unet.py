@@ -1,4 +1,6 @@
 """UNet engine parity against the CPU oracle (oracle/unet_oracle.py) on seeded synthetic weights."""
+import os
+
 import pytest
 import torch
 
@@ -124,7 +126,7 @@ def test_imagenet_unet_forward_matches_oracle():
         del m
 
 
-@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("mode", [1, 2] + ([3] if os.environ.get("DPIR_TEST_EXPERIMENTAL") == "1" else []))
 def test_gn_fusion_equivalence(mode):
     """fp16s: ResBlock GroupNorm+SiLU evaluated inside the convolutions (v4 kernel) vs as separate passes - same network, the
     only difference is where the activated operand is rounded to fp16 (mode 1: identical arithmetic) -> agreement far inside
@@ -144,7 +146,7 @@ def test_gn_fusion_equivalence(mode):
         assert any(r["gn_fused"] for r in rows), "no convolution took the fused-operand path"
         ea, eb, eab = rel_l2(a, ref), rel_l2(b, ref), rel_l2(b, a)
         print(f"gn fusion mode {mode}: separate {ea:.3e} fused {eb:.3e} fused-vs-separate {eab:.3e}")
-        assert ea < TOL["fp16s"] and eb < TOL["fp16s"] * (1 if mode == 1 else 1.5)
+        assert ea < TOL["fp16s"] and eb < TOL["fp16s"] * (1.5 if mode == 2 else 1)
         # not bit-identical: the two routes round ~1 in 10^3 activations to neighbouring fp16 values and the difference
         # propagates through ~25 chained layers like any other fp16 rounding noise (measured 1.2e-3)
         assert eab < 4e-3
