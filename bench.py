@@ -281,8 +281,9 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-steps", type=int, default=3)
-    ap.add_argument("--gn-fusion", type=int, default=1, choices=[0, 1, 2],
-                    help="ResBlock GroupNorm+SiLU inside the convolutions: 1 (default, fp32 operand arithmetic), 2 (packed half), 0 separate passes")
+    ap.add_argument("--gn-fusion", type=int, default=1, choices=[0, 1, 2, 4],
+                    help="ResBlock GroupNorm+SiLU inside the convolutions: 1 (default, activate-once producers), 4 (round-1 per-tap "
+                         "producers), 2 (per-tap packed half), 0 separate passes")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libdiffpir_b200.so")
 PRECISION_FP32 = 0
 PRECISION_FP16 = 1
 PRECISION_FP16S = 2
+PRECISION_FP16X3 = 3
 
 
 class UNetConfigC(ctypes.Structure):
@@ -51,11 +52,19 @@ SIGNATURES = {
                                    c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dpir_fft_solve": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int32, c_int32, c_int32,
                                  c_int32, c_float, c_float, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p]),
+    "dpir_fft_solve_dev": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
+                                     c_int32, c_float, c_float, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p]),
+    "dpir_inpaint_prox_dev": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_float, c_void_p, c_int64,
+                                        c_void_p]),
+    "dpir_ibp_update_dev": (c_int32, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int32, c_int32, c_int32, c_int32,
+                                      c_void_p, c_void_p]),
     "dpir_inpaint_prox": (c_int32, [c_void_p, c_void_p, c_void_p, c_float, c_float, c_float, c_float, c_void_p, c_int64,
                                     c_void_p]),
     "dpir_renoise": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_float, c_float, c_float,
                                c_float, c_void_p, c_int64, c_void_p]),
     "dpir_eps_to_x0": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    "dpir_sample_step": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_int32, c_int32,
+                                   c_int32, c_int32, c_int32, c_void_p]),
     "dpir_affine": (c_int32, [c_void_p, c_float, c_float, c_void_p, c_int64, c_void_p]),
     "dpir_resize_separable": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_int32,
                                         c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
@@ -98,9 +107,19 @@ def load(build_if_missing=True):
         if stale:
             try:
                 _build.build()
-            except Exception as exc:  # no nvcc on the box: use the shipped .so if there is one
+            except Exception as exc:
+                # no nvcc on this box.  A shipped library may only be used when its stamp matches the sources (a stale binary
+                # bound with the current ctypes SIGNATURES gives silent wrong results); DPIR_ALLOW_STALE_LIB=1 overrides.
                 if not os.path.exists(LIB_PATH):
                     raise RuntimeError(f"libdiffpir_b200.so is missing and could not be built: {exc}") from exc
+                if os.environ.get("DPIR_ALLOW_STALE_LIB") != "1":
+                    raise RuntimeError(
+                        f"libdiffpir_b200.so does not match the sources (stamp {_build.stamp_hash()} vs sources "
+                        f"{_build.source_hash()}) and could not be rebuilt: {exc}; set DPIR_ALLOW_STALE_LIB=1 to load it anyway"
+                    ) from exc
+                import warnings
+                warnings.warn(f"diffpir_b200: loading a STALE libdiffpir_b200.so (stamp {_build.stamp_hash()} vs sources "
+                              f"{_build.source_hash()}): {exc}")
     if not os.path.exists(LIB_PATH):
         raise RuntimeError(f"{LIB_PATH} not found: run `python -m diffpir_b200.build` (there is no CPU fallback)")
     lib = ctypes.CDLL(LIB_PATH)
@@ -125,6 +144,19 @@ def require_cuda(*tensors):
     for t in tensors:
         if t is not None and not t.is_cuda:
             raise RuntimeError("diffpir_b200: tensors must live on the GPU (no CPU fallback)")
+
+
+def device_scalar(v, device):
+    """A scalar argument that lives on the GPU (the reference drivers pass `rhos[t_i]` as a CUDA tensor, main_ddpir.py:389):
+    returns a 1-element contiguous fp32 CUDA tensor whose pointer the *_dev entry points read inside the kernel - no
+    .item(), no host synchronisation.  Host numbers / CPU tensors return None (the caller passes them by value)."""
+    import torch
+    if torch.is_tensor(v) and v.is_cuda:
+        v = v.reshape(-1)[:1]
+        if v.dtype != torch.float32:
+            v = v.float()
+        return v.contiguous()
+    return None
 
 
 def ptr(t):

@@ -30,6 +30,17 @@ def _source_hash():
     return h.hexdigest()
 
 
+def source_hash():
+    return _source_hash()[:16]
+
+
+def stamp_hash():
+    try:
+        return open(STAMP).read().strip()[:16]
+    except OSError:
+        return "<none>"
+
+
 def needs_build():
     if not os.path.exists(LIB):
         return True

@@ -115,6 +115,12 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *m, uin
       : "memory");
 }
 
+// L2 prefetch of a tensor box (no shared-memory destination): warms the lines the operand producers are about to read
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap *m, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap *m, const void *src, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
                    reinterpret_cast<uint64_t>(m)),
@@ -189,6 +195,7 @@ constexpr int TC_THREADS = 192;
 
 struct ConvTcGeom {
   int B, H, W, Cin, Cout, taps, ksize;
+  int a_wrap;                 // split-precision: K chunk ch reads activation chunk (ch >= a_wrap ? ch - a_wrap : ch); else INT_MAX
   int TW, TH, TN;             // M-tile box (TW*TH*TN == 128)
   int tiles_w, tiles_h, tiles_n;
 };
@@ -233,6 +240,7 @@ __device__ __forceinline__ void epi_nhwc_chunk32(const ConvEpi &epi, const ConvT
 #pragma unroll
   for (int j = 0; j < 8; ++j) { qs[j] = 0.f; qq[j] = 0.f; }
   if (valid) {
+    const float sc = epi.acc_scale ? __ldg(epi.acc_scale) : 1.f;
     const int64_t pix = ((int64_t)n * g.H + yh) * g.W + xw;
     const float *rs = (epi.residual && !epi.res_half) ? epi.residual + pix * g.Cout + co : nullptr;
     const __half *rsh = (epi.residual && epi.res_half) ? reinterpret_cast<const __half *>(epi.residual) + pix * g.Cout + co : nullptr;
@@ -245,8 +253,8 @@ __device__ __forceinline__ void epi_nhwc_chunk32(const ConvEpi &epi, const ConvT
           float4 c4 = __ldg(reinterpret_cast<const float4 *>(epi.bias2 + co + j));
           b4.x += c4.x; b4.y += c4.y; b4.z += c4.z; b4.w += c4.w;
         }
-        v[j] = __uint_as_float(r[j]) + b4.x; v[j + 1] = __uint_as_float(r[j + 1]) + b4.y;
-        v[j + 2] = __uint_as_float(r[j + 2]) + b4.z; v[j + 3] = __uint_as_float(r[j + 3]) + b4.w;
+        v[j] = fmaf(__uint_as_float(r[j]), sc, b4.x); v[j + 1] = fmaf(__uint_as_float(r[j + 1]), sc, b4.y);
+        v[j + 2] = fmaf(__uint_as_float(r[j + 2]), sc, b4.z); v[j + 3] = fmaf(__uint_as_float(r[j + 3]), sc, b4.w);
         if (rs) {
           float4 rv = *reinterpret_cast<const float4 *>(rs + j);
           v[j] += rv.x; v[j + 1] += rv.y; v[j + 2] += rv.z; v[j + 3] += rv.w;
@@ -334,7 +342,8 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(const __grid_constant__ 
         const int dy = tap / g.ksize - pad, dx = tap % g.ksize - pad;
         uint8_t *sa = smem + s * STAGE_BYTES;
         mbar_expect_tx(&full[s], STAGE_BYTES);
-        tma_load_4d(sa, &tmA, &full[s], ch * TC_BK, w0 + dx, h0 + dy, n0);
+        const int ach = ch >= g.a_wrap ? ch - g.a_wrap : ch;
+        tma_load_4d(sa, &tmA, &full[s], ach * TC_BK, w0 + dx, h0 + dy, n0);
         tma_load_3d(sa + TC_A_BYTES, &tmB, &full[s], ch * TC_BK, co0, tap);
       }
     }
@@ -430,10 +439,20 @@ constexpr int V4_THREADS = 640;
 constexpr int V2_STG_BYTES = 8 * 4096;                // per-epilogue-warp 32 x 128 B transpose buffers
 constexpr int V2_SMEM = V2_STAGES * V2_STAGE_BYTES + V2_STG_BYTES + 1024 + 256;
 constexpr int V3_STG_BYTES = 8 * 6144;                // v3: per-epilogue-warp fp16 tiles OUT, RES0, RES1 (2 KB each)
-constexpr int V3_SMEM = V2_STAGES * V2_STAGE_BYTES + V3_STG_BYTES + 1024 + 512;
+// v3 pipeline: the activation operand and the weights live in SEPARATE rings.  An activation slot is one (64-channel chunk, dx)
+// halo box (36 KB, read by the three dy taps); a weight slot is one tap tile (128 couts x 64 k, 16 KB).  Three activation slots
+// hold all three dx copies of a chunk, so the activate-once producers (FUSE == 3) publish a whole chunk back to back and have
+// the tensor core's entire chunk time (3 x 12 MMAs) to fetch and activate the next one; with the fused 2-stage ring of round 1
+// the load latency of every chunk was exposed (profiles/r02_conv_ring_experiments.md).
+constexpr int V3_A_SLOTS = 3;
+constexpr int V3_W_SLOTS = 4;
+constexpr int V3_W_BYTES = 128 * 128;                 // one tap: 128 couts x 64 fp16
+constexpr int V3_RING_BYTES = V3_A_SLOTS * V2_A_BYTES + V3_W_SLOTS * V3_W_BYTES;     // 176,128 B
+constexpr int V3_SMEM = V3_RING_BYTES + V3_STG_BYTES + 1024 + 512;
 
 struct ConvV2Geom {
   int B, H, W, Cin, Cout;
+  int a_wrap;                         // split-precision K-chunk -> activation-chunk wrap (see ConvTcGeom), INT_MAX otherwise
   int skip_chunks;                    // extra K chunks of a fused 1x1 convolution on a second operand (ResBlock skip), or 0
   int skip_chunks_a;                  // of which the first skip_chunks_a come from tmA2, the rest from tmA2b (concat skip input)
   int dbg;                            // timing diagnostics only (env DPIR_CONV_DEBUG): 1 = no epilogue memory traffic,
@@ -441,6 +460,9 @@ struct ConvV2Geom {
                                       // arithmetic, 128 = no proxy fence; results are garbage when non-zero
   int tiles_w, tiles_h, n_tiles;      // 16x16 pixel tiles per image, Cout/128 column tiles
   int total_tiles;                    // B * tiles_h * tiles_w * n_tiles
+  int a_slots, w_slots, w_taps;       // v3 rings: activation halo boxes (36 KB each) and weight slots of w_taps taps (16 KB per tap);
+                                      // a_slots*36 KB + w_slots*w_taps*16 KB <= V3_RING_BYTES
+  int pf_dist;                        // fused kernels: L2 prefetch distance of the raw operand in 64-channel chunks (0 = off)
 };
 
 __device__ __forceinline__ float tanh_approx_f(float x) {
@@ -523,8 +545,9 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_conv3x3_v2(const __grid_const
           uint8_t *sa = smem + s * V2_STAGE_BYTES;
           if (k < num_main) {
             const int ch = k / 3, dx = k - ch * 3;
+            const int ach = ch >= g.a_wrap ? ch - g.a_wrap : ch;
             mbar_expect_tx(&full[s], V2_STAGE_BYTES);
-            tma_load_4d(sa, &tmA, &full[s], ch * TC_BK, w0 + dx - 1, h0 - 1, n);
+            tma_load_4d(sa, &tmA, &full[s], ach * TC_BK, w0 + dx - 1, h0 - 1, n);
 #pragma unroll
             for (int dy = 0; dy < 3; ++dy)
               tma_load_3d(sa + V2_A_BYTES + dy * (128 * 128), &tmB, &full[s], ch * TC_BK, co0, dy * 3 + dx);
@@ -579,6 +602,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_conv3x3_v2(const __grid_const
     const int sub = ew >> 2;              // which 128-row sub-tile
     float4 *stg = reinterpret_cast<float4 *>(stg_base + ew * 4096);
     const int tr = lane >> 3, tcn = lane & 7;     // transposed role: row (4i + tr), 16-byte column tcn
+    const float acc_sc = epi.acc_scale ? __ldg(epi.acc_scale) : 1.f;      // split-precision weight scale (fp32-output path only)
     uint32_t tc = 0;
     for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++tc) {
       const uint32_t ab = tc & 1u, aph = (tc >> 1) & 1u;
@@ -627,8 +651,8 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_conv3x3_v2(const __grid_const
               float4 c4 = __ldg(reinterpret_cast<const float4 *>(epi.bias2 + co + 4 * j));
               b4.x += c4.x; b4.y += c4.y; b4.z += c4.z; b4.w += c4.w;
             }
-            float4 v4 = make_float4(__uint_as_float(r[4 * j]) + b4.x, __uint_as_float(r[4 * j + 1]) + b4.y,
-                                    __uint_as_float(r[4 * j + 2]) + b4.z, __uint_as_float(r[4 * j + 3]) + b4.w);
+            float4 v4 = make_float4(fmaf(__uint_as_float(r[4 * j]), acc_sc, b4.x), fmaf(__uint_as_float(r[4 * j + 1]), acc_sc, b4.y),
+                                    fmaf(__uint_as_float(r[4 * j + 2]), acc_sc, b4.z), fmaf(__uint_as_float(r[4 * j + 3]), acc_sc, b4.w));
             if (epi.residual) { v4.x += res[j].x; v4.y += res[j].y; v4.z += res[j].z; v4.w += res[j].w; }
             qs[j] = my_ok ? (v4.x + v4.y) + (v4.z + v4.w) : 0.f;
             qq[j] = my_ok ? (v4.x * v4.x + v4.y * v4.y) + (v4.z * v4.z + v4.w * v4.w) : 0.f;
@@ -757,6 +781,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_conv3x3_v2(const __grid_const
 // MMA issue and the epilogue are unchanged.
 template <int FUSE>
 __global__ void __launch_bounds__(FUSE ? V4_THREADS : V2_THREADS, 1) k_conv3x3_v3(const __grid_constant__ CUtensorMap tmA,
+                                                               const __grid_constant__ CUtensorMap tmAb,
                                                                const __grid_constant__ CUtensorMap tmB,
                                                                const __grid_constant__ CUtensorMap tmA2,
                                                                const __grid_constant__ CUtensorMap tmA2b,
@@ -768,10 +793,15 @@ __global__ void __launch_bounds__(FUSE ? V4_THREADS : V2_THREADS, 1) k_conv3x3_v
   constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t *stg_base = smem + V2_STAGES * V2_STAGE_BYTES;     // per epilogue warp: OUT, RES0, RES1 (2 KB each)
-  uint64_t *full = reinterpret_cast<uint64_t *>(stg_base + V3_STG_BYTES);
-  uint64_t *empty = full + V2_STAGES;
-  uint64_t *tmem_full = empty + V2_STAGES;     // [2]
+  uint8_t *a_ring = smem;                                    // [A_SL][V2_A_BYTES]  activation halo boxes
+  const int A_SL = g.a_slots, W_SL = g.w_slots;              // ring depths (runtime: tuned per kernel flavour)
+  uint8_t *w_ring = smem + A_SL * V2_A_BYTES;                // [W_SL][w_taps * V3_W_BYTES]  weight tap tiles
+  uint8_t *stg_base = smem + V3_RING_BYTES;                  // per epilogue warp: OUT, RES0, RES1 (2 KB each)
+  uint64_t *a_full = reinterpret_cast<uint64_t *>(stg_base + V3_STG_BYTES);
+  uint64_t *a_empty = a_full + 4;              // up to 4 activation slots
+  uint64_t *w_full = a_empty + 4;
+  uint64_t *w_empty = w_full + 8;              // up to 8 weight slots
+  uint64_t *tmem_full = w_empty + 8;           // [2]
   uint64_t *tmem_empty = tmem_full + 2;        // [2]
   uint64_t *res_full = tmem_empty + 2;         // [8 warps][2 buffers]
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(res_full + 16);
@@ -785,9 +815,10 @@ __global__ void __launch_bounds__(FUSE ? V4_THREADS : V2_THREADS, 1) k_conv3x3_v
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (g.skip_chunks) { tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmB2); }
-    // FUSE: a stage is full once the TMA bytes (weights) have landed AND the 8 producer warps have published the operand
-    // (FUSE == 3: 9 producer warps)
-    for (int s = 0; s < V2_STAGES; ++s) { mbar_init(&full[s], FUSE == 3 ? 10 : (FUSE ? 9 : 1)); mbar_init(&empty[s], 1); }
+    // an activation slot is full once the TMA thread has arrived (expect_tx + bytes when the operand comes by TMA: plain kernel
+    // and fused 1x1-skip stages) AND, in the fused kernels, the 8 (FUSE 1|2) / 9 (FUSE 3) producer warps have published it
+    for (int s = 0; s < A_SL; ++s) { mbar_init(&a_full[s], FUSE == 3 ? 10 : (FUSE ? 9 : 1)); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < W_SL; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 8); }
     for (int a = 0; a < 16; ++a) mbar_init(&res_full[a], 1);
     tma_prefetch_desc(&tmOut);
@@ -812,31 +843,63 @@ __global__ void __launch_bounds__(FUSE ? V4_THREADS : V2_THREADS, 1) k_conv3x3_v
   };
 
   // warp roles as lambdas: the two thread layouts (v3: 10 warps; v4: 5 warpgroups with re-balanced registers) share them
+  // Ring bookkeeping shared by all roles: every (chunk, dx) stage and every fused-skip chunk consumes ONE activation slot
+  // (counter ia), every tap ONE weight slot (counter iw); all roles walk the same static tile list in the same order.
+  // Ring bookkeeping shared by all roles: every (chunk, dx) stage and every fused-skip chunk consumes ONE activation slot
+  // (counter ia); the weights of a stage take 3 / W_TP weight slots (counter iw; a fused-skip chunk takes one); all roles walk
+  // the same static tile list in the same order.
+  const int W_TP = g.w_taps;
+  const int W_SLOT_BYTES = W_TP * V3_W_BYTES;
   auto role_tma = [&]() {
     if (lane == 0) {
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+      uint32_t ia = 0, iw = 0;
+      auto load_w = [&](const CUtensorMap *tm, int c0, int co0, int tap0, int ntap, int tap_stride) {
+        const int s = iw % W_SL;
+        mbar_wait(&w_empty[s], ((iw / W_SL) & 1u) ^ 1u);
+        mbar_expect_tx(&w_full[s], ntap * V3_W_BYTES);
+        for (int j = 0; j < ntap; ++j)
+          tma_load_3d(w_ring + s * W_SLOT_BYTES + j * V3_W_BYTES, tm, &w_full[s], c0, co0, tap0 + j * tap_stride);
+        ++iw;
+      };
+      // fused kernels: the producers read the raw operand with ordinary global loads whose latency sits on their critical
+      // path (load -> activate -> publish); an L2 prefetch of the 18 x 18 halo box `pf_dist` chunks ahead turns it into an
+      // L2 hit.  tmA / tmAb describe the one or two raw sources (virtual concat) with a {64 ch, 18 px, 18 rows} box.
+      uint32_t tile_it = 0;
+      auto prefetch_raw = [&](uint32_t lin) {
+        const uint32_t ti = lin / (uint32_t)chunks, ch = lin - ti * (uint32_t)chunks;
+        const int64_t tl = (int64_t)blockIdx.x + (int64_t)ti * gridDim.x;
+        if (tl >= g.total_tiles) return;
+        int n, h0, w0, co0;
+        decode((int)tl, n, h0, w0, co0);
+        const int c = (int)ch * TC_BK;
+        if (c < gf.C1) tma_prefetch_4d(&tmA, c, w0 - 1, h0 - 1, n);
+        else tma_prefetch_4d(&tmAb, c - gf.C1, w0 - 1, h0 - 1, n);
+      };
+      if (FUSE && g.pf_dist > 0)
+        for (int i = 1; i < g.pf_dist; ++i) prefetch_raw((uint32_t)i);
+      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++tile_it) {
         int n, h0, w0, co0;
         decode(tile, n, h0, w0, co0);
-        for (int k = 0; k < num_k; ++k, ++it) {
-          const int s = it % V2_STAGES;
-          const uint32_t ph = (it / V2_STAGES) & 1u;
-          mbar_wait(&empty[s], ph ^ 1u);
-          uint8_t *sa = smem + s * V2_STAGE_BYTES;
-          if (g.dbg & 4) { mbar_arrive(&full[s]); continue; }
+        for (int k = 0; k < num_k; ++k, ++ia) {
+          const int s = ia % A_SL;
+          mbar_wait(&a_empty[s], ((ia / A_SL) & 1u) ^ 1u);
+          uint8_t *sa = a_ring + s * V2_A_BYTES;
           if (k < num_main) {
             const int ch = k / 3, dx = k - ch * 3;
-            mbar_expect_tx(&full[s], FUSE ? V2_B_BYTES : V2_STAGE_BYTES);
-            if (!FUSE) tma_load_4d(sa, &tmA, &full[s], ch * TC_BK, w0 + dx - 1, h0 - 1, n);
-#pragma unroll
-            for (int dy = 0; dy < 3; ++dy)
-              tma_load_3d(sa + V2_A_BYTES + dy * (128 * 128), &tmB, &full[s], ch * TC_BK, co0, dy * 3 + dx);
+            if (FUSE) {
+              mbar_arrive(&a_full[s]);           // the operand is written by the producer warps
+              if (dx == 0 && g.pf_dist > 0) prefetch_raw(tile_it * (uint32_t)chunks + (uint32_t)ch + (uint32_t)g.pf_dist);
+            } else {
+              mbar_expect_tx(&a_full[s], V2_A_BYTES);
+              tma_load_4d(sa, &tmA, &a_full[s], ch * TC_BK, w0 + dx - 1, h0 - 1, n);
+            }
+            for (int dy = 0; dy < 3; dy += W_TP) load_w(&tmB, ch * TC_BK, co0, dy * 3 + dx, W_TP, 3);
           } else {
             const int ch = k - num_main;
-            mbar_expect_tx(&full[s], V2_A_BYTES + 128 * 128);
-            if (ch < g.skip_chunks_a) tma_load_4d(sa, &tmA2, &full[s], ch * TC_BK, w0, h0 - 1, n);
-            else tma_load_4d(sa, &tmA2b, &full[s], (ch - g.skip_chunks_a) * TC_BK, w0, h0 - 1, n);
-            tma_load_3d(sa + V2_A_BYTES + 1 * (128 * 128), &tmB2, &full[s], ch * TC_BK, co0, 0);
+            mbar_expect_tx(&a_full[s], V2_A_BYTES);
+            if (ch < g.skip_chunks_a) tma_load_4d(sa, &tmA2, &a_full[s], ch * TC_BK, w0, h0 - 1, n);
+            else tma_load_4d(sa, &tmA2b, &a_full[s], (ch - g.skip_chunks_a) * TC_BK, w0, h0 - 1, n);
+            load_w(&tmB2, ch * TC_BK, co0, 0, 1, 0);
           }
         }
       }
@@ -844,27 +907,35 @@ __global__ void __launch_bounds__(FUSE ? V4_THREADS : V2_THREADS, 1) k_conv3x3_v
   };
   auto role_mma = [&]() {
     if (lane == 0) {
-      uint32_t it = 0, tc = 0;
+      uint32_t ia = 0, iw = 0, tc = 0;
       for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++tc) {
         const uint32_t ab = tc & 1u, aph = (tc >> 1) & 1u;
         mbar_wait(&tmem_empty[ab], aph ^ 1u);
         tc_fence_after();
         const uint32_t d = tmem_base + ab * 256u;
-        for (int k = 0; k < num_k; ++k, ++it) {
-          const int s = it % V2_STAGES;
-          const uint32_t ph = (it / V2_STAGES) & 1u;
-          mbar_wait(&full[s], ph);
+        for (int k = 0; k < num_k; ++k, ++ia) {
+          const int s = ia % A_SL;
+          mbar_wait(&a_full[s], (ia / A_SL) & 1u);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + s * V2_STAGE_BYTES);
-          const int dy_lo = k < num_main ? 0 : 1, dy_hi = k < num_main ? 3 : 2;
-          for (int dy = dy_lo; dy < dy_hi && !(g.dbg & 2); ++dy) {
-            const uint64_t wdesc = make_sw128_desc(sa + V2_A_BYTES + dy * (128 * 128));   // A operand: 128 couts x 64 k
-            const uint64_t pdesc = make_sw128_desc(sa + (uint32_t)(dy * 16 * 128));       // B operand: 256 pixels x 64 k
+          const uint32_t sa = smem_u32(a_ring + s * V2_A_BYTES);
+          const bool main_stage = k < num_main;
+          const int dy_lo = main_stage ? 0 : 1, dy_hi = main_stage ? 3 : 2;
+          for (int dy = dy_lo; dy < dy_hi; ++iw) {
+            const int ws = iw % W_SL;
+            mbar_wait(&w_full[ws], (iw / W_SL) & 1u);
+            tc_fence_after();
+            const int nt = main_stage ? W_TP : 1;
+            for (int j = 0; j < nt; ++j, ++dy) {
+              if (g.dbg & 2) continue;
+              const uint64_t wdesc = make_sw128_desc(smem_u32(w_ring + ws * W_SLOT_BYTES + j * V3_W_BYTES));   // A: 128 couts x 64 k
+              const uint64_t pdesc = make_sw128_desc(sa + (uint32_t)(dy * 16 * 128));                          // B: 256 pixels x 64 k
 #pragma unroll
-            for (int kk = 0; kk < TC_BK / 16; ++kk)
-              umma_f16(d, wdesc + (uint64_t)(2 * kk), pdesc + (uint64_t)(2 * kk), IDESC, (k | (dy - dy_lo) | kk) ? 1u : 0u);
+              for (int kk = 0; kk < TC_BK / 16; ++kk)
+                umma_f16(d, wdesc + (uint64_t)(2 * kk), pdesc + (uint64_t)(2 * kk), IDESC, (k | (dy - dy_lo) | kk) ? 1u : 0u);
+            }
+            umma_commit(&w_empty[ws]);
           }
-          umma_commit(&empty[s]);
+          umma_commit(&a_empty[s]);
         }
         umma_commit(&tmem_full[ab]);
       }
@@ -946,12 +1017,12 @@ __global__ void __launch_bounds__(FUSE ? V4_THREADS : V2_THREADS, 1) k_conv3x3_v
     for (; tile < g.total_tiles; tile += gridDim.x) {
       const int n = ln;                   // image of the tile being transformed (the loader moves on during its last stage)
       for (int k = 0; k < num_k; ++k, ++it) {
-        const int s = it % V2_STAGES;
-        const uint32_t ph = (it / V2_STAGES) & 1u;
+        const int s = it % A_SL;
+        const uint32_t ph = (it / A_SL) & 1u;
         if (k >= num_main) {               // fused 1x1-skip stage: operand comes by TMA, only keep the barrier count
-          mbar_wait(&empty[s], ph ^ 1u);
+          mbar_wait(&a_empty[s], ph ^ 1u);
           __syncwarp();
-          if (lane == 0) mbar_arrive(&full[s]);
+          if (lane == 0) mbar_arrive(&a_full[s]);
           continue;
         }
         const int ch = k / 3;
@@ -962,8 +1033,8 @@ __global__ void __launch_bounds__(FUSE ? V4_THREADS : V2_THREADS, 1) k_conv3x3_v
           hs[0] = a0.x; hs[1] = a0.y; hs[2] = a0.z; hs[3] = a0.w; hs[4] = a1.x; hs[5] = a1.y; hs[6] = a1.z; hs[7] = a1.w;
           ho[0] = b0.x; ho[1] = b0.y; ho[2] = b0.z; ho[3] = b0.w; ho[4] = b1.x; ho[5] = b1.y; ho[6] = b1.z; ho[7] = b1.w;
         }
-        mbar_wait(&empty[s], ph ^ 1u);
-        uint8_t *dst = smem + s * V2_STAGE_BYTES + dst_off;
+        mbar_wait(&a_empty[s], ph ^ 1u);
+        uint8_t *dst = a_ring + s * V2_A_BYTES + dst_off;
         if (g.dbg & 64) {                   // timing diagnostic: raw copy, no arithmetic
 #pragma unroll
           for (int i = 0; i < 9; ++i) *reinterpret_cast<uint4 *>(dst + i * 4096) = buf[i];
@@ -980,7 +1051,7 @@ __global__ void __launch_bounds__(FUSE ? V4_THREADS : V2_THREADS, 1) k_conv3x3_v
         }
         if (!(g.dbg & 128)) fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
         __syncwarp();
-        if (lane == 0) mbar_arrive(&full[s]);
+        if (lane == 0) mbar_arrive(&a_full[s]);
         // the next main stage (same tile, or the first stage of this CTA's next tile)
         if (k + 1 < num_main) {
           issue(k + 1);
@@ -1044,12 +1115,12 @@ __global__ void __launch_bounds__(FUSE ? V4_THREADS : V2_THREADS, 1) k_conv3x3_v
       const int n = ln;
       mask = lmask;
       for (int k = 0; k < num_k; ++k, ++it) {
-        const int s = it % V2_STAGES;
-        const uint32_t ph = (it / V2_STAGES) & 1u;
+        const int s = it % A_SL;
+        const uint32_t ph = (it / A_SL) & 1u;
         if (k >= num_main) {               // fused 1x1-skip stage: operand comes by TMA, only keep the barrier count
-          mbar_wait(&empty[s], ph ^ 1u);
+          mbar_wait(&a_empty[s], ph ^ 1u);
           __syncwarp();
-          if (lane == 0) mbar_arrive(&full[s]);
+          if (lane == 0) mbar_arrive(&a_full[s]);
           continue;
         }
         const int ch = k / 3, dx = k - ch * 3;
@@ -1073,16 +1144,16 @@ __global__ void __launch_bounds__(FUSE ? V4_THREADS : V2_THREADS, 1) k_conv3x3_v
             buf[i] = make_uint4(ok ? w[0] : 0u, ok ? w[1] : 0u, ok ? w[2] : 0u, ok ? w[3] : 0u);
           }
         }
-        mbar_wait(&empty[s], ph ^ 1u);
+        mbar_wait(&a_empty[s], ph ^ 1u);
         const int xx = X - dx;
         if ((unsigned)xx < 16u) {
-          uint8_t *dst = smem + s * V2_STAGE_BYTES + (rg * 2048 + xx * 128 + ((j ^ (xx & 7)) << 4));
+          uint8_t *dst = a_ring + s * V2_A_BYTES + (rg * 2048 + xx * 128 + ((j ^ (xx & 7)) << 4));
 #pragma unroll
           for (int i = 0; i < 9; ++i) *reinterpret_cast<uint4 *>(dst + i * 4096) = buf[i];
         }
         if (!(g.dbg & 128)) fence_proxy_async();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&full[s]);
+        if (lane == 0) mbar_arrive(&a_full[s]);
         if (dx == 2) {                     // the chunk is published three times: fetch the next one into the same registers
           if (ch + 1 < chunks) {
             issue(ch + 1);
@@ -1239,12 +1310,15 @@ struct ConvTcPlan {
   CUtensorMap tmA, tmB;
   ConvTcGeom g;
   int BN, CoutPad;
+  bool split = false;     // split-precision operands ([hi | lo] activations, [hi | hi | lo] weights)
   bool v2 = false;        // persistent 3x3 kernel (k_conv3x3_v2 / k_conv3x3_v3)
   bool use_v3 = true;     // swap-AB variant
   ConvV2Geom g2;
   CUtensorMap tmA2, tmB2; // fused 1x1 skip operand / weights (v2 only; copies of tmA/tmB when unused)
   CUtensorMap tmA2b;      // second source of a concatenated skip operand (v3/v4)
+  CUtensorMap tmAb;       // fused kernels: raw source 2 of the virtual concat (L2 prefetch boxes); tmA then describes source 1
   GnFuse gf{};            // v4: fused GroupNorm+SiLU on the activation operand (gf.coef != null)
+  int gf_math = 3;        // producer flavour of the fused kernel (k_conv3x3_v3<gf_math>): 3 activate-once, 1 per-tap fp32, 2 per-tap half
   CUtensorMap tmOut, tmRes;   // v3: fp16 output / residual tensors for the TMA-store epilogue
   bool io_half = false;       // tmOut (and tmRes when has_res) are valid
   bool has_res = false;
@@ -1252,9 +1326,16 @@ struct ConvTcPlan {
 };
 
 static int g_force_v1 = 0;   // dpir_conv_tc_variant: 0 = auto (persistent swap-AB v3), 1 = v1 everywhere, 2 = persistent v2
-static int g_num_sms = 0;
-static int g_gnfuse_math = 1; // fused-operand kernel: 1 = fp32 arithmetic (as k_gn_apply), 2 = packed half (tanh.approx.f16x2),
-                              // 3 = experimental activate-once-per-chunk producers (k_conv3x3_v3<3>, not validated on hardware)
+// per-device launch state: cudaFuncSetAttribute and the SM count belong to a device, and one process may drive several
+struct DevState { bool attr_v1[3] = {false, false, false}; bool attr_v3 = false; int num_sms = 0; };
+static DevState g_dev[64];
+static DevState *dev_state() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+  return &g_dev[dev];
+}
+static int g_gnfuse_math = 3; // fused-operand kernel: 3 (default) = activate-once-per-chunk producers (k_conv3x3_v3<3>, fp32 arithmetic),
+                              // 1 = per-tap-box producers, fp32 arithmetic, 2 = the same with packed half (tanh.approx.f16x2)
 
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
@@ -1271,9 +1352,11 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 
 static int pow2_ge(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
-int conv_tc_plan_create(const void *act_half, const void *w_half, int B, int H, int W, int Cin, int CoutPad, int ksize,
-                        ConvTcPlan **out) {
-  DPIR_REQUIRE(Cin % TC_BK == 0, "conv_tc: Cin must be a multiple of 64 (got %d)", Cin);
+int conv_tc_plan_create(const void *act_half, const void *w_half, int B, int H, int W, int Cin_real, int CoutPad, int ksize,
+                        ConvTcPlan **out, int split) {
+  DPIR_REQUIRE(Cin_real % TC_BK == 0, "conv_tc: Cin must be a multiple of 64 (got %d)", Cin_real);
+  const int Cin = split ? 3 * Cin_real : Cin_real;          // K extent of the weights
+  const int Cact = split ? 2 * Cin_real : Cin_real;         // channels per pixel of the activation tensor ([hi | lo] when split)
   DPIR_REQUIRE(ksize == 1 || ksize == 3, "conv_tc: ksize must be 1 or 3");
   DPIR_REQUIRE(CoutPad == 16 || CoutPad % 128 == 0, "conv_tc: padded Cout must be 16 or a multiple of 128 (got %d)", CoutPad);
   DPIR_REQUIRE((((uintptr_t)act_half | (uintptr_t)w_half) & 15) == 0, "conv_tc: operands must be 16-byte aligned");
@@ -1282,6 +1365,8 @@ int conv_tc_plan_create(const void *act_half, const void *w_half, int B, int H, 
   ConvTcPlan *p = new ConvTcPlan();
   ConvTcGeom &g = p->g;
   g.B = B; g.H = H; g.W = W; g.Cin = Cin; g.Cout = 0; g.ksize = ksize; g.taps = ksize * ksize;
+  g.a_wrap = split ? Cact / TC_BK : 0x7fffffff;
+  p->split = split != 0;
   g.TW = W >= 128 ? 128 : pow2_ge(W);
   int th = 128 / g.TW;
   g.TH = th < pow2_ge(H) ? th : pow2_ge(H);
@@ -1296,12 +1381,14 @@ int conv_tc_plan_create(const void *act_half, const void *w_half, int B, int H, 
   if (p->v2) {
     ConvV2Geom &g2 = p->g2;
     g2.B = B; g2.H = H; g2.W = W; g2.Cin = Cin; g2.Cout = 0; g2.skip_chunks = 0; g2.skip_chunks_a = 0; g2.dbg = 0;
+    g2.a_wrap = g.a_wrap;
     g2.tiles_w = cdiv(W, 16); g2.tiles_h = cdiv(H, 16); g2.n_tiles = CoutPad / 128;
     g2.total_tiles = B * g2.tiles_w * g2.tiles_h * g2.n_tiles;
+    g2.a_slots = V3_A_SLOTS; g2.w_slots = V3_W_SLOTS; g2.w_taps = 1; g2.pf_dist = 0;
   }
   {
-    cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-    cuuint64_t gstr[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
+    cuuint64_t gdim[4] = {(cuuint64_t)Cact, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t gstr[3] = {(cuuint64_t)Cact * 2, (cuuint64_t)W * Cact * 2, (cuuint64_t)H * W * Cact * 2};
     cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)g.TW, (cuuint32_t)g.TH, (cuuint32_t)g.TN};
     if (p->v2) { box[1] = 16; box[2] = 18; box[3] = 1; }
     cuuint32_t estr[4] = {1, 1, 1, 1};
@@ -1322,6 +1409,7 @@ int conv_tc_plan_create(const void *act_half, const void *w_half, int B, int H, 
   }
   p->tmA2 = p->tmA;
   p->tmA2b = p->tmA;
+  p->tmAb = p->tmA;
   p->tmB2 = p->tmB;
   *out = p;
   return DPIR_OK;
@@ -1364,6 +1452,7 @@ int conv_tc_plan_set_io(ConvTcPlan *p, const void *out, int out_half, const void
 int conv_tc_plan_add_skip(ConvTcPlan *p, const void *act2_half, const void *w2_half, int Cin2a, const void *act2b_half,
                           int Cin2b) {
   DPIR_REQUIRE(p->v2, "conv_tc: skip fusion needs the persistent 3x3 kernel");
+  DPIR_REQUIRE(!p->split, "conv_tc: skip fusion is not available for split-precision operands");
   DPIR_REQUIRE(Cin2a % TC_BK == 0 && Cin2b % TC_BK == 0, "conv_tc: fused skip Cin must be a multiple of 64");
   DPIR_REQUIRE(!act2b_half || p->use_v3, "conv_tc: a concatenated skip operand needs the swap-AB kernel");
   auto encode = get_encode_fn();
@@ -1402,13 +1491,34 @@ int conv_tc_plan_add_skip(ConvTcPlan *p, const void *act2_half, const void *w2_h
 
 // v4: the activation operand is SiLU(GroupNorm(src)) computed inside the kernel from the raw fp16 source(s) and the
 // per-(image, channel) coefficient table of launch_gn_coef; needs the swap-AB kernel with its fp16 TMA-store epilogue
-int conv_tc_plan_set_gn_fuse(ConvTcPlan *p, const GnFuse &gf) {
-  DPIR_REQUIRE(p->v2 && p->use_v3, "conv_tc: GroupNorm fusion needs the persistent swap-AB 3x3 kernel");
+int conv_tc_plan_set_gn_fuse(ConvTcPlan *p, const GnFuse &gf, int math) {
+  p->gf_math = (math == 1 || math == 2) ? math : (math == 0 ? g_gnfuse_math : 3);
+  DPIR_REQUIRE(p->v2 && p->use_v3 && !p->split, "conv_tc: GroupNorm fusion needs the persistent swap-AB 3x3 kernel");
   DPIR_REQUIRE(gf.src1 && gf.coef && gf.C1 % TC_BK == 0 && gf.C2 % TC_BK == 0 && gf.C1 + gf.C2 == p->g2.Cin && (gf.C2 == 0 || gf.src2),
                "conv_tc: bad GroupNorm fusion operands (C1 %d, C2 %d, Cin %d)", gf.C1, gf.C2, p->g2.Cin);
   DPIR_REQUIRE((((uintptr_t)gf.src1 | (uintptr_t)gf.src2 | (uintptr_t)gf.coef) & 15) == 0, "conv_tc: fused operands must be 16-byte aligned");
   p->gf = gf;
-  return DPIR_OK;
+  // tensor maps of the raw source(s) for the L2 prefetch of the producers' 18 x 18 pixel halo box (the kernel's activation TMA
+  // map is unused when the operand is produced in-kernel)
+  auto encode = get_encode_fn();
+  if (!encode) { set_error("conv_tc: cuTensorMapEncodeTiled entry point unavailable"); return DPIR_E_CUDA; }
+  const ConvTcGeom &g = p->g;
+  auto make = [&](CUtensorMap *tm, const void *ptr, int C) -> int {
+    cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.B};
+    cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)g.W * C * 2, (cuuint64_t)g.H * g.W * C * 2};
+    cuuint32_t box[4] = {(cuuint32_t)TC_BK, 18, 18, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(ptr), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled(raw operand) failed: %d", (int)r); return DPIR_E_CUDA; }
+    return DPIR_OK;
+  };
+  int rc = make(&p->tmA, gf.src1, gf.C1);
+  if (rc) return rc;
+  p->tmAb = p->tmA;
+  if (gf.C2) rc = make(&p->tmAb, gf.src2, gf.C2);
+  return rc;
 }
 
 void conv_tc_plan_destroy(ConvTcPlan *p) { delete p; }
@@ -1416,7 +1526,7 @@ void conv_tc_plan_destroy(ConvTcPlan *p) { delete p; }
 template <int BN, int STAGES>
 static int launch_tc_impl(const ConvTcPlan *p, const ConvTcGeom &g, const ConvEpi &epi, cudaStream_t st) {
   constexpr int smem = STAGES * (TC_A_BYTES + BN * TC_BK * 2) + 1024 + 256;
-  static bool attr_set = false;
+  bool &attr_set = dev_state()->attr_v1[BN == 16 ? 0 : (BN == 64 ? 1 : 2)];
   if (!attr_set) {
     DPIR_CUDA_CHECK(cudaFuncSetAttribute(k_conv_tc<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
@@ -1430,13 +1540,14 @@ static int launch_tc_impl(const ConvTcPlan *p, const ConvTcGeom &g, const ConvEp
 void conv_tc_force_v1(int on) { g_force_v1 = on; }
 bool conv_tc_v2_enabled() { return g_force_v1 != 1; }
 bool conv_tc_swapab_enabled() { return g_force_v1 == 0; }
-void conv_tc_set_gnfuse_math(int m) { g_gnfuse_math = (m == 2 || m == 3) ? m : 1; }
+void conv_tc_set_gnfuse_math(int m) { g_gnfuse_math = (m == 1 || m == 2) ? m : 3; }   // default of the per-kernel test entry
 
 int launch_conv_tc(const ConvTcPlan *p, const ConvEpi &epi, int Cout, cudaStream_t st) {
   DPIR_REQUIRE(Cout <= p->CoutPad, "conv_tc: Cout exceeds padded weight rows");
   DPIR_REQUIRE(epi.mode != EPI_NHWC || Cout % 4 == 0, "conv_tc: NHWC epilogue needs Cout %% 4 == 0");
   if (p->v2 && epi.mode == EPI_NHWC) {
-    static bool attr_set = false;
+    DevState *ds = dev_state();
+    bool &attr_set = ds->attr_v3;
     if (!attr_set) {
       DPIR_CUDA_CHECK(cudaFuncSetAttribute(k_conv3x3_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, V2_SMEM));
       DPIR_CUDA_CHECK(cudaFuncSetAttribute(k_conv3x3_v3<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM));
@@ -1445,29 +1556,58 @@ int launch_conv_tc(const ConvTcPlan *p, const ConvEpi &epi, int Cout, cudaStream
       DPIR_CUDA_CHECK(cudaFuncSetAttribute(k_conv3x3_v3<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM));
       int dev = 0;
       DPIR_CUDA_CHECK(cudaGetDevice(&dev));
-      DPIR_CUDA_CHECK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+      DPIR_CUDA_CHECK(cudaDeviceGetAttribute(&ds->num_sms, cudaDevAttrMultiProcessorCount, dev));
       attr_set = true;
     }
+    const int g_num_sms = ds->num_sms;
     ConvV2Geom g2 = p->g2;
     g2.Cout = Cout;
     static int dbg = -1;
     if (dbg < 0) { const char *e = getenv("DPIR_CONV_DEBUG"); dbg = e ? atoi(e) : 0; }
     g2.dbg = dbg;
+    {
+      // ring shapes: the TMA-fed plain kernel keeps round 1's two (halo box + 3 taps) stages; the activate-once producers want a
+      // whole chunk (3 dx boxes) of activation slots, per-tap weight slots and an L2 prefetch of the raw operand two chunks ahead.
+      // DPIR_CONV_RING="a,w,t,af,wf,tf,pf" overrides (plain: a boxes, w slots of t taps; fused likewise; pf = prefetch distance).
+      static int ring[7] = {-1, 0, 0, 0, 0, 0, 0};
+      if (ring[0] < 0) {
+        int v[7] = {2, 2, 3, V3_A_SLOTS, V3_W_SLOTS, 1, 1};
+        const char *e = getenv("DPIR_CONV_RING");
+        if (e) {
+          int u[7] = {v[0], v[1], v[2], v[3], v[4], v[5], v[6]};
+          const int n = sscanf(e, "%d,%d,%d,%d,%d,%d,%d", &u[0], &u[1], &u[2], &u[3], &u[4], &u[5], &u[6]);
+          auto ok = [](int a, int w, int t) {
+            return a >= 2 && a <= 4 && w >= 2 && w <= 8 && (t == 1 || t == 3) && a * V2_A_BYTES + w * t * V3_W_BYTES <= V3_RING_BYTES;
+          };
+          if (n >= 3 && ok(u[0], u[1], u[2])) { v[0] = u[0]; v[1] = u[1]; v[2] = u[2]; }
+          if (n >= 6 && ok(u[3], u[4], u[5])) { v[3] = u[3]; v[4] = u[4]; v[5] = u[5]; }
+          if (n >= 7 && u[6] >= 0 && u[6] <= 8) v[6] = u[6];
+        }
+        for (int i = 1; i < 7; ++i) ring[i] = v[i];
+        ring[0] = v[0];
+      }
+      const bool fused = p->gf.coef != nullptr;
+      g2.a_slots = fused ? ring[3] : ring[0];
+      g2.w_slots = fused ? ring[4] : ring[1];
+      g2.w_taps = fused ? ring[5] : ring[2];
+      g2.pf_dist = fused ? ring[6] : 0;
+    }
     int grid = g2.total_tiles < g_num_sms ? g2.total_tiles : g_num_sms;
-    const bool v3_ok = p->use_v3 && p->io_half && epi.out_half && epi.out == p->io_out && epi.residual == p->io_res &&
+    const bool v3_ok = !p->split && p->use_v3 && p->io_half && epi.out_half && epi.out == p->io_out && epi.residual == p->io_res &&
                        (!epi.residual || epi.res_half);
     DPIR_REQUIRE(v3_ok || (!p->gf.coef && g2.skip_chunks_a == g2.skip_chunks),
                  "conv_tc: GroupNorm / concat-skip fusion planned for a conv the swap-AB kernel cannot run");
     if (v3_ok && p->gf.coef) {
-      if (g_gnfuse_math == 3)
-        k_conv3x3_v3<3><<<grid, V4_THREADS, V3_SMEM, st>>>(p->tmA, p->tmB, p->tmA2, p->tmA2b, p->tmB2, p->tmOut, p->tmRes, g2, epi, p->gf);
-      else if (g_gnfuse_math == 2)
-        k_conv3x3_v3<2><<<grid, V4_THREADS, V3_SMEM, st>>>(p->tmA, p->tmB, p->tmA2, p->tmA2b, p->tmB2, p->tmOut, p->tmRes, g2, epi, p->gf);
+      if (p->gf_math == 3)
+        k_conv3x3_v3<3><<<grid, V4_THREADS, V3_SMEM, st>>>(p->tmA, p->tmAb, p->tmB, p->tmA2, p->tmA2b, p->tmB2, p->tmOut, p->tmRes, g2, epi, p->gf);
+      else if (p->gf_math == 2)
+        k_conv3x3_v3<2><<<grid, V4_THREADS, V3_SMEM, st>>>(p->tmA, p->tmAb, p->tmB, p->tmA2, p->tmA2b, p->tmB2, p->tmOut, p->tmRes, g2, epi, p->gf);
       else
-        k_conv3x3_v3<1><<<grid, V4_THREADS, V3_SMEM, st>>>(p->tmA, p->tmB, p->tmA2, p->tmA2b, p->tmB2, p->tmOut, p->tmRes, g2, epi, p->gf);
+        k_conv3x3_v3<1><<<grid, V4_THREADS, V3_SMEM, st>>>(p->tmA, p->tmAb, p->tmB, p->tmA2, p->tmA2b, p->tmB2, p->tmOut, p->tmRes, g2, epi, p->gf);
     } else if (v3_ok) {
-      k_conv3x3_v3<0><<<grid, V2_THREADS, V3_SMEM, st>>>(p->tmA, p->tmB, p->tmA2, p->tmA2b, p->tmB2, p->tmOut, p->tmRes, g2, epi, p->gf);
+      k_conv3x3_v3<0><<<grid, V2_THREADS, V3_SMEM, st>>>(p->tmA, p->tmAb, p->tmB, p->tmA2, p->tmA2b, p->tmB2, p->tmOut, p->tmRes, g2, epi, p->gf);
     } else {
+      DPIR_REQUIRE(!p->split || !epi.out_half, "conv_tc: split-precision convolutions write fp32");
       DPIR_REQUIRE(!epi.residual || (epi.res_half != 0) == (epi.out_half != 0),
                    "conv_tc: the v2 persistent kernel needs residual and output of the same precision");
       k_conv3x3_v2<<<grid, V2_THREADS, V2_SMEM, st>>>(p->tmA, p->tmB, p->tmA2, p->tmB2, g2, epi);

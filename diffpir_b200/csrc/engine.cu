@@ -22,7 +22,6 @@ constexpr size_t ALIGN = 256;
 static inline size_t align_up(size_t v, size_t a = ALIGN) { return (v + a - 1) / a * a; }
 
 // ---------------------------------------------------------------------------------------------- structure
-static int g_gn_fuse = 1;    // dpir_set_gn_fusion: ResBlock GroupNorm+SiLU fused into the conv operand (v4 kernel) where eligible
 
 struct LayerDesc {
   int kind;  // 0 conv(stem), 1 res, 2 attn
@@ -39,10 +38,11 @@ struct ParamSlot {
   size_t bytes = 0;    // packed bytes
   int ldw = 0;         // padded Cout (fp32: %4, fp16: 16 or %128)
   int film_row = 0;    // PK_FILM_*: first row in the concatenated FiLM matrix
+  size_t scale_off = 0; // PK_CONV in split-precision mode: arena offset of the float accumulator scale (1 / weight scale)
   bool loaded = false;
 };
 
-struct ConvW { size_t w_off = 0, b_off = 0; int cin = 0, cout = 0, ldw = 0, ksize = 3; };
+struct ConvW { size_t w_off = 0, b_off = 0, s_off = 0; int cin = 0, cout = 0, ldw = 0, ksize = 3; };   // s_off: accumulator scale (split mode)
 struct NormW { size_t g_off = 0, b_off = 0; };
 struct ResW { NormW n1, n2; ConvW c1, c2, skip; bool has_skip = false; int film_row = 0; };
 struct AttnW { NormW n; ConvW qkv, proj; };
@@ -57,7 +57,7 @@ struct Buf {   // workspace tensor
   bool has_stats = false;
 };
 
-enum OpKind { OP_MEMSET, OP_TIME_EMBED, OP_FILM, OP_CONV_IN, OP_GN_STATS, OP_GN_APPLY, OP_CONV, OP_ATTN, OP_GN_COEF };
+enum OpKind { OP_MEMSET, OP_TIME_EMBED, OP_FILM, OP_CONV_IN, OP_GN_STATS, OP_GN_APPLY, OP_CONV, OP_ATTN, OP_GN_COEF, OP_SPLIT_CAST };
 struct Op {
   OpKind kind;
   // generic pointers / ints, interpreted per kind
@@ -139,6 +139,10 @@ struct dpir_engine {
   dpir_unet_config cfg{};
   bool half = false;          // tensor-core path (fp16 operands)
   bool stream_half = false;   // fp16s: the residual stream (block outputs, skip tensors) is stored in fp16 too
+  int gn_fuse = 1;            // dpir_set_gn_fusion (per engine): ResBlock GroupNorm+SiLU fused into the conv operand where eligible
+  int gn_math = 3;            // producer flavour of the fused kernels: 3 activate-once (default), 1 per-tap fp32, 2 per-tap packed half
+  bool split = false;         // fp16x3: split-precision tensor-core mode - conv operands are fp16 (hi, lo) pairs, three MMA passes
+                              // x_hi*w_hi + x_lo*w_hi + x_hi*w_lo per convolution, fp32 everywhere else (<= 1e-4 parity mode)
   int ted = 0, ch0 = 0;
   std::vector<std::vector<LayerDesc>> inputs, middle, outputs;
   std::map<std::string, ParamSlot> slots;
@@ -168,6 +172,9 @@ struct dpir_engine {
   float *g_x = nullptr, *g_out = nullptr;
   int64_t *g_t = nullptr;
   size_t g_cap = 0;
+  // clamped copy of the caller's timesteps (table lookups stay inside [0, diffusion_steps) whatever the caller passes)
+  int64_t *t_buf = nullptr;
+  int t_cap = 0;
   // graphs are captured and replayed on an engine-owned stream (the caller may be on the legacy default stream, which
   // cannot be captured); ev_in / ev_out order it after / before the caller's stream
   cudaStream_t gstream = nullptr;
@@ -267,9 +274,11 @@ int build_params(dpir_engine *e) {
   auto add_conv = [&](const std::string &pre, int cin, int cout, int ksize, bool conv1d) {
     ConvW w;
     w.cin = cin; w.cout = cout; w.ksize = ksize; w.ldw = conv_ldw(half, cout);
-    size_t bytes = (size_t)ksize * ksize * cin * w.ldw * (half ? 2 : 4);
+    size_t bytes = (size_t)ksize * ksize * cin * w.ldw * (half ? 2 : 4) * (e->split ? 3 : 1);
     std::vector<int64_t> shape = conv1d ? std::vector<int64_t>{cout, cin, 1} : std::vector<int64_t>{cout, cin, ksize, ksize};
-    w.w_off = add(pre + "weight", PK_CONV, shape, bytes, w.ldw).off;
+    ParamSlot &ws = add(pre + "weight", PK_CONV, shape, bytes, w.ldw);
+    w.w_off = ws.off;
+    if (e->split) { w.s_off = ab.take(sizeof(float)); e->slots[pre + "weight"].scale_off = w.s_off; }
     w.b_off = add(pre + "bias", PK_COPY, {cout}, (size_t)conv_ldw(false, cout) * 4).off;
     return w;
   };
@@ -420,9 +429,10 @@ struct PlanBuilder {
     n_norms++;
     // fp16 stream: the raw (resampled / concatenated) residual copy is fp16 as well and is written through `rawact`
     const bool raw_as_act = want_raw32 && e->stream_half;
-    *act_id = new_buf(B, Ho, Wo, C, e->half);
+    const int Cop = e->split ? 2 * C : C;            // operand tensors hold [hi | lo] pairs in split-precision mode
+    *act_id = new_buf(B, Ho, Wo, Cop, e->half);
     *raw32_id = (want_raw32 || raw_as_act) ? new_buf(B, Ho, Wo, C, raw_as_act) : -1;
-    *rawact_id = want_rawact ? new_buf(B, Ho, Wo, C, e->half) : -1;
+    *rawact_id = want_rawact ? new_buf(B, Ho, Wo, Cop, e->half) : -1;
     if (raw_as_act && want_rawact) { set_error("internal: raw copy requested twice"); err = DPIR_E_STATE; }
     Op ap;
     ap.kind = OP_GN_APPLY;
@@ -436,7 +446,7 @@ struct PlanBuilder {
     a.film = film_row >= 0 ? wp<float>(film_off + (size_t)film_row * 4) : nullptr;
     a.film_stride = e->film_rows;
     ap.film_row = film_row;
-    a.silu = silu; a.resample = resample; a.B = B; a.H = Hin; a.W = Win; a.out_half = e->half;
+    a.silu = silu; a.resample = resample; a.B = B; a.H = Hin; a.W = Win; a.out_half = e->half; a.split = e->split ? 1 : 0;
     a.act = bp<void>(*act_id);
     a.raw32 = (want_raw32 && !raw_as_act) ? bp<float>(*raw32_id) : nullptr;
     a.rawact = want_rawact ? bp<void>(*rawact_id) : (raw_as_act ? bp<void>(*raw32_id) : nullptr);
@@ -455,7 +465,7 @@ struct PlanBuilder {
   int conv(int act, const ConvW &cw, int residual, int *out_id, bool want_stats = false, bool out_half = false,
            int skip_act = -1, const ConvW *skip_w = nullptr, int skip_act2 = -1) {
     const Buf a = bufs[act];   // by value: new_buf() below may reallocate `bufs`
-    out_half = out_half && e->half;
+    out_half = out_half && e->half && !e->split;       // split-precision mode keeps every conv output in fp32
     *out_id = new_buf(B, a.H, a.W, cw.cout, out_half, want_stats);
     if (residual >= 0 && bufs[residual].half && !e->half) { set_error("internal: fp16 residual in fp32 mode"); err = DPIR_E_STATE; }
     Op op;
@@ -470,6 +480,7 @@ struct PlanBuilder {
     op.epi.out = bp<float>(*out_id);
     op.epi.out_half = out_half ? 1 : 0;
     op.epi.qstats = (want_stats && e->half) ? sp(*out_id) : nullptr;
+    op.epi.acc_scale = e->split ? e->ap<float>(cw.s_off) : nullptr;
     if (skip_act >= 0) {   // out = conv3x3(act) + conv1x1(skip_act): one accumulation (unet.py:222, 256)
       op.p2 = bp<void>(skip_act);
       op.w2 = e->arena + skip_w->w_off;
@@ -519,7 +530,7 @@ struct PlanBuilder {
   // ResBlock eligible for the fused-operand kernel: fp16 stream, no resampling, 3x3 convs on the persistent swap-AB kernel
   bool gn_fusable(const LayerDesc &l, int x, int skip, const ResW &rw) const {
     const Buf &a = bufs[x];
-    if (!(g_gn_fuse && e->stream_half && conv_tc_swapab_enabled() && l.updown == RS_NONE && a.H >= 16 && a.W >= 16)) return false;
+    if (!(e->gn_fuse && e->stream_half && conv_tc_swapab_enabled() && l.updown == RS_NONE && a.H >= 16 && a.W >= 16)) return false;
     if (!a.half || (skip >= 0 && !bufs[skip].half)) return false;
     if (a.C % 64 || (skip >= 0 && bufs[skip].C % 64)) return false;
     if (rw.c1.ksize != 3 || rw.c2.ksize != 3 || rw.c1.ldw % 128 || rw.c2.ldw % 128 || rw.c1.cout % 64) return false;
@@ -571,7 +582,7 @@ struct PlanBuilder {
     int a2, d0, d1;
     gn(h1, -1, rw.n2, rw.film_row, 1, RS_NONE, false, false, &a2, &d0, &d1);
     release(h1);
-    if (rw.has_skip && v2_eligible(a2, rw.c2)) {
+    if (rw.has_skip && v2_eligible(a2, rw.c2) && !e->split) {
       conv(a2, rw.c2, -1, out, /*want_stats=*/true, /*out_half=*/e->stream_half, xraw, &rw.skip);
       release(xraw);
     } else {
@@ -594,13 +605,24 @@ struct PlanBuilder {
     conv(xn, aw.qkv, -1, &qkv);
     release(xn);
     const Buf &xb = bufs[x];
-    int a = new_buf(B, xb.H, xb.W, l.cin, e->half);
+    const int aH = xb.H, aW = xb.W;
+    int a = new_buf(B, aH, aW, l.cin, e->half && !e->split);
     Op op;
     op.kind = OP_ATTN;
     op.p0 = bp<float>(qkv); op.q0 = bp<void>(a);
-    op.B = B; op.HW = xb.H * xb.W; op.Cin = l.cin; op.heads = l.heads; op.out_half = e->half;
+    op.B = B; op.HW = aH * aW; op.Cin = l.cin; op.heads = l.heads; op.out_half = (e->half && !e->split) ? 1 : 0;
     plan->ops.push_back(op);
     release(qkv);
+    if (e->split) {      // fp32 attention output -> [hi | lo] operand of the proj convolution
+      int a2 = new_buf(B, aH, aW, 2 * l.cin, true);
+      Op sc;
+      sc.kind = OP_SPLIT_CAST;
+      sc.p0 = bp<float>(a); sc.q0 = bp<void>(a2);
+      sc.B = B; sc.HW = aH * aW; sc.Cin = l.cin;
+      plan->ops.push_back(sc);
+      release(a);
+      a = a2;
+    }
     conv(a, aw.proj, x, out, /*want_stats=*/true, /*out_half=*/e->stream_half);
     release(a);
     release(x);
@@ -672,6 +694,8 @@ struct PlanBuilder {
     fc.B = B; fc.H = H; fc.W = W; fc.Cin = e->outconv.cin; fc.Cout = e->outconv.cout; fc.ldw = e->outconv.ldw; fc.ksize = 3;
     fc.epi.mode = EPI_NCHW; fc.epi.bias = e->ap<float>(e->outconv.b_off);
     fc.epi.coef = e->ap<float>(e->coef_off);
+    fc.epi.coef_rows = e->cfg.diffusion_steps;
+    fc.epi.acc_scale = e->split ? e->ap<float>(e->outconv.s_off) : nullptr;
     fc.bind_out = true;
     plan->final_conv = (int)plan->ops.size();
     plan->ops.push_back(fc);
@@ -729,7 +753,7 @@ int get_plan(dpir_engine *e, int B, int H, int W, Plan **out) {
     for (Op &op : plan->ops) {
       if (op.kind != OP_CONV) continue;
       ConvTcPlan *tp = nullptr;
-      rc = conv_tc_plan_create(op.p0, op.w, op.B, op.H, op.W, op.Cin, op.ldw, op.ksize, &tp);
+      rc = conv_tc_plan_create(op.p0, op.w, op.B, op.H, op.W, op.Cin, op.ldw, op.ksize, &tp, e->split ? 1 : 0);
       if (rc) return rc;
       op.tc = tp;
       plan->tc_plans.push_back(tp);
@@ -743,7 +767,7 @@ int get_plan(dpir_engine *e, int B, int H, int W, Plan **out) {
         if (rc) return rc;
       }
       if (op.gf.coef) {
-        rc = conv_tc_plan_set_gn_fuse(tp, op.gf);
+        rc = conv_tc_plan_set_gn_fuse(tp, op.gf, e->gn_math);
         if (rc) return rc;
       }
     }
@@ -815,6 +839,9 @@ int run_plan(dpir_engine *e, Plan *plan, const float *x, const int64_t *t, float
                                    op.ksize, st);
         break;
       }
+      case OP_SPLIT_CAST:
+        rc = launch_split_cast((const float *)op.p0, (__half *)op.q0, (int64_t)op.B * op.HW, op.Cin, st);
+        break;
       case OP_ATTN:
         rc = launch_attention((const float *)op.p0, op.q0, op.out_half, op.B, op.HW, op.Cin, op.heads,
                               e->cfg.use_new_attention_order, st);
@@ -884,7 +911,19 @@ int forward_impl(dpir_engine *e, const float *x, const int64_t *t, float *out, i
   }
   rc = get_plan(e, B, H, W, &plan);
   if (rc) return rc;
-  if (!e->graph_mode || e->profiling) return run_plan(e, plan, x, t, out, mode, st);
+  if (!e->graph_mode || e->profiling) {
+    if (e->use_film_table) {          // per-timestep tables are indexed with t: work on a clamped copy
+      if (e->t_cap < B) {
+        if (e->t_buf) { DPIR_CUDA_CHECK(cudaStreamSynchronize(st)); cudaFree(e->t_buf); e->t_buf = nullptr; }
+        DPIR_CUDA_CHECK(cudaMalloc(&e->t_buf, (size_t)B * 8 + 256));
+        e->t_cap = B;
+      }
+      rc = launch_clamp_t(t, e->t_buf, B, e->cfg.diffusion_steps, st);
+      if (rc) return rc;
+      t = e->t_buf;
+    }
+    return run_plan(e, plan, x, t, out, mode, st);
+  }
 
   // graph mode: fixed staging buffers, one captured graph per (shape, output mode), replayed on the engine's stream
   rc = ensure_graph_staging(e, B, H, W);
@@ -901,7 +940,12 @@ int forward_impl(dpir_engine *e, const float *x, const int64_t *t, float *out, i
   DPIR_CUDA_CHECK(cudaEventRecord(e->ev_in, st));
   DPIR_CUDA_CHECK(cudaStreamWaitEvent(gs, e->ev_in, 0));
   DPIR_CUDA_CHECK(cudaMemcpyAsync(e->g_x, x, xin, cudaMemcpyDeviceToDevice, gs));
-  DPIR_CUDA_CHECK(cudaMemcpyAsync(e->g_t, t, (size_t)B * 8, cudaMemcpyDeviceToDevice, gs));
+  if (e->use_film_table) {
+    rc = launch_clamp_t(t, e->g_t, B, e->cfg.diffusion_steps, gs);
+    if (rc) return rc;
+  } else {
+    DPIR_CUDA_CHECK(cudaMemcpyAsync(e->g_t, t, (size_t)B * 8, cudaMemcpyDeviceToDevice, gs));
+  }
   if (!gexec) {
     // warm-up run outside capture (sets function attributes, validates the tape), then capture
     rc = run_plan(e, plan, e->g_x, e->g_t, e->g_out, mode, gs);
@@ -940,7 +984,7 @@ extern "C" {
 int dpir_create(const dpir_unet_config *cfg, dpir_engine **out) {
   DPIR_REQUIRE(cfg && out, "dpir_create: null pointer");
   DPIR_REQUIRE(cfg->precision == DPIR_PRECISION_FP32 || cfg->precision == DPIR_PRECISION_FP16 ||
-                   cfg->precision == DPIR_PRECISION_FP16S, "dpir_create: bad precision");
+                   cfg->precision == DPIR_PRECISION_FP16S || cfg->precision == DPIR_PRECISION_FP16X3, "dpir_create: bad precision");
   DPIR_REQUIRE(cfg->diffusion_steps >= 1, "dpir_create: diffusion_steps must be >= 1");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -949,7 +993,8 @@ int dpir_create(const dpir_unet_config *cfg, dpir_engine **out) {
   }
   std::unique_ptr<dpir_engine> e(new dpir_engine());
   e->cfg = *cfg;
-  e->half = cfg->precision == DPIR_PRECISION_FP16 || cfg->precision == DPIR_PRECISION_FP16S;
+  e->half = cfg->precision == DPIR_PRECISION_FP16 || cfg->precision == DPIR_PRECISION_FP16S || cfg->precision == DPIR_PRECISION_FP16X3;
+  e->split = cfg->precision == DPIR_PRECISION_FP16X3;
   e->stream_half = cfg->precision == DPIR_PRECISION_FP16S;
   int rc = build_structure(e.get());
   if (rc) return rc;
@@ -972,6 +1017,7 @@ int dpir_destroy(dpir_engine *e) {
   if (e->film_table) cudaFree(e->film_table);
   if (e->ws) cudaFree(e->ws);
   if (e->g_x) { cudaFree(e->g_x); cudaFree(e->g_out); cudaFree(e->g_t); }
+  if (e->t_buf) cudaFree(e->t_buf);
   if (e->gstream) { cudaStreamDestroy(e->gstream); cudaEventDestroy(e->ev_in); cudaEventDestroy(e->ev_out); }
   delete e;
   return DPIR_OK;
@@ -1007,7 +1053,26 @@ int dpir_load_weight(dpir_engine *e, const char *name, const float *data, const 
     int O = (int)s.shape[0], I = (int)s.shape[1];
     int taps = s.shape.size() == 4 ? (int)(s.shape[2] * s.shape[3]) : 1;
     int ldw = s.ldw;
-    if (e->half) {   // [tap][ldw][I] fp16
+    if (e->split) {  // [tap][ldw][hi(I) | hi(I) | lo(I)] fp16 of S*w, S a power of two; the epilogue multiplies by 1/S
+      float mx = 0.f;
+      for (size_t i = 0; i < (size_t)O * I * taps; ++i) mx = std::max(mx, std::fabs(data[i]));
+      int ex = 0;
+      if (mx > 0.f) std::frexp(mx, &ex);             // mx = m * 2^ex, m in [0.5, 1)
+      const float S = std::ldexp(1.0f, 11 - ex);     // S*mx in [1024, 2048): hi and lo stay far from fp16's subnormal range
+      std::vector<__half> pk((size_t)taps * ldw * 3 * I, __float2half(0.f));
+      for (int o = 0; o < O; ++o)
+        for (int i = 0; i < I; ++i)
+          for (int tp = 0; tp < taps; ++tp) {
+            const float w = data[((size_t)o * I + i) * taps + tp] * S;
+            const __half hi = __float2half_rn(w);
+            const __half lo = __float2half_rn(w - __half2float(hi));
+            __half *row = pk.data() + ((size_t)tp * ldw + o) * 3 * I;
+            row[i] = hi; row[I + i] = hi; row[2 * I + i] = lo;
+          }
+      DPIR_CUDA_CHECK(cudaMemcpy(e->arena + s.off, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
+      const float inv = 1.0f / S;
+      DPIR_CUDA_CHECK(cudaMemcpy(e->arena + s.scale_off, &inv, sizeof(float), cudaMemcpyHostToDevice));
+    } else if (e->half) {   // [tap][ldw][I] fp16
       std::vector<__half> pk((size_t)taps * ldw * I, __float2half(0.f));
       for (int o = 0; o < O; ++o)
         for (int i = 0; i < I; ++i)
@@ -1125,7 +1190,7 @@ int dpir_profile_end(dpir_engine *e, int32_t *kind, int32_t *dims, float *ms, in
     int H = op.H, W = op.W, Cin = op.Cin, Cout = op.Cout;
     if (op.kind == OP_GN_APPLY) { H = op.gn.H; W = op.gn.W; Cin = op.gn.C1 + op.gn.C2; Cout = op.gn.resample; }
     if (op.kind == OP_GN_STATS) { H = op.HW; W = 1; Cin = op.C1 + op.C2; Cout = 0; }
-    if (op.kind == OP_ATTN) { H = op.HW; W = 1; Cout = op.heads; }
+    if (op.kind == OP_ATTN || op.kind == OP_SPLIT_CAST) { H = op.HW; W = 1; Cout = op.heads; }
     dims[6 * i] = H; dims[6 * i + 1] = W; dims[6 * i + 2] = Cin; dims[6 * i + 3] = Cout;
     dims[6 * i + 4] = op.kind == OP_CONV ? op.ksize + (op.gf.coef ? 10 : 0) : 0;   // 13 = 3x3 with the GroupNorm+SiLU fused on its operand
     dims[6 * i + 5] = op.kind == OP_CONV ? op.Cin2 : 0;
@@ -1170,11 +1235,17 @@ int dpir_conv_tc_f16io(const void *act, const void *w, const float *bias, const 
  * (no k_gn_apply pass, fp16s pipeline only), fp32 operand arithmetic; 2: the same with packed-half arithmetic; 0: every norm
  * is a separate pass.  Cached plans of `e` are dropped. */
 int dpir_set_gn_fusion(dpir_engine *e, int32_t enable) {
-  DPIR_REQUIRE(enable >= 0 && enable <= 3,
-               "dpir_set_gn_fusion: 0 = off, 1 = on (fp32 operand arithmetic), 2 = on (packed half), 3 = experimental v5 producers");
-  g_gn_fuse = enable ? 1 : 0;
-  if (enable) conv_tc_set_gnfuse_math(enable);
-  if (e) { cudaDeviceSynchronize(); e->plans.clear(); }
+  DPIR_REQUIRE(enable >= 0 && enable <= 4,
+               "dpir_set_gn_fusion: 0 = off, 1 | 3 = on (activate-once producers), 2 = per-tap packed half, 4 = per-tap fp32");
+  const int math = enable == 2 ? 2 : (enable == 4 ? 1 : 3);
+  if (e) {                       // per engine: other engines of the process keep their setting
+    e->gn_fuse = enable ? 1 : 0;
+    if (enable) e->gn_math = math;
+    cudaDeviceSynchronize();
+    e->plans.clear();
+  } else if (enable) {           // no engine: default of the per-kernel test entry dpir_conv_gnfuse_f16io
+    conv_tc_set_gnfuse_math(math);
+  }
   return DPIR_OK;
 }
 

@@ -41,7 +41,9 @@ __device__ __forceinline__ float inpaint1(float x0, float y, float m, float tau,
   return x0 + g * (x0p - x0);
 }
 __global__ void k_inpaint_prox(const float *__restrict__ x0, const float *__restrict__ y, const float *__restrict__ mask,
-                               float tau, float ys, float yb, float g, float *__restrict__ out, int64_t n4, int64_t n) {
+                               float tau, const float *__restrict__ tau_p, float ys, float yb, float g, float *__restrict__ out,
+                               int64_t n4, int64_t n) {
+  if (tau_p) tau = __ldg(tau_p);      // device-resident scalar (the drivers keep rhos[t] on the GPU, main_ddpir.py:389): no host sync
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t j = i; j < n4; j += stride) {
@@ -99,6 +101,45 @@ __global__ void k_eps_to_x0(const float *__restrict__ mo, const float *__restric
   }
 }
 
+// p_sample / ddim_sample tails (gaussian_diffusion.py:258-311 + 430-438, and :566-585) as ONE pass over the UNet output:
+//   eps = mo[:, :3], v = mo[:, 3:6];  x0 = clamp(c1 x - c2 eps)
+//   mode 0 (p_sample, LEARNED_RANGE):  mean = pm1 x0 + pm2 x;  logvar = f max_log + (1-f) min_log, f = (v+1)/2;
+//                                      sample = mean + [t != 0] exp(0.5 logvar) noise
+//   mode 1 (ddim_sample):              eps' = (c1 x - x0)/c2;  sample = sqrt_ac_prev x0 + ce eps' + [t != 0] sigma noise
+// tab[t] = (c1, c2, pm1, pm2, min_log, max_log, sqrt_ac_prev, ce, sigma, -) as float (float64 tables cast like
+// _extract_into_tensor :905).  Either output may be null.
+__global__ void k_sample_step(const float *__restrict__ mo, const float *__restrict__ x, const float *__restrict__ noise,
+                              const int64_t *__restrict__ t, const float *__restrict__ tab, int T, float *__restrict__ sample,
+                              float *__restrict__ x0o, int B, int Cout, int HW, int mode, int clip) {
+  int64_t total = (int64_t)B * 3 * HW;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int b = (int)(i / (3 * (int64_t)HW));
+    int64_t r = i - (int64_t)b * 3 * HW;
+    int64_t tt = t[b];
+    if (tt < 0 || tt >= T) __trap();                 // the reference raises IndexError
+    const float *c = tab + tt * 10;
+    const float xv = x[i];
+    const float eps = mo[(int64_t)b * Cout * HW + r];
+    float v0 = c[0] * xv - c[1] * eps;
+    if (clip) v0 = fminf(fmaxf(v0, -1.f), 1.f);
+    if (x0o) x0o[i] = v0;
+    if (sample) {
+      const float nz = (noise && tt != 0) ? noise[i] : 0.f;
+      float sv;
+      if (mode == 0) {
+        const float mean = c[2] * v0 + c[3] * xv;
+        const float f = (mo[(int64_t)b * Cout * HW + (int64_t)3 * HW + r] + 1.f) / 2.f;
+        const float logvar = f * c[5] + (1.f - f) * c[4];
+        sv = mean + expf(0.5f * logvar) * nz;
+      } else {
+        const float epsd = (c[0] * xv - v0) / c[1];
+        sv = v0 * c[6] + c[7] * epsd + c[8] * nz;
+      }
+      sample[i] = sv;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------ FFT helpers
 // psf -> zero-padded, centre rolled to (0,0)   [utils_sisr.py:34-37]
 __global__ void k_psf_place(const float *__restrict__ k, float *__restrict__ otf_in, int Bk, int kh, int kw, int H, int W) {
@@ -152,8 +193,9 @@ __global__ void k_mul_conj(const float2 *__restrict__ FB, float2 *__restrict__ F
 // in place on spec.  Algorithmic bytes per image (3x256x256): X r/w folded into the cuFFT passes; here
 // spec read+write (2 x 792,576) + FBFy 792,576 + F2B 132,096.
 __global__ void k_solve_sf1(float2 *__restrict__ spec, const float *__restrict__ F2B, const float2 *__restrict__ FBFy,
-                            float alpha, int B, int C, int Bk, int64_t plane, float HW, float in_scale, float in_bias,
-                            float out_scale, float out_bias, float blend) {
+                            float alpha, const float *__restrict__ alpha_p, int B, int C, int Bk, int64_t plane, float HW,
+                            float in_scale, float in_bias, float out_scale, float out_bias, float blend) {
+  if (alpha_p) alpha = __ldg(alpha_p);
   int64_t total = (int64_t)B * C * plane;
   float inv = 1.0f / HW;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -182,8 +224,9 @@ __device__ __forceinline__ float2 herm_load(const float2 *__restrict__ p, int r,
 //   S = mean_i FB_i Xi_i,  Wm = mean_i |FB_i|^2,  FX_j = Xi_j + (FBFy_j - conj(FB_j) S)/(Wm + alpha)
 // Equivalent to utils_sisr.py:66-72 but without the (FR - ...)/alpha cancellation.  Out-of-place.
 __global__ void k_solve_sf(const float2 *__restrict__ spec, float2 *__restrict__ spec_out, const float2 *__restrict__ FB,
-                           const float2 *__restrict__ FBFy, float alpha, int B, int C, int Bk, int H, int W, int sf,
-                           float in_scale, float in_bias, float out_scale, float out_bias, float blend) {
+                           const float2 *__restrict__ FBFy, float alpha, const float *__restrict__ alpha_p, int B, int C, int Bk,
+                           int H, int W, int sf, float in_scale, float in_bias, float out_scale, float out_bias, float blend) {
+  if (alpha_p) alpha = __ldg(alpha_p);
   int Hl = H / sf, Wl = W / sf, Wh = W / 2 + 1;
   int64_t total = (int64_t)B * C * Hl * Wl;
   float HWf = (float)H * (float)W;
@@ -254,7 +297,8 @@ __global__ void k_resize_pass(const float *__restrict__ in, float *__restrict__ 
 
 // out = 2*((x0/2+.5) + gamma * up_nearest(y - down)/(1+rho)) - 1    [main_ddpir.py:403-406]
 __global__ void k_ibp(const float *__restrict__ x0, const float *__restrict__ y, const float *__restrict__ down, float gamma,
-                      float rho, int N, int H, int W, int sf, float *__restrict__ out) {
+                      float rho, const float *__restrict__ rho_p, int N, int H, int W, int sf, float *__restrict__ out) {
+  if (rho_p) rho = __ldg(rho_p);
   int Hl = H / sf, Wl = W / sf;
   int64_t total = (int64_t)N * H * W;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -419,14 +463,23 @@ int dpir_affine(const float *x, float a, float b, float *out, int64_t n, void *s
   return DPIR_OK;
 }
 
-int dpir_inpaint_prox(const float *x0, const float *y, const float *mask, float tau, float y_scale, float y_bias,
-                      float guidance, float *out, int64_t n, void *stream) {
+static int inpaint_prox_impl(const float *x0, const float *y, const float *mask, float tau, const float *tau_p, float y_scale,
+                             float y_bias, float guidance, float *out, int64_t n, void *stream) {
   DPIR_REQUIRE(x0 && y && mask && out, "dpir_inpaint_prox: null pointer");
   bool al = (((uintptr_t)x0 | (uintptr_t)y | (uintptr_t)mask | (uintptr_t)out) & 15) == 0;
   int64_t n4 = al ? n / 4 : 0;
-  k_inpaint_prox<<<grid_for(n / 4 + 1), 256, 0, (cudaStream_t)stream>>>(x0, y, mask, tau, y_scale, y_bias, guidance, out, n4, n);
+  k_inpaint_prox<<<grid_for(n / 4 + 1), 256, 0, (cudaStream_t)stream>>>(x0, y, mask, tau, tau_p, y_scale, y_bias, guidance, out, n4, n);
   DPIR_LAUNCH_CHECK();
   return DPIR_OK;
+}
+int dpir_inpaint_prox(const float *x0, const float *y, const float *mask, float tau, float y_scale, float y_bias,
+                      float guidance, float *out, int64_t n, void *stream) {
+  return inpaint_prox_impl(x0, y, mask, tau, nullptr, y_scale, y_bias, guidance, out, n, stream);
+}
+int dpir_inpaint_prox_dev(const float *x0, const float *y, const float *mask, const float *tau_dev, float y_scale, float y_bias,
+                          float guidance, float *out, int64_t n, void *stream) {
+  DPIR_REQUIRE(tau_dev, "dpir_inpaint_prox_dev: null tau");
+  return inpaint_prox_impl(x0, y, mask, 0.f, tau_dev, y_scale, y_bias, guidance, out, n, stream);
 }
 
 int dpir_renoise(const float *x, const float *x0, const float *noise_eta, const float *noise_zeta, float sa_t, float s1_t,
@@ -445,6 +498,17 @@ int dpir_eps_to_x0(const float *model_out, const float *x, const float *coef, fl
                    int32_t HW, int32_t clip, void *stream) {
   DPIR_REQUIRE(model_out && x && coef && x0 && Cout >= 3, "dpir_eps_to_x0: bad arguments");
   k_eps_to_x0<<<grid_for((int64_t)B * 3 * HW), 256, 0, (cudaStream_t)stream>>>(model_out, x, coef, x0, B, Cout, HW, clip);
+  DPIR_LAUNCH_CHECK();
+  return DPIR_OK;
+}
+
+int dpir_sample_step(const float *model_out, const float *x, const float *noise, const int64_t *t, const float *tab, int32_t T,
+                     float *sample, float *x0, int32_t B, int32_t Cout, int32_t HW, int32_t mode, int32_t clip, void *stream) {
+  DPIR_REQUIRE(model_out && x && t && tab && (sample || x0), "dpir_sample_step: null pointer");
+  DPIR_REQUIRE(mode == 1 || Cout >= 6, "dpir_sample_step: p_sample needs the learned-range variance channels (Cout >= 6)");
+  DPIR_REQUIRE(Cout >= 3 && (mode == 0 || mode == 1) && T >= 1, "dpir_sample_step: bad arguments");
+  k_sample_step<<<grid_for((int64_t)B * 3 * HW), 256, 0, (cudaStream_t)stream>>>(model_out, x, noise, t, tab, T, sample, x0, B, Cout,
+                                                                                  HW, mode, clip);
   DPIR_LAUNCH_CHECK();
   return DPIR_OK;
 }
@@ -518,9 +582,9 @@ int dpir_fft_precalc(dpir_fft_plan *plan_k, dpir_fft_plan *plan_y, const float *
   return DPIR_OK;
 }
 
-int dpir_fft_solve(dpir_fft_plan *plan_x, const float *x, const float *FB, const float *F2B, const float *FBFy, float alpha,
-                   int32_t B, int32_t C, int32_t Bk, int32_t sf, float in_scale, float in_bias, float out_scale,
-                   float out_bias, float blend, float *spec, float *out, void *stream) {
+static int fft_solve_impl(dpir_fft_plan *plan_x, const float *x, const float *FB, const float *F2B, const float *FBFy, float alpha,
+                          const float *alpha_p, int32_t B, int32_t C, int32_t Bk, int32_t sf, float in_scale, float in_bias,
+                          float out_scale, float out_bias, float blend, float *spec, float *out, void *stream) {
   DPIR_REQUIRE(plan_x && x && FB && F2B && FBFy && spec && out, "dpir_fft_solve: null pointer");
   DPIR_REQUIRE(plan_x->batch == B * C, "dpir_fft_solve: plan batch != B*C");
   DPIR_REQUIRE(Bk == 1 || Bk == B, "dpir_fft_solve: kernel batch must be 1 or B");
@@ -533,18 +597,31 @@ int dpir_fft_solve(dpir_fft_plan *plan_x, const float *x, const float *FB, const
   float *inv_in = spec;
   if (sf == 1) {
     k_solve_sf1<<<grid_for((int64_t)B * C * plane), 256, 0, st>>>(reinterpret_cast<float2 *>(spec), F2B,
-                                                                  reinterpret_cast<const float2 *>(FBFy), alpha, B, C, Bk,
-                                                                  plane, (float)H * (float)W, in_scale, in_bias, out_scale,
+                                                                  reinterpret_cast<const float2 *>(FBFy), alpha, alpha_p, B, C,
+                                                                  Bk, plane, (float)H * (float)W, in_scale, in_bias, out_scale,
                                                                   out_bias, blend);
   } else {
     float *spec2 = spec + (size_t)B * C * plane * 2;
     k_solve_sf<<<grid_for((int64_t)B * C * (H / sf) * (W / sf)), 256, 0, st>>>(
         reinterpret_cast<const float2 *>(spec), reinterpret_cast<float2 *>(spec2), reinterpret_cast<const float2 *>(FB),
-        reinterpret_cast<const float2 *>(FBFy), alpha, B, C, Bk, H, W, sf, in_scale, in_bias, out_scale, out_bias, blend);
+        reinterpret_cast<const float2 *>(FBFy), alpha, alpha_p, B, C, Bk, H, W, sf, in_scale, in_bias, out_scale, out_bias, blend);
     inv_in = spec2;
   }
   DPIR_LAUNCH_CHECK();
   return dpir_irfft2(plan_x, inv_in, out, stream);
+}
+int dpir_fft_solve(dpir_fft_plan *plan_x, const float *x, const float *FB, const float *F2B, const float *FBFy, float alpha,
+                   int32_t B, int32_t C, int32_t Bk, int32_t sf, float in_scale, float in_bias, float out_scale,
+                   float out_bias, float blend, float *spec, float *out, void *stream) {
+  return fft_solve_impl(plan_x, x, FB, F2B, FBFy, alpha, nullptr, B, C, Bk, sf, in_scale, in_bias, out_scale, out_bias, blend, spec,
+                        out, stream);
+}
+int dpir_fft_solve_dev(dpir_fft_plan *plan_x, const float *x, const float *FB, const float *F2B, const float *FBFy,
+                       const float *alpha_dev, int32_t B, int32_t C, int32_t Bk, int32_t sf, float in_scale, float in_bias,
+                       float out_scale, float out_bias, float blend, float *spec, float *out, void *stream) {
+  DPIR_REQUIRE(alpha_dev, "dpir_fft_solve_dev: null alpha");
+  return fft_solve_impl(plan_x, x, FB, F2B, FBFy, 0.f, alpha_dev, B, C, Bk, sf, in_scale, in_bias, out_scale, out_bias, blend, spec,
+                        out, stream);
 }
 
 int dpir_resize_separable(const float *in, int32_t N, int32_t Hin, int32_t Win, int32_t Hout, int32_t Wout, const float *w_h,
@@ -559,12 +636,21 @@ int dpir_resize_separable(const float *in, int32_t N, int32_t Hin, int32_t Win, 
   return DPIR_OK;
 }
 
-int dpir_ibp_update(const float *x0, const float *y, const float *down, float gamma, float rho, int32_t N, int32_t H,
-                    int32_t W, int32_t sf, float *out, void *stream) {
+static int ibp_impl(const float *x0, const float *y, const float *down, float gamma, float rho, const float *rho_p, int32_t N,
+                    int32_t H, int32_t W, int32_t sf, float *out, void *stream) {
   DPIR_REQUIRE(x0 && y && down && out && sf >= 1 && H % sf == 0 && W % sf == 0, "dpir_ibp_update: bad arguments");
-  k_ibp<<<grid_for((int64_t)N * H * W), 256, 0, (cudaStream_t)stream>>>(x0, y, down, gamma, rho, N, H, W, sf, out);
+  k_ibp<<<grid_for((int64_t)N * H * W), 256, 0, (cudaStream_t)stream>>>(x0, y, down, gamma, rho, rho_p, N, H, W, sf, out);
   DPIR_LAUNCH_CHECK();
   return DPIR_OK;
+}
+int dpir_ibp_update(const float *x0, const float *y, const float *down, float gamma, float rho, int32_t N, int32_t H,
+                    int32_t W, int32_t sf, float *out, void *stream) {
+  return ibp_impl(x0, y, down, gamma, rho, nullptr, N, H, W, sf, out, stream);
+}
+int dpir_ibp_update_dev(const float *x0, const float *y, const float *down, float gamma, const float *rho_dev, int32_t N, int32_t H,
+                        int32_t W, int32_t sf, float *out, void *stream) {
+  DPIR_REQUIRE(rho_dev, "dpir_ibp_update_dev: null rho");
+  return ibp_impl(x0, y, down, gamma, 0.f, rho_dev, N, H, W, sf, out, stream);
 }
 
 int dpir_blur_reflect(const float *x, const float *k, int32_t planes, int32_t H, int32_t W, int32_t kh, int32_t kw, float *out,

@@ -198,6 +198,24 @@ int launch_gn_stats(const void *src, int src_half, int C, double *qstats, int B,
 }
 
 // =========================================================================================== GroupNorm apply
+// store 4 activated channels of work pixel `pix` (C channels per pixel): plain, or split into fp16 hi | lo halves of a 2C row
+template <typename T, bool SPLIT>
+__device__ __forceinline__ void store_act4(T *base, int64_t pix, int C, int c, float4 v) {
+  if constexpr (SPLIT) {
+    __half *row = reinterpret_cast<__half *>(base) + pix * (2 * (int64_t)C);
+    const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+    const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+    const __half2 l0 = __floats2half2_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2half2_rn(v.z - f1.x, v.w - f1.y);
+    uint2 uh, ul;
+    uh.x = *reinterpret_cast<const uint32_t *>(&h0); uh.y = *reinterpret_cast<const uint32_t *>(&h1);
+    ul.x = *reinterpret_cast<const uint32_t *>(&l0); ul.y = *reinterpret_cast<const uint32_t *>(&l1);
+    *reinterpret_cast<uint2 *>(row + c) = uh;
+    *reinterpret_cast<uint2 *>(row + C + c) = ul;
+  } else {
+    Store4<T>::st(base + pix * C + c, v);
+  }
+}
+
 struct GnDev {
   const void *s1; int C1; const void *s2; int C2;
   const double *q1, *q2;             // quad statistics of the two sources
@@ -241,9 +259,9 @@ constexpr int GN_APPLY_PIX = 256;  // work pixels per block
 
 // MODE none: one work pixel = one pixel.  MODE down: work pixel = output pixel (reads 2x2 inputs, averages the
 // ACTIVATED values as unet.py:238-241 does: in_rest(x) then h_upd).  MODE up: work pixel = input pixel, written 2x2.
-template <typename T, typename TI, int MODE>
+template <typename T, typename TI, int MODE, bool SPLIT = false>
 __global__ void k_gn_apply(GnDev a, T *__restrict__ act, T *__restrict__ rawact) {
-  constexpr bool FAST = sizeof(T) == 2;
+  constexpr bool FAST = sizeof(T) == 2 && !SPLIT;      // split-precision operands keep the exact SiLU
   __shared__ float s_mean[32], s_rstd[32];
   int C = a.C1 + a.C2, C4 = C / 4;
   int b = blockIdx.y;
@@ -298,17 +316,17 @@ __global__ void k_gn_apply(GnDev a, T *__restrict__ act, T *__restrict__ rawact)
       for (int u = 0; u < UN; ++u) {
         const float4 v = Load4<TI>::cvt(rv[u]);
         int64_t o = (obase + p + u * ppb) * C + c4 * 4;
-        Store4<T>::st(act + o, gn_act<FAST>(v, mean, rstd, ga, be, has_film, sc, sh, a.silu));
+        store_act4<T, SPLIT>(act, obase + p + u * ppb, C, c4 * 4, gn_act<FAST>(v, mean, rstd, ga, be, has_film, sc, sh, a.silu));
         if (a.raw32) *reinterpret_cast<float4 *>(a.raw32 + o) = v;
-        if (rawact) Store4<T>::st(rawact + o, v);
+        if (rawact) store_act4<T, SPLIT>(rawact, obase + p + u * ppb, C, c4 * 4, v);
       }
     }
     for (; p < p1; p += ppb) {
       float4 v = Load4<TI>::ld(src + (int64_t)p * Cs + cc);
       int64_t o = (obase + p) * C + c4 * 4;
-      Store4<T>::st(act + o, gn_act<FAST>(v, mean, rstd, ga, be, has_film, sc, sh, a.silu));
+      store_act4<T, SPLIT>(act, obase + p, C, c4 * 4, gn_act<FAST>(v, mean, rstd, ga, be, has_film, sc, sh, a.silu));
       if (a.raw32) *reinterpret_cast<float4 *>(a.raw32 + o) = v;
-      if (rawact) Store4<T>::st(rawact + o, v);
+      if (rawact) store_act4<T, SPLIT>(rawact, obase + p, C, c4 * 4, v);
     }
   } else if (MODE == RS_DOWN) {
     for (int p = p0 + lane_p; p < p1; p += ppb) {
@@ -327,9 +345,9 @@ __global__ void k_gn_apply(GnDev a, T *__restrict__ act, T *__restrict__ rawact)
       accA.x *= 0.25f; accA.y *= 0.25f; accA.z *= 0.25f; accA.w *= 0.25f;
       accR.x *= 0.25f; accR.y *= 0.25f; accR.z *= 0.25f; accR.w *= 0.25f;
       int64_t o = (obase + p) * C + c4 * 4;
-      Store4<T>::st(act + o, accA);
+      store_act4<T, SPLIT>(act, obase + p, C, c4 * 4, accA);
       if (a.raw32) *reinterpret_cast<float4 *>(a.raw32 + o) = accR;
-      if (rawact) Store4<T>::st(rawact + o, accR);
+      if (rawact) store_act4<T, SPLIT>(rawact, obase + p, C, c4 * 4, accR);
     }
   } else {
     for (int p = p0 + lane_p; p < p1; p += ppb) {
@@ -338,10 +356,11 @@ __global__ void k_gn_apply(GnDev a, T *__restrict__ act, T *__restrict__ rawact)
       float4 o = gn_act<FAST>(v, mean, rstd, ga, be, has_film, sc, sh, a.silu);
 #pragma unroll
       for (int d = 0; d < 4; ++d) {
-        int64_t q = (obase + (int64_t)(2 * yi + (d >> 1)) * Wo + 2 * xi + (d & 1)) * C + c4 * 4;
-        Store4<T>::st(act + q, o);
+        const int64_t qp = obase + (int64_t)(2 * yi + (d >> 1)) * Wo + 2 * xi + (d & 1);
+        int64_t q = qp * C + c4 * 4;
+        store_act4<T, SPLIT>(act, qp, C, c4 * 4, o);
         if (a.raw32) *reinterpret_cast<float4 *>(a.raw32 + q) = v;
-        if (rawact) Store4<T>::st(rawact + q, v);
+        if (rawact) store_act4<T, SPLIT>(rawact, qp, C, c4 * 4, v);
       }
     }
   }
@@ -358,7 +377,13 @@ int launch_gn_apply(const GnApplyArgs &a, cudaStream_t st) {
   dim3 grid(cdiv(nwork, GN_APPLY_PIX), a.B);
   int threads = gn_threads(C);
 #define GN_LAUNCH(T, TI, M) k_gn_apply<T, TI, M><<<grid, threads, 0, st>>>(d, (T *)a.act, (T *)a.rawact)
-  if (a.out_half && a.src_half) {
+  DPIR_REQUIRE(!a.split || (a.out_half && !a.src_half), "gn_apply: split operands are written from fp32 sources as fp16 pairs");
+#define GN_LAUNCH_S(M) k_gn_apply<__half, float, M, true><<<grid, threads, 0, st>>>(d, (__half *)a.act, (__half *)a.rawact)
+  if (a.split) {
+    if (a.resample == RS_NONE) GN_LAUNCH_S(RS_NONE);
+    else if (a.resample == RS_DOWN) GN_LAUNCH_S(RS_DOWN);
+    else GN_LAUNCH_S(RS_UP);
+  } else if (a.out_half && a.src_half) {
     if (a.resample == RS_NONE) GN_LAUNCH(__half, __half, RS_NONE);
     else if (a.resample == RS_DOWN) GN_LAUNCH(__half, __half, RS_DOWN);
     else GN_LAUNCH(__half, __half, RS_UP);
@@ -372,6 +397,7 @@ int launch_gn_apply(const GnApplyArgs &a, cudaStream_t st) {
     else GN_LAUNCH(float, float, RS_UP);
   }
 #undef GN_LAUNCH
+#undef GN_LAUNCH_S
   DPIR_LAUNCH_CHECK();
   return DPIR_OK;
 }
@@ -760,6 +786,39 @@ int launch_attention(const float *qkv, void *out, int out_half, int B, int T, in
   } else {
     k_attention<float><<<grid, 256, smem, st>>>(qkv, (float *)out, T, C, heads, new_order);
   }
+  DPIR_LAUNCH_CHECK();
+  return DPIR_OK;
+}
+
+// =========================================================================================== split cast
+// fp32 [npix][C] -> fp16 [npix][hi(C) | lo(C)]: the operand form of the split-precision convolutions (attention output -> proj)
+__global__ void k_split_cast(const float *__restrict__ in, __half *__restrict__ out, int64_t n4, int C) {
+  const int C4 = C / 4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t pix = i / C4;
+    const int c = (int)(i - pix * C4) * 4;
+    store_act4<__half, true>(out, pix, C, c, *reinterpret_cast<const float4 *>(in + pix * C + c));
+  }
+}
+int launch_split_cast(const float *in, __half *out, int64_t npix, int C, cudaStream_t st) {
+  DPIR_REQUIRE(C % 4 == 0, "split_cast: channels must be a multiple of 4");
+  const int64_t n4 = npix * (C / 4);
+  int64_t blocks = (n4 + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  k_split_cast<<<(int)blocks, 256, 0, st>>>(in, out, n4, C);
+  DPIR_LAUNCH_CHECK();
+  return DPIR_OK;
+}
+
+// =========================================================================================== timestep clamp
+// Device-side timesteps index the per-timestep FiLM table and the eps->x0 coefficient table; a value outside [0, T) would read
+// out of bounds (the reference raises IndexError, which needs a host read).  The engine works on a clamped copy.
+__global__ void k_clamp_t(const int64_t *__restrict__ t, int64_t *__restrict__ out, int B, int64_t T) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B) { int64_t v = t[i]; out[i] = v < 0 ? 0 : (v >= T ? T - 1 : v); }
+}
+int launch_clamp_t(const int64_t *t, int64_t *out, int B, int T, cudaStream_t st) {
+  k_clamp_t<<<cdiv(B, 128), 128, 0, st>>>(t, out, B, (int64_t)T);
   DPIR_LAUNCH_CHECK();
   return DPIR_OK;
 }

@@ -31,11 +31,17 @@ def inpaint_prox(x0, y, mask, tau, guidance_scale=1.0, y_scale=2.0, y_bias=-1.0,
     x0, y, mask = _f32c(x0, y, mask)
     if mask.shape != x0.shape:
         mask = mask.expand_as(x0).contiguous()
-    tau = float(tau.reshape(-1)[0].item()) if torch.is_tensor(tau) else float(tau)
     out = torch.empty_like(x0) if out is None else out
-    _lib.check(_lib.load().dpir_inpaint_prox(_lib.ptr(x0), _lib.ptr(y), _lib.ptr(mask), tau, float(y_scale), float(y_bias),
-                                             float(guidance_scale), _lib.ptr(out), x0.numel(), _lib.stream_ptr()),
-               "dpir_inpaint_prox")
+    tau_dev = _lib.device_scalar(tau, x0.device)
+    if tau_dev is not None:        # tau lives on the GPU (main_ddpir.py:389): read it in the kernel, no host sync
+        _lib.check(_lib.load().dpir_inpaint_prox_dev(_lib.ptr(x0), _lib.ptr(y), _lib.ptr(mask), _lib.ptr(tau_dev), float(y_scale),
+                                                     float(y_bias), float(guidance_scale), _lib.ptr(out), x0.numel(),
+                                                     _lib.stream_ptr()), "dpir_inpaint_prox_dev")
+    else:
+        tau = float(tau.reshape(-1)[0]) if torch.is_tensor(tau) else float(tau)
+        _lib.check(_lib.load().dpir_inpaint_prox(_lib.ptr(x0), _lib.ptr(y), _lib.ptr(mask), tau, float(y_scale), float(y_bias),
+                                                 float(guidance_scale), _lib.ptr(out), x0.numel(), _lib.stream_ptr()),
+                   "dpir_inpaint_prox")
     return out
 
 

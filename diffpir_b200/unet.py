@@ -56,7 +56,8 @@ class UNetModel:
             c.attention_ds[i] = a
         c.num_heads, c.num_head_channels, c.num_heads_upsample = cfg.num_heads, cfg.num_head_channels, cfg.num_heads_upsample
         c.use_new_attention_order = int(cfg.use_new_attention_order)
-        c.precision = {"fp32": _lib.PRECISION_FP32, "fp16": _lib.PRECISION_FP16, "fp16s": _lib.PRECISION_FP16S}[precision]
+        c.precision = {"fp32": _lib.PRECISION_FP32, "fp16": _lib.PRECISION_FP16, "fp16s": _lib.PRECISION_FP16S,
+                       "fp16x3": _lib.PRECISION_FP16X3}[precision]
         c.diffusion_steps = diffusion_steps
         h = ctypes.c_void_p()
         _lib.check(lib.dpir_create(ctypes.byref(c), ctypes.byref(h)), "dpir_create")
@@ -69,6 +70,7 @@ class UNetModel:
         _lib.check(lib.dpir_set_tables(h, ctypes.c_void_p(freqs.data_ptr()), half,
                                        ctypes.c_void_p(coef.ctypes.data), diffusion_steps), "dpir_set_tables")
         self._sd = {}
+        self._film_table = True
         if graph:
             self.set_graph_mode(True)
 
@@ -125,6 +127,7 @@ class UNetModel:
         """True (default): per-timestep FiLM table (integer timesteps in [0, diffusion_steps)); False: evaluate the embedding
         MLPs per call (arbitrary timesteps)."""
         _lib.check(self._lib.dpir_set_film_table(self._h, int(enable)), "dpir_set_film_table")
+        self._film_table = bool(enable)
 
     def _prep(self, x, timesteps):
         _lib.require_cuda(x)
@@ -134,6 +137,12 @@ class UNetModel:
         B = x.shape[0]
         if not torch.is_tensor(timesteps):
             timesteps = torch.tensor(timesteps)
+        if not timesteps.is_cuda and timesteps.numel() and self._film_table:
+            # host-side timesteps can be validated for free (the reference raises IndexError); device-side ones are clamped
+            # inside the engine before any table lookup
+            lo, hi = int(timesteps.min()), int(timesteps.max())
+            if lo < 0 or hi >= self.diffusion_steps:
+                raise ValueError(f"timesteps must lie in [0, {self.diffusion_steps}) (got {lo}..{hi})")
         t = timesteps.to(device=x.device, dtype=torch.int64).reshape(-1).contiguous()
         if t.numel() == 1 and B > 1:
             t = t.expand(B).contiguous()
@@ -180,11 +189,12 @@ class UNetModel:
         return int(self._lib.dpir_workspace_bytes(self._h))
 
     # ---- per-op device timing (CUDA events inside the engine)
-    OP_KINDS = ("memset", "time_embed", "film", "conv_in", "gn_stats", "gn_apply", "conv", "attention", "gn_coef")
+    OP_KINDS = ("memset", "time_embed", "film", "conv_in", "gn_stats", "gn_apply", "conv", "attention", "gn_coef", "split_cast")
 
     def set_gn_fusion(self, enable):
-        """A/B switch (process-wide): 1/True ResBlock GroupNorm+SiLU inside the convolutions (default, fp32 operand arithmetic),
-        2 the same with packed-half arithmetic, 0/False separate passes; drops this model's cached plans."""
+        """A/B switch (this model only): 1/True ResBlock GroupNorm+SiLU inside the convolutions (default: producers that activate
+        each element once per chunk), 4 round-1 per-tap-box producers, 2 per-tap-box with packed-half arithmetic, 0/False
+        separate passes; drops this model's cached plans."""
         _lib.check(self._lib.dpir_set_gn_fusion(self._h, int(enable)), "dpir_set_gn_fusion")
 
     def profile_begin(self):

@@ -6,14 +6,23 @@
     test_mode(model_fn, model_diffusion, L, mode, refield, min_size, sf, modulo, noise_level, vec_t,
               model_out_type, diffusion, ddim_sample, alphas_cumprod)                   :16-195
 
-`model_fn` takes the fast path (one fused UNet + eps->x0 launch sequence, no dead variance / posterior /
-randn work of p_sample) when the output type is 'pred_xstart' and `model_diffusion` is a
-diffpir_b200.UNetModel; 'epsilon' / 'score' derive from it as the reference does (:241-256).  Output types
-that need p_sample's random `sample` ('pred_x_prev', 'pred_x_prev_and_start') or DDIM are delegated to the
-`diffusion` object passed by the caller (the reference's own SpacedDiffusion), with our model plugged in.
+When `model_diffusion` is a diffpir_b200.UNetModel every output type runs natively:
+  'pred_xstart' (p_sample)                 one fused UNet + eps->x0 launch sequence (dpir_unet_x0), none of p_sample's dead
+                                           variance / posterior work
+  'pred_x_prev', 'pred_x_prev_and_start',  UNet forward + ONE elementwise kernel (diffpir_b200.diffusion.GaussianDiffusion =
+  ddim_sample=True                         gaussian_diffusion.py:395-439 / 537-585 with the reference's float64 tables)
+  'epsilon', 'score'                       derived from pred_xstart exactly as :247-256
+The `diffusion` argument may be the reference's own SpacedDiffusion (its betas / timestep map are mirrored), a native
+GaussianDiffusion, or None (DiffPIR's linear 1000-step schedule).  Any other model object is handed to the caller's
+`diffusion` unchanged (reference behaviour).
 """
 import numpy as np
 import torch
+
+# The reference draws torch.randn_like(x) inside p_sample / ddim_sample on EVERY call, also when only pred_xstart is used
+# (gaussian_diffusion.py:430, 575).  True keeps the torch generator in lockstep with the reference (same seed -> same
+# trajectory under the unmodified drivers); False skips the dead draw (one launch less per step).
+RNG_COMPAT = True
 
 
 def find_nearest(array, value):
@@ -24,17 +33,45 @@ def find_nearest(array, value):
 
 
 _sigma_cache = {}
+_native_cache = {}
 
 
 def _reduced_alpha_cumprod(alphas_cumprod):
-    """sigma_bar table (utils_model.py:210-212), cached on the host per alphas_cumprod tensor."""
-    key = (alphas_cumprod.data_ptr(), alphas_cumprod.numel(), str(alphas_cumprod.device))
+    """sigma_bar table (utils_model.py:210-212) on the host, cached by CONTENT (a freed and re-allocated tensor with another
+    schedule must not hit a stale entry: the key holds size, first/last/mid values, not the data pointer)."""
+    ac = alphas_cumprod.detach().to("cpu")
+    n = ac.numel()
+    key = (n, float(ac[0]), float(ac[n // 2]), float(ac[-1]), str(ac.dtype))
     tab = _sigma_cache.get(key)
     if tab is None:
-        ac = alphas_cumprod.detach().to("cpu")
         tab = torch.div(torch.sqrt(1.0 - ac), torch.sqrt(ac)).numpy()
         _sigma_cache[key] = tab
     return tab
+
+
+def _native_diffusion(diffusion):
+    from .diffusion import GaussianDiffusion
+    if isinstance(diffusion, GaussianDiffusion):
+        return diffusion
+    key = id(diffusion) if diffusion is not None else None
+    ent = _native_cache.get(key)
+    if ent is None or ent[0] is not diffusion:
+        nat = GaussianDiffusion() if diffusion is None else GaussianDiffusion.from_reference(diffusion)
+        nat.is_default = (nat.timestep_map is None or list(nat.timestep_map) == list(range(nat.num_timesteps))) and \
+            not nat.rescale_timesteps
+        ent = (diffusion, nat)
+        _native_cache[key] = ent
+    return ent[1]
+
+
+def _engine_matches(model, nat):
+    """dpir_unet_x0 converts eps->x0 with the engine's built-in linear-schedule table: usable when `nat` is that schedule."""
+    if not getattr(nat, "is_default", False) or nat.num_timesteps != getattr(model, "diffusion_steps", -1):
+        return False
+    if not hasattr(nat, "_linear"):
+        from .diffusion import linear_betas
+        nat._linear = bool(np.array_equal(nat.betas, linear_betas(nat.num_timesteps)))
+    return nat._linear
 
 
 def model_fn(x, noise_level, model_diffusion, vec_t=None, model_out_type='pred_xstart',
@@ -43,35 +80,44 @@ def model_fn(x, noise_level, model_diffusion, vec_t=None, model_out_type='pred_x
     if not torch.is_tensor(vec_t):
         t_step = find_nearest(_reduced_alpha_cumprod(alphas_cumprod), float(noise_level) / 255.)
         vec_t = torch.full((x.shape[0],), t_step, device=x.device, dtype=torch.int64)
-    fast = hasattr(model_diffusion, "x0") and not ddim_sample and not model_kwargs
-    if fast and model_out_type in ('pred_xstart', 'epsilon', 'score'):
-        x0 = model_diffusion.x0(x, vec_t)
-        if model_out_type == 'pred_xstart':
-            return x0
-        if t_step is None:
-            t_step = int(vec_t.reshape(-1)[0].item())
-        alpha_prod_t = alphas_cumprod[int(t_step)]
-        beta_prod_t = 1 - alpha_prod_t
-        out = (x - alpha_prod_t ** (0.5) * x0) / beta_prod_t ** (0.5)
-        if model_out_type == 'score':
-            out = - out / beta_prod_t ** (0.5)
-        return out
-    if diffusion is None:
-        raise RuntimeError(f"model_fn: output type '{model_out_type}' / ddim needs the `diffusion` object")
-    sampler = diffusion.ddim_sample if ddim_sample else diffusion.p_sample
-    kw = dict(clip_denoised=True, denoised_fn=None, cond_fn=None, model_kwargs=model_kwargs)
-    if ddim_sample:
-        kw["eta"] = 0
-    out = sampler(model_diffusion, x, vec_t, **kw)
+    native = hasattr(model_diffusion, "x0") and not model_kwargs
+    if native:
+        try:
+            nat = _native_diffusion(diffusion)
+        except NotImplementedError:
+            native = False
+    if native:
+        need_sample = model_out_type in ('pred_x_prev', 'pred_x_prev_and_start')
+        if not need_sample and not ddim_sample and _engine_matches(model_diffusion, nat):
+            if RNG_COMPAT:
+                torch.randn_like(x)                    # p_sample's draw (gaussian_diffusion.py:430), result unused
+            out = {"pred_xstart": model_diffusion.x0(x, vec_t)}
+        elif ddim_sample:
+            out = nat.ddim_sample(model_diffusion, x, vec_t, clip_denoised=True, eta=0)
+        else:
+            out = nat.p_sample(model_diffusion, x, vec_t, clip_denoised=True)
+    else:
+        if diffusion is None:
+            raise RuntimeError("model_fn: a model that is not a diffpir_b200.UNetModel needs the `diffusion` object")
+        sampler = diffusion.ddim_sample if ddim_sample else diffusion.p_sample
+        kw = dict(clip_denoised=True, denoised_fn=None, cond_fn=None, model_kwargs=model_kwargs)
+        if ddim_sample:
+            kw["eta"] = 0
+        out = sampler(model_diffusion, x, vec_t, **kw)
     if model_out_type == 'pred_x_prev_and_start':
         return out["sample"], out["pred_xstart"]
     if model_out_type == 'pred_x_prev':
         return out["sample"]
     if model_out_type == 'pred_xstart':
         return out["pred_xstart"]
-    if t_step is None:
-        t_step = int(vec_t.reshape(-1)[0].item())
-    alpha_prod_t = alphas_cumprod[int(t_step)]
+    if model_out_type not in ('epsilon', 'score'):
+        raise ValueError(f"unknown model_out_type {model_out_type!r}")
+    # :247-256.  The reference indexes alphas_cumprod[int(t_step)] (t_step only exists when vec_t was not given); with an
+    # explicit vec_t the first entry is used, indexed ON THE DEVICE (no .item(), no host sync)
+    if t_step is not None:
+        alpha_prod_t = alphas_cumprod[int(t_step)]
+    else:
+        alpha_prod_t = torch.index_select(alphas_cumprod.to(x.device), 0, vec_t.reshape(-1)[:1]).reshape(())
     beta_prod_t = 1 - alpha_prod_t
     e = (x - alpha_prod_t ** (0.5) * out["pred_xstart"]) / beta_prod_t ** (0.5)
     return e if model_out_type == 'epsilon' else - e / beta_prod_t ** (0.5)

@@ -131,8 +131,12 @@ def ibp_update(x0, y, down, gamma, rho, sf, out=None):
     x0 = x0.float().contiguous(); y = y.float().contiguous(); down = down.float().contiguous()
     H, W = x0.shape[-2:]
     N = x0.numel() // (H * W)
-    rho = float(rho.reshape(-1)[0].item()) if torch.is_tensor(rho) else float(rho)
     out = torch.empty_like(x0) if out is None else out
-    _lib.check(_lib.load().dpir_ibp_update(_lib.ptr(x0), _lib.ptr(y), _lib.ptr(down), float(gamma), rho, N, H, W, sf,
-                                           _lib.ptr(out), _lib.stream_ptr()), "dpir_ibp_update")
+    rho_dev = _lib.device_scalar(rho, x0.device)
+    if rho_dev is not None:        # rho lives on the GPU (main_ddpir.py:389): read it in the kernel, no host sync
+        _lib.check(_lib.load().dpir_ibp_update_dev(_lib.ptr(x0), _lib.ptr(y), _lib.ptr(down), float(gamma), _lib.ptr(rho_dev), N, H,
+                                                   W, sf, _lib.ptr(out), _lib.stream_ptr()), "dpir_ibp_update_dev")
+    else:
+        _lib.check(_lib.load().dpir_ibp_update(_lib.ptr(x0), _lib.ptr(y), _lib.ptr(down), float(gamma), float(rho), N, H, W, sf,
+                                               _lib.ptr(out), _lib.stream_ptr()), "dpir_ibp_update")
     return out

@@ -68,9 +68,15 @@ def data_solution_fused(x, FB, F2B, FBFy, alpha, sf, in_scale=1.0, in_bias=0.0, 
         spec = torch.empty(need, device=x.device, dtype=torch.float32)
     FBr = torch.view_as_real(FB) if FB.is_complex() else FB
     FYr = torch.view_as_real(FBFy) if FBFy.is_complex() else FBFy
-    _lib.check(lib.dpir_fft_solve(_plan(B * C, H, W, x.device), _lib.ptr(x), _lib.ptr(FBr), _lib.ptr(F2B), _lib.ptr(FYr),
-                                  _as_float(alpha), B, C, Bk, sf, in_scale, in_bias, out_scale, out_bias, blend,
-                                  _lib.ptr(spec), _lib.ptr(out), _lib.stream_ptr()), "dpir_fft_solve")
+    alpha_dev = _lib.device_scalar(alpha, x.device)
+    if alpha_dev is not None:      # alpha lives on the GPU (main_ddpir.py:389): read it in the kernel, no host sync
+        _lib.check(lib.dpir_fft_solve_dev(_plan(B * C, H, W, x.device), _lib.ptr(x), _lib.ptr(FBr), _lib.ptr(F2B), _lib.ptr(FYr),
+                                          _lib.ptr(alpha_dev), B, C, Bk, sf, in_scale, in_bias, out_scale, out_bias, blend,
+                                          _lib.ptr(spec), _lib.ptr(out), _lib.stream_ptr()), "dpir_fft_solve_dev")
+    else:
+        _lib.check(lib.dpir_fft_solve(_plan(B * C, H, W, x.device), _lib.ptr(x), _lib.ptr(FBr), _lib.ptr(F2B), _lib.ptr(FYr),
+                                      _as_float(alpha), B, C, Bk, sf, in_scale, in_bias, out_scale, out_bias, blend,
+                                      _lib.ptr(spec), _lib.ptr(out), _lib.stream_ptr()), "dpir_fft_solve")
     return out
 
 

@@ -42,6 +42,12 @@ extern "C" {
                                   reference's own use_fp16=True mode does, unet.py:620-632); GroupNorm statistics, softmax and
                                   all accumulation stay fp32/fp64: throughput mode */
 
+#define DPIR_PRECISION_FP16X3 3 /* split-precision tensor-core mode: every convolution operand is a pair of fp16 values
+                                  (hi = fp16(v), lo = fp16(v - hi)) and the tcgen05 K loop accumulates x_hi*w_hi + x_lo*w_hi +
+                                  x_hi*w_lo in fp32 (products exact, dropped term ~2^-24): fp32-equivalent convolutions at 3x
+                                  the MMA work; fp32 residual stream, exact SiLU, fp32 attention: the <=1e-4 rel-L2 parity
+                                  mode on tensor cores */
+
 const char *dpir_last_error(void);
 int dpir_version(void);
 /* number of CUDA kernels launched by this library on the calling thread since the last reset */
@@ -153,6 +159,12 @@ int dpir_fft_solve(dpir_fft_plan *plan_x, const float *x, const float *FB, const
                    float alpha, int32_t B, int32_t C, int32_t Bk, int32_t sf,
                    float in_scale, float in_bias, float out_scale, float out_bias, float blend,
                    float *spec, float *out, void *stream);
+/* the same with alpha read from DEVICE memory (alpha_dev points at one float): the reference drivers keep rho_t on the GPU
+ * (`tau = rhos[t_i].float().repeat(1,1,1,1)`, main_ddpir.py:389), so the drop-in path never synchronises the host */
+int dpir_fft_solve_dev(dpir_fft_plan *plan_x, const float *x, const float *FB, const float *F2B, const float *FBFy,
+                       const float *alpha_dev, int32_t B, int32_t C, int32_t Bk, int32_t sf,
+                       float in_scale, float in_bias, float out_scale, float out_bias, float blend,
+                       float *spec, float *out, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Elementwise steps of the loop (inline in the reference drivers).
@@ -161,6 +173,9 @@ int dpir_fft_solve(dpir_fft_plan *plan_x, const float *x, const float *FB, const
  *   x0_p = (mask*(y_scale*y + y_bias) + tau*x0)/(mask+tau); out = x0 + guidance*(x0_p - x0).  n elements. */
 int dpir_inpaint_prox(const float *x0, const float *y, const float *mask, float tau, float y_scale, float y_bias,
                       float guidance, float *out, int64_t n, void *stream);
+/* tau read from device memory (one float), see dpir_fft_solve_dev */
+int dpir_inpaint_prox_dev(const float *x0, const float *y, const float *mask, const float *tau_dev, float y_scale, float y_bias,
+                          float guidance, float *out, int64_t n, void *stream);
 /* re-noise, main_ddpir.py:451-456 with precomputed scalars:
  *   eps = (x - sa_t*x0)/s1_t;  out = sa_p*x0 + c_eps*eps + c_eta*noise_eta + c_zeta*noise_zeta
  * noise_eta may be NULL when c_eta == 0. */
@@ -171,6 +186,18 @@ int dpir_renoise(const float *x, const float *x0, const float *noise_eta, const 
  *   model_out dev (B,Cout>=3,H,W), x dev (B,3,H,W), coef dev (B,2) = (c1,c2) per sample. */
 int dpir_eps_to_x0(const float *model_out, const float *x, const float *coef, float *x0,
                    int32_t B, int32_t Cout, int32_t HW, int32_t clip, void *stream);
+/* diffusion.p_sample / diffusion.ddim_sample tails on the raw UNet output (gaussian_diffusion.py:258-311, 395-439, 537-585;
+ * reached from utils_model.model_fn with model_out_type 'pred_x_prev' / 'pred_x_prev_and_start' or ddim_sample=True,
+ * utils/utils_model.py:219-243), one elementwise pass:
+ *   x0 = clamp(c1 x - c2 eps);
+ *   mode 0 (p_sample, learned-range variance): sample = pm1 x0 + pm2 x + [t!=0] exp(0.5 (f max_log + (1-f) min_log)) noise,
+ *                                              f = (v+1)/2, v = model_out[:,3:6]
+ *   mode 1 (ddim_sample): sample = sqrt_ac_prev x0 + ce (c1 x - x0)/c2 + [t!=0] sigma noise
+ * model_out dev (B,Cout,HW); x, noise (or NULL), sample (or NULL), x0 (or NULL) dev (B,3,HW); t dev (B,) int64;
+ * tab dev [T][10] fp32 rows (c1, c2, pm1, pm2, min_log, max_log, sqrt_ac_prev, ce, sigma, 0) indexed by t (a t outside
+ * [0,T) traps, where the reference raises IndexError). */
+int dpir_sample_step(const float *model_out, const float *x, const float *noise, const int64_t *t, const float *tab, int32_t T,
+                     float *sample, float *x0, int32_t B, int32_t Cout, int32_t HW, int32_t mode, int32_t clip, void *stream);
 /* generic y = a*x + b (range conversions x/2+.5, 2x-1 around the operators) */
 int dpir_affine(const float *x, float a, float b, float *out, int64_t n, void *stream);
 
@@ -189,6 +216,9 @@ int dpir_resize_separable(const float *in, int32_t N, int32_t Hin, int32_t Win, 
  *   out = 2*((x0/2+.5) + gamma*nearest_up(y - down, sf)/(1+rho)) - 1 */
 int dpir_ibp_update(const float *x0, const float *y, const float *down, float gamma, float rho,
                     int32_t N, int32_t H, int32_t W, int32_t sf, float *out, void *stream);
+/* rho read from device memory (one float), see dpir_fft_solve_dev */
+int dpir_ibp_update_dev(const float *x0, const float *y, const float *down, float gamma, const float *rho_dev,
+                        int32_t N, int32_t H, int32_t W, int32_t sf, float *out, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Blur operator H (reference utils/utils_deblur.py:641-727 Blurkernel.forward: ReflectionPad2d(k//2) +
@@ -239,11 +269,12 @@ int dpir_gn_coef(const double *q1, const double *q2, int32_t C1, int32_t C2, con
 int dpir_conv_gnfuse_f16io(const void *src1, int32_t C1, const void *src2, int32_t C2, const float *coef, const void *w,
                            const float *bias, const void *residual_half, void *out_half, int32_t B, int32_t H, int32_t W,
                            int32_t Cout, int32_t CoutPad, void *stream);
-/* 1 (default): eligible ResBlocks of the fp16s pipeline run GroupNorm+SiLU inside their convolutions (above) with fp32
- * operand arithmetic (bit-identical activation values to the separate pass); 2: packed-half arithmetic (tanh.approx.f16x2);
- * 0: every norm is a separate k_gn_apply pass; 3: EXPERIMENTAL producers that activate each element once per 64-channel chunk
- * (k_conv3x3_v3<3>; builds, not yet validated on hardware, never selected by default).  Process-wide; drops the cached plans
- * of `e` (may be NULL). */
+/* GroupNorm+SiLU inside the convolutions of eligible ResBlocks (fp16s pipeline).  1 (default; 3 is an alias): producers that
+ * activate each input element once per 64-channel chunk and publish the three horizontal tap boxes from registers
+ * (k_conv3x3_v3<3>, fp32 operand arithmetic = the activation values of the separate pass); 4: round-1 producers (one
+ * activation per tap box, fp32 arithmetic); 2: the same with packed-half arithmetic (tanh.approx.f16x2); 0: every norm is a
+ * separate k_gn_apply pass.  Per engine (drops the cached plans of `e`); with e == NULL it sets the flavour used by the
+ * per-kernel test entry dpir_conv_gnfuse_f16io. */
 int dpir_set_gn_fusion(dpir_engine *e, int32_t enable);
 /* A/B switch for tests and benchmarks.  0 (default): 3x3 convs on >=16x16 maps use the persistent swap-AB halo-reuse
  * kernel (k_conv3x3_v3), everything else the one-tile-per-CTA kernel (k_conv_tc); 1: k_conv_tc everywhere;

@@ -117,7 +117,7 @@ def gen_misc():
     return res
 
 
-def reference_loop(model, diffusion, task, y, k, mask, sf, hp, iters, init_noise, zeta_noise, x_init):
+def reference_loop(model, diffusion, task, y, k, mask, sf, hp, iters, init_noise, zeta_noise, x_init, iter_num_U=1, u_noise=None):
     """main_ddpir.py:259-470 (DiffPIR / sub_1_analytic / pred_xstart branch), with the reference's own model_fn,
     pre_calculate and data_solution, and the torch.randn_like draws replaced by the pre-drawn tensors."""
     from utils import utils_model, utils_sisr as sr
@@ -143,27 +143,37 @@ def reference_loop(model, diffusion, task, y, k, mask, sf, hp, iters, init_noise
     seq = [int(s) for s in list(seq)]
     seq[-1] = seq[-1] - 1
     zeta, eta = hp["zeta"], 0.0
+    nz = nu = 0
     for i in range(len(seq)):
         curr_sigma = sigmas[seq[i]].cpu().numpy()
         t_i = utils_model.find_nearest(reduced_alpha_cumprod, curr_sigma)
-        x0 = utils_model.model_fn(x, noise_level=curr_sigma * 255, model_out_type="pred_xstart", model_diffusion=model,
-                                  diffusion=diffusion, ddim_sample=False, alphas_cumprod=alphas_cumprod)
-        if seq[i] != seq[-1]:
-            tau = rhos[t_i].float().repeat(1, 1, 1, 1)
-            if task == "inpaint":
-                x0_p = (mask * (2 * y - 1) + tau * x0).div(mask + tau)
-                x0 = x0 + 1.0 * (x0_p - x0)
-            else:
-                x0_p = x0 / 2 + 0.5
-                x0_p = sr.data_solution(x0_p.float(), FB, FBC, F2B, FBFy, tau, sf)
-                x0_p = x0_p * 2 - 1
-                x0 = x0 + 1.0 * (x0_p - x0)
-            t_im1 = utils_model.find_nearest(reduced_alpha_cumprod, sigmas[seq[i + 1]].cpu().numpy())
-            eps = (x - sqrt_alphas_cumprod[t_i] * x0) / sqrt_1m_alphas_cumprod[t_i]
-            eta_sigma = eta * sqrt_1m_alphas_cumprod[t_im1] / sqrt_1m_alphas_cumprod[t_i] * torch.sqrt(betas[t_i])
-            x = sqrt_alphas_cumprod[t_im1] * x0 + np.sqrt(1 - zeta) * (
-                torch.sqrt(sqrt_1m_alphas_cumprod[t_im1] ** 2 - eta_sigma ** 2) * eps
-                + eta_sigma * torch.zeros_like(x)) + np.sqrt(zeta) * sqrt_1m_alphas_cumprod[t_im1] * zeta_noise[i]
+        # main_ddpir.py:349 `for u in range(config.iter_num_U)`.  On the final sequence entry the reference's re-noise would
+        # index seq[i+1] for u < iter_num_U-1 (IndexError), so the repeats only exist before it.
+        for u in range(iter_num_U if seq[i] != seq[-1] else 1):
+            x0 = utils_model.model_fn(x, noise_level=curr_sigma * 255, model_out_type="pred_xstart", model_diffusion=model,
+                                      diffusion=diffusion, ddim_sample=False, alphas_cumprod=alphas_cumprod)
+            if seq[i] != seq[-1]:
+                tau = rhos[t_i].float().repeat(1, 1, 1, 1)
+                if task == "inpaint":
+                    x0_p = (mask * (2 * y - 1) + tau * x0).div(mask + tau)
+                    x0 = x0 + 1.0 * (x0_p - x0)
+                else:
+                    x0_p = x0 / 2 + 0.5
+                    x0_p = sr.data_solution(x0_p.float(), FB, FBC, F2B, FBFy, tau, sf)
+                    x0_p = x0_p * 2 - 1
+                    x0 = x0 + 1.0 * (x0_p - x0)
+                t_im1 = utils_model.find_nearest(reduced_alpha_cumprod, sigmas[seq[i + 1]].cpu().numpy())
+                eps = (x - sqrt_alphas_cumprod[t_i] * x0) / sqrt_1m_alphas_cumprod[t_i]
+                eta_sigma = eta * sqrt_1m_alphas_cumprod[t_im1] / sqrt_1m_alphas_cumprod[t_i] * torch.sqrt(betas[t_i])
+                x = sqrt_alphas_cumprod[t_im1] * x0 + np.sqrt(1 - zeta) * (
+                    torch.sqrt(sqrt_1m_alphas_cumprod[t_im1] ** 2 - eta_sigma ** 2) * eps
+                    + eta_sigma * torch.zeros_like(x)) + np.sqrt(zeta) * sqrt_1m_alphas_cumprod[t_im1] * zeta_noise[nz]
+                nz += 1
+                if u < iter_num_U - 1:                   # :460-467 set back to x_t from x_{t-1}
+                    sqrt_alpha_effective = sqrt_alphas_cumprod[t_i] / sqrt_alphas_cumprod[t_im1]
+                    x = sqrt_alpha_effective * x + torch.sqrt(sqrt_1m_alphas_cumprod[t_i] ** 2 -
+                                                              sqrt_alpha_effective ** 2 * sqrt_1m_alphas_cumprod[t_im1] ** 2) * u_noise[nu]
+                    nu += 1
     return x / 2 + 0.5
 
 
@@ -203,6 +213,59 @@ def gen_loops(iters=6):
         with torch.no_grad():
             out = reference_loop(model, diffusion, task, y, k, mask, sf, hp, iters, init, zs, x_init)
         res[task + "_x0"] = out.numpy()
+    return res
+
+
+def gen_loop_u2(iters=4):
+    """The same loop with iter_num_U = 2 (main_ddpir.py:349, 460-467), deblur."""
+    cfg = small_cfg()
+    model, diffusion = ref_shim.create_reference_model(ref_shim.ref_model_config(cfg))
+    model.load_state_dict(synth.synthetic_state_dict(cfg, 0))
+    task, sf, hp = LOOP_CASES[0]
+    gt, y, k, mask = loop_inputs(task, sf=sf)
+    init, zs = synth.predrawn_noise((2, 3, 64, 64), 2 * iters, seed=8)
+    _, us = synth.predrawn_noise((2, 3, 64, 64), iters, seed=9)
+    with torch.no_grad():
+        out = reference_loop(model, diffusion, task, y, k, mask, sf, hp, iters, init, zs, None, iter_num_U=2, u_noise=us)
+    return {"iters": np.array(iters), "deblur_U2_x0": out.numpy()}
+
+
+MODEL_FN_SEED = 4321
+
+
+def model_fn_inputs():
+    g = torch.Generator().manual_seed(21)
+    return torch.randn(2, 3, 64, 64, generator=g), 37.0          # x, noise_level (255 * sigma)
+
+
+def gen_model_fn():
+    """utils_model.model_fn (utils/utils_model.py:207-258) for every output type, p_sample and ddim_sample, small UNet.  The
+    reference draws its noise with th.randn_like(x) from the global generator: seeded with MODEL_FN_SEED right before each call,
+    so a test can re-draw the identical tensor on the CPU."""
+    from utils import utils_model
+    cfg = small_cfg()
+    model, diffusion = ref_shim.create_reference_model(ref_shim.ref_model_config(cfg))
+    model.load_state_dict(synth.synthetic_state_dict(cfg, 0))
+    x, nl = model_fn_inputs()
+    betas = torch.from_numpy(np.linspace(0.0001, 0.02, 1000, dtype=np.float32))
+    alphas_cumprod = np.cumprod((1.0 - betas).cpu(), axis=0)
+    res = {}
+    with torch.no_grad():
+        for ddim in (False, True):
+            tag = "ddim" if ddim else "p"
+            for typ in ("pred_xstart", "pred_x_prev", "epsilon", "score"):
+                torch.manual_seed(MODEL_FN_SEED)
+                res[f"{tag}_{typ}"] = utils_model.model_fn(x, noise_level=nl, model_out_type=typ, model_diffusion=model,
+                                                           diffusion=diffusion, ddim_sample=ddim, alphas_cumprod=alphas_cumprod).numpy()
+            torch.manual_seed(MODEL_FN_SEED)
+            a, b = utils_model.model_fn(x, noise_level=nl, model_out_type="pred_x_prev_and_start", model_diffusion=model,
+                                        diffusion=diffusion, ddim_sample=ddim, alphas_cumprod=alphas_cumprod)
+            res[f"{tag}_both_prev"], res[f"{tag}_both_start"] = a.numpy(), b.numpy()
+        # explicit vec_t including t = 0 (no noise added there, gaussian_diffusion.py:431-433)
+        vt = torch.tensor([0, 500])
+        torch.manual_seed(MODEL_FN_SEED)
+        res["p_vec_t_prev"] = utils_model.model_fn(x, noise_level=0, vec_t=vt, model_out_type="pred_x_prev", model_diffusion=model,
+                                                   diffusion=diffusion, alphas_cumprod=alphas_cumprod).numpy()
     return res
 
 
@@ -252,7 +315,7 @@ def gen_imresize():
 
 
 FILES = {"imresize.npz": gen_imresize, "test_mode.npz": gen_test_mode, "unet_small.npz": gen_unet_small, "unet_ffhq.npz": gen_unet_ffhq, "sisr.npz": gen_sisr,
-         "misc.npz": gen_misc, "loops.npz": gen_loops}
+         "misc.npz": gen_misc, "loops.npz": gen_loops, "loop_u2.npz": gen_loop_u2, "model_fn.npz": gen_model_fn}
 
 
 def main(check=False):

@@ -164,9 +164,9 @@ def _quad_stats(xh):
     return torch.stack([v.sum(dim=(1, 3)), (v * v).sum(dim=(1, 3))], dim=-1).contiguous()
 
 
-# "3" = k_conv3x3_v3<3> (activate-once producers): written in round 1, not yet validated on hardware, never the default;
-# DPIR_TEST_EXPERIMENTAL=1 adds it to the parity runs
-_FUSE_MODES = ["1", "2"] + (["3"] if os.environ.get("DPIR_TEST_EXPERIMENTAL") == "1" else [])
+# dpir_set_gn_fusion flavours: "1" = activate-once producers (k_conv3x3_v3<3>, the default since round 2), "4" = round-1
+# per-tap-box producers with fp32 arithmetic, "2" = per-tap-box with packed-half arithmetic
+_FUSE_MODES = ["1", "4", "2"]
 
 
 @pytest.mark.parametrize("math", _FUSE_MODES)
@@ -183,7 +183,7 @@ def test_conv_gn_fused_matches_torch(B, H, W, C1, C2, Cout, residual, film, math
     """k_conv3x3_v3<FUSE>: out = conv3x3(SiLU(FiLM(GroupNorm(x1|x2)))) + bias (+ residual), the norm evaluated inside the conv."""
     from diffpir_b200 import _lib
     lib = _lib.load()
-    _lib.check(lib.dpir_set_gn_fusion(None, int(math)), "dpir_set_gn_fusion")     # 1: fp32 operand arithmetic, 2: packed half
+    _lib.check(lib.dpir_set_gn_fusion(None, int(math)), "dpir_set_gn_fusion")
     C = C1 + C2
     g = torch.Generator().manual_seed(11)
     x = torch.randn(B, C, H, W, generator=g) * 1.7 + 0.6 * torch.randn(B, C, 1, 1, generator=g)

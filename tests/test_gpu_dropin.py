@@ -1,0 +1,252 @@
+"""The drop-in surface ON THE GPU: the reference drivers' own loop arithmetic (main_ddpir.py:341-470, re-typed exactly as
+oracle/gen_golden.py:reference_loop does for the goldens) driven with diffpir_b200.utils_model.model_fn,
+utils_sisr.pre_calculate / data_solution and CUDA tensors - i.e. what a reference user gets after install() - against the
+goldens the UNMODIFIED reference produced (tests/golden/loops.npz, model_fn.npz, loop_u2.npz).  Also proves that the step
+performs no host synchronisation (torch sync-debug mode 'error' around the loop body)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from diffpir_b200 import synth
+from dpir_testutil import make_model, rel_l2, small_config
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+LOOP_CASES = [("deblur", 1, dict(lambda_=7.0, zeta=0.3, sigma=0.05)),
+              ("sr", 4, dict(lambda_=6.0, zeta=0.25, sigma=0.05)),
+              ("inpaint", 1, dict(lambda_=1.0, zeta=1.0, sigma=0.0))]
+
+
+def _loop_inputs(task, B=2, size=64, sf=1):
+    """oracle/gen_golden.py:loop_inputs (same seeds)."""
+    imgs = synth.synthetic_images(B, size, seed=100)
+    gt = torch.from_numpy(imgs).permute(0, 3, 1, 2).float() / 255.0
+    k = mask = None
+    if task == "deblur":
+        kk = synth.gaussian_kernel(21, 2.0)
+        y = np.stack([synth.blur_measurement(imgs[b], kk, 0.05, seed=b) for b in range(B)])
+        y = torch.from_numpy(y).permute(0, 3, 1, 2).contiguous()
+        k = torch.from_numpy(kk)[None, None].repeat(B, 1, 1, 1)
+    elif task == "sr":
+        kk = synth.gaussian_kernel(25, 1.6)
+        k = torch.from_numpy(kk)[None, None].repeat(B, 1, 1, 1)
+        y = torch.nn.functional.avg_pool2d(gt, sf)
+    else:
+        y = gt.clone()
+        mask = synth.random_mask(B, size, 0.5, seed=3)
+    return gt, y, k, mask
+
+
+def _driver_loop(model, task, y, k, mask, sf, hp, iters, init_noise, zeta_noise, x_init, dev, sync_check=True):
+    """main_ddpir.py:259-470 with the module attributes a patched driver resolves (utils_model.model_fn, sr.pre_calculate,
+    sr.data_solution); every tensor lives on `dev` like in the driver (rhos, sigmas, schedule tables: main_ddpir.py:184-190,
+    274-286 are created on config.device)."""
+    from diffpir_b200 import utils_model, utils_sisr as sr
+    T = 1000
+    betas = torch.from_numpy(np.linspace(0.0001, 0.02, T, dtype=np.float32)).to(dev)
+    alphas = 1.0 - betas
+    alphas_cumprod = np.cumprod(alphas.cpu(), axis=0)                     # :187 (stays on the CPU in the driver)
+    sqrt_alphas_cumprod = torch.sqrt(alphas_cumprod)
+    sqrt_1m_alphas_cumprod = torch.sqrt(1. - alphas_cumprod)
+    reduced_alpha_cumprod = torch.div(sqrt_1m_alphas_cumprod, sqrt_alphas_cumprod)
+    sigma = max(0.001, hp["sigma"])
+    sigmas, rhos = [], []
+    for i in range(T):
+        sigmas.append(reduced_alpha_cumprod[T - 1 - i])
+        rhos.append(hp["lambda_"] * (sigma ** 2) / ((sqrt_1m_alphas_cumprod[i] / sqrt_alphas_cumprod[i]) ** 2))
+    rhos, sigmas = torch.tensor(rhos).to(dev), torch.tensor(sigmas).to(dev)         # :285 on the device
+    sigmas_host = sigmas.cpu().numpy()                                              # the driver syncs here per step (:342); hoisted
+    t_start = T - 1
+    x = y * mask if task == "inpaint" else (x_init if x_init is not None else y)
+    x = sqrt_alphas_cumprod[t_start] * (2 * x - 1) + sqrt_1m_alphas_cumprod[t_start] * init_noise
+    if task in ("sr", "deblur"):
+        FB, FBC, F2B, FBFy = sr.pre_calculate(y, k, sf)
+    seq = np.sqrt(np.linspace(0, T ** 2, iters))
+    seq = [int(s) for s in list(seq)]
+    seq[-1] = seq[-1] - 1
+    zeta, eta = hp["zeta"], 0.0
+    sa_d, s1_d = sqrt_alphas_cumprod.to(dev), sqrt_1m_alphas_cumprod.to(dev)
+    torch.cuda.synchronize()
+    for i in range(len(seq)):
+        curr_sigma = sigmas_host[seq[i]]
+        t_i = utils_model.find_nearest(reduced_alpha_cumprod, curr_sigma)
+        if sync_check:
+            torch.cuda.set_sync_debug_mode("error")       # any .item() / blocking copy inside the step raises
+        try:
+            x0 = utils_model.model_fn(x, noise_level=curr_sigma * 255, model_out_type="pred_xstart", model_diffusion=model,
+                                      diffusion=None, ddim_sample=False, alphas_cumprod=alphas_cumprod)
+            if seq[i] != seq[-1]:
+                tau = rhos[t_i].float().repeat(1, 1, 1, 1)                 # :389 a CUDA tensor
+                if task == "inpaint":
+                    x0_p = (mask * (2 * y - 1) + tau * x0).div(mask + tau)
+                    x0 = x0 + 1.0 * (x0_p - x0)
+                else:
+                    x0_p = x0 / 2 + 0.5
+                    x0_p = sr.data_solution(x0_p.float(), FB, FBC, F2B, FBFy, tau, sf)
+                    x0_p = x0_p * 2 - 1
+                    x0 = x0 + 1.0 * (x0_p - x0)
+                t_im1 = utils_model.find_nearest(reduced_alpha_cumprod, sigmas_host[seq[i + 1]])
+                eps = (x - sa_d[t_i] * x0) / s1_d[t_i]
+                eta_sigma = eta * s1_d[t_im1] / s1_d[t_i] * torch.sqrt(betas[t_i])
+                x = sa_d[t_im1] * x0 + np.sqrt(1 - zeta) * (
+                    torch.sqrt(s1_d[t_im1] ** 2 - eta_sigma ** 2) * eps
+                    + eta_sigma * torch.zeros_like(x)) + np.sqrt(zeta) * s1_d[t_im1] * zeta_noise[i]
+        finally:
+            torch.cuda.set_sync_debug_mode("default")
+    return x / 2 + 0.5
+
+
+@pytest.mark.parametrize("task,sf,hp", LOOP_CASES)
+def test_driver_loop_on_gpu_matches_reference_golden(task, sf, hp):
+    """fp32 engine under the reference's loop arithmetic, CUDA tensors, vs the golden of the unmodified reference."""
+    gold = np.load(os.path.join(GOLD, "loops.npz"))
+    iters = int(gold["iters"])
+    dev = torch.device("cuda")
+    gt, y, k, mask = _loop_inputs(task, sf=sf)
+    init, zs = synth.predrawn_noise((2, 3, 64, 64), iters, seed=7)
+    x_init = torch.nn.functional.interpolate(y, scale_factor=sf, mode="bicubic", align_corners=False) if task == "sr" else None
+    model = make_model(small_config(), "fp32")
+    c = lambda v: v.to(dev) if v is not None else None     # noqa: E731
+    out = _driver_loop(model, task, c(y), c(k), c(mask), sf, hp, iters, c(init), [z.to(dev) for z in zs], c(x_init), dev)
+    ref = torch.from_numpy(gold[task + "_x0"])
+    # The golden is the reference's own fp32 run: its FFT prox loses digits at small rho ((FR - ...)/alpha, utils_sisr.py:70-72;
+    # SURVEY.md section 7 #2), so it sits `dev` away from the fp64 evaluation of the same formulae.  Our path is scored against
+    # fp64 with the usual bar max(1e-4, 1.5 dev) and must be at least as close to fp64 as the reference's golden is.
+    from oracle import diffpir_oracle as orc
+    from dpir_testutil import weights
+    cfg = small_config()
+    d = lambda v: v.double() if v is not None else None      # noqa: E731
+    ref64 = orc.diffpir_loop(weights(cfg), cfg.as_dict(), task, d(y), k=d(k), mask=d(mask), sf=sf, iter_num=iters,
+                             init_noise=d(init), zeta_noise=[z.double() for z in zs], x_init=d(x_init), **hp)
+    dev = rel_l2(ref, ref64)
+    err64, err_gold = rel_l2(out, ref64), rel_l2(out, ref)
+    print(f"drop-in loop {task}: rel-L2 vs fp64 oracle {err64:.3e}, vs reference fp32 golden {err_gold:.3e} "
+          f"(golden vs fp64: {dev:.3e})")
+    assert err64 < max(1e-4, 1.5 * dev), (err64, dev)
+    assert err_gold < max(1e-4, 2.5 * dev), (err_gold, dev)
+
+
+def test_prox_scalars_on_device_need_no_sync():
+    """alpha / tau / rho passed as CUDA tensors (main_ddpir.py:389) are read inside the kernels: same result as host floats,
+    no host synchronisation."""
+    from diffpir_b200 import ops, utils_sisr as sr
+    from diffpir_b200.utils_resizer import Resizer, ibp_update
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(2, 3, 64, 64, generator=g).to(dev)
+    y = torch.rand(2, 3, 64, 64, generator=g).to(dev)
+    k = torch.rand(1, 1, 9, 9, generator=g).to(dev)
+    k = k / k.sum()
+    mask = (torch.rand(2, 3, 64, 64, generator=g) > 0.5).float().to(dev)
+    t = sr.pre_calculate(y, k, 1)
+    a_host, a_dev = 0.0123, torch.tensor(0.0123, device=dev).repeat(1, 1, 1, 1)
+    ylr = torch.rand(2, 3, 16, 16, generator=g).to(dev)
+    down = Resizer((2, 3, 64, 64), 0.25).to(dev)(x)
+    torch.cuda.synchronize()
+    r_host = [sr.data_solution(x, *t, a_host, 1), ops.inpaint_prox(x, y, mask, a_host), ibp_update(x, ylr, down, 0.01, a_host, 4)]
+    torch.cuda.set_sync_debug_mode("error")
+    try:
+        r_dev = [sr.data_solution(x, *t, a_dev, 1), ops.inpaint_prox(x, y, mask, a_dev), ibp_update(x, ylr, down, 0.01, a_dev, 4)]
+    finally:
+        torch.cuda.set_sync_debug_mode("default")
+    for a, b in zip(r_host, r_dev):
+        assert torch.equal(a, b)
+
+
+MODEL_FN_SEED = 4321
+
+
+@pytest.mark.parametrize("ddim", [False, True])
+def test_model_fn_output_types_match_reference(ddim, monkeypatch):
+    """utils_model.model_fn for every output type (p_sample and ddim_sample), native UNet + dpir_sample_step, vs goldens from
+    the reference's model_fn / p_sample / ddim_sample.  The reference's th.randn_like draw is reproduced on the CPU with the
+    same seed and injected."""
+    from diffpir_b200 import utils_model
+    gold = np.load(os.path.join(GOLD, "model_fn.npz"))
+    dev = torch.device("cuda")
+    x = torch.randn(2, 3, 64, 64, generator=torch.Generator().manual_seed(21))
+    torch.manual_seed(MODEL_FN_SEED)
+    noise = torch.randn_like(x)
+    monkeypatch.setattr(torch, "randn_like", lambda t_, **kw: noise.to(t_.device))
+    model = make_model(small_config(), "fp32")
+    betas = torch.from_numpy(np.linspace(0.0001, 0.02, 1000, dtype=np.float32))
+    alphas_cumprod = np.cumprod((1.0 - betas).cpu(), axis=0)
+    tag = "ddim" if ddim else "p"
+    xd = x.to(dev)
+    for typ in ("pred_xstart", "pred_x_prev", "epsilon", "score"):
+        out = utils_model.model_fn(xd, noise_level=37.0, model_out_type=typ, model_diffusion=model, diffusion=None,
+                                   ddim_sample=ddim, alphas_cumprod=alphas_cumprod)
+        err = rel_l2(out, torch.from_numpy(gold[f"{tag}_{typ}"]))
+        print(f"model_fn {tag} {typ}: rel-L2 {err:.2e}")
+        assert err < 2e-5, (typ, err)
+    a, b = utils_model.model_fn(xd, noise_level=37.0, model_out_type="pred_x_prev_and_start", model_diffusion=model,
+                                diffusion=None, ddim_sample=ddim, alphas_cumprod=alphas_cumprod)
+    assert rel_l2(a, torch.from_numpy(gold[f"{tag}_both_prev"])) < 2e-5
+    assert rel_l2(b, torch.from_numpy(gold[f"{tag}_both_start"])) < 2e-5
+    if not ddim:
+        vt = torch.tensor([0, 500], device=dev)
+        out = utils_model.model_fn(xd, noise_level=0, vec_t=vt, model_out_type="pred_x_prev", model_diffusion=model,
+                                   diffusion=None, alphas_cumprod=alphas_cumprod)
+        assert rel_l2(out, torch.from_numpy(gold["p_vec_t_prev"])) < 2e-5
+        # epsilon / score with an explicit vec_t index alphas_cumprod on the device (no .item())
+        torch.cuda.synchronize()
+        torch.cuda.set_sync_debug_mode("error")
+        try:
+            e = utils_model.model_fn(xd, noise_level=0, vec_t=torch.full((2,), 500, device=dev), model_out_type="epsilon",
+                                     model_diffusion=model, diffusion=None, alphas_cumprod=alphas_cumprod.to(dev))
+        finally:
+            torch.cuda.set_sync_debug_mode("default")
+        assert torch.isfinite(e).all()
+
+
+def test_timestep_out_of_range_is_safe():
+    """A timestep outside [0, diffusion_steps) would index past the FiLM / eps->x0 tables (the reference raises IndexError;
+    ADVICE r1).  Host-side timesteps are validated and raise; device-side ones cannot be read without a sync, so the engine
+    clamps them before any table lookup."""
+    model = make_model(small_config(), "fp16")
+    x = torch.randn(1, 3, 64, 64, device="cuda")
+    with pytest.raises(ValueError):
+        model.x0(x, [1000])
+    with pytest.raises(ValueError):
+        model.x0(x, torch.tensor([-1]))
+    a = model.x0(x, torch.tensor([1000], device="cuda"))
+    b = model.x0(x, torch.tensor([999], device="cuda"))
+    assert torch.isfinite(a).all() and torch.equal(a, b)
+
+
+def test_iter_num_U_matches_reference_golden():
+    """DiffPIRSampler(iter_num_U=2) vs the reference loop arithmetic with the inner repeats (main_ddpir.py:349, 460-467)."""
+    from diffpir_b200.sampler import DiffPIRSampler
+    gold = np.load(os.path.join(GOLD, "loop_u2.npz"))
+    iters = int(gold["iters"])
+    task, sf, hp = LOOP_CASES[0]
+    gt, y, k, mask = _loop_inputs(task)
+    init, zs = synth.predrawn_noise((2, 3, 64, 64), 2 * iters, seed=8)
+    _, us = synth.predrawn_noise((2, 3, 64, 64), iters, seed=9)
+    model = make_model(small_config(), "fp32")
+    out = DiffPIRSampler(model, task, iter_num=iters, iter_num_U=2, **hp).run(
+        y.cuda(), k=k.cuda(), init_noise=init.cuda(), zeta_noise=[z.cuda() for z in zs], u_noise=[u.cuda() for u in us])
+    err = rel_l2(out, torch.from_numpy(gold["deblur_U2_x0"]))
+    print(f"iter_num_U=2 deblur: rel-L2 vs reference golden {err:.3e}")
+    assert err < 5e-4, err
+
+
+def test_sr_default_start_is_the_bicubic_upsample():
+    """x_init=None for task 'sr' starts from F.interpolate(y, bicubic) like main_ddpir.py:295 (it used to start
+    from the LR measurement itself)."""
+    from diffpir_b200.sampler import DiffPIRSampler
+    task, sf, hp = LOOP_CASES[1]
+    gt, y, k, mask = _loop_inputs(task, sf=sf)
+    init, zs = synth.predrawn_noise((2, 3, 64, 64), 3, seed=7)
+    model = make_model(small_config(), "fp16")
+    s = DiffPIRSampler(model, task, sf=sf, iter_num=3, **hp)
+    kw = dict(k=k.cuda(), init_noise=init.cuda(), zeta_noise=[z.cuda() for z in zs])
+    a = s.run(y.cuda(), **kw)
+    xi = torch.nn.functional.interpolate(y, scale_factor=sf, mode="bicubic", align_corners=False)
+    b = s.run(y.cuda(), x_init=xi.cuda(), **kw)
+    assert a.shape[-2:] == (64, 64) and rel_l2(a, b) < 1e-6
+    with pytest.raises(ValueError):
+        s.run(y.cuda(), x_init=y.cuda(), **kw)

@@ -39,7 +39,7 @@ CASES = [
 
 
 @pytest.mark.parametrize("task,sf,hp", CASES)
-@pytest.mark.parametrize("precision", ["fp32", "fp16", "fp16s"])
+@pytest.mark.parametrize("precision", ["fp32", "fp16x3", "fp16", "fp16s"])
 def test_loop_matches_oracle(task, sf, hp, precision):
     from diffpir_b200.sampler import DiffPIRSampler
     cfg = small_config()
@@ -68,7 +68,8 @@ def test_loop_matches_oracle(task, sf, hp, precision):
                 x_init=(x_init.cuda() if x_init is not None else None), init_noise=init.cuda(),
                 zeta_noise=[z.cuda() for z in zs], trace=tr)
     assert len(tr) == len(tr_ref)
-    tol = max(1e-4, 1.5 * ref_dev) if precision == "fp32" else (1e-2 if precision == "fp16" else 2e-2)
+    strict = precision in ("fp32", "fp16x3")      # the two modes that meet north_star's 1e-4 rel-L2 bar
+    tol = max(1e-4, 1.5 * ref_dev) if strict else (1e-2 if precision == "fp16" else 2e-2)
     print(f"loop {task} {precision}: final rel-L2 {rel_l2(out, ref):.3e}, dPSNR {abs(psnr(out, gt) - psnr(ref, gt)):.5f} dB")
     worst = 0.0
     for (n1, i1, a), (n2, i2, b) in zip(tr, tr_ref):
@@ -77,7 +78,7 @@ def test_loop_matches_oracle(task, sf, hp, precision):
     assert rel_l2(out, ref) < tol, (rel_l2(out, ref), worst, ref_dev)
     # north-star bar: PSNR against ground truth within 0.01 dB of the reference path
     assert abs(psnr(out, gt) - psnr(ref, gt)) < 0.01
-    if precision == "fp32":
+    if strict:
         assert worst < 5e-4, worst
 
 

@@ -10,7 +10,9 @@ from dpir_testutil import make_model, rel_l2, small_config, weights
 
 pytestmark = pytest.mark.gpu
 
-TOL = {"fp32": 1e-4, "fp16": 4e-3, "fp16s": 6e-3}   # rel-L2 of the eps prediction; fp16 = operand rounding of ~60 chained GEMMs
+# rel-L2 of the eps prediction.  fp32 (CUDA cores) and fp16x3 (split-precision tensor cores: 3 MMA passes per conv, fp32-equivalent)
+# meet north_star's 1e-4 bar; fp16 / fp16s = single-pass operand rounding of ~60 chained GEMMs (PSNR bar only)
+TOL = {"fp32": 1e-4, "fp16x3": 1e-4, "fp16": 4e-3, "fp16s": 6e-3}
 
 
 def _inputs(B, size, seed=0):
@@ -18,7 +20,7 @@ def _inputs(B, size, seed=0):
     return torch.randn(B, 3, size, size, generator=g), torch.randint(0, 1000, (B,), generator=g)
 
 
-@pytest.mark.parametrize("precision", ["fp32", "fp16", "fp16s"])
+@pytest.mark.parametrize("precision", ["fp32", "fp16x3", "fp16", "fp16s"])
 def test_small_unet_forward_matches_oracle(precision):
     cfg = small_config()
     sd = weights(cfg)
@@ -37,7 +39,7 @@ def test_small_unet_forward_matches_oracle(precision):
     assert torch.equal(out3, out)
 
 
-@pytest.mark.parametrize("precision", ["fp32", "fp16", "fp16s"])
+@pytest.mark.parametrize("precision", ["fp32", "fp16x3", "fp16", "fp16s"])
 def test_small_unet_x0_matches_oracle(precision):
     cfg = small_config()
     sd = weights(cfg)
@@ -49,7 +51,7 @@ def test_small_unet_x0_matches_oracle(precision):
     x0 = m.x0(x.cuda(), t.cuda())
     # before the clamp the error of eps is amplified by sqrt(1/abar - 1) (157 at t=999): compare where not saturated too
     assert float(x0.max()) <= 1 and float(x0.min()) >= -1
-    assert rel_l2(x0, ref) < (2e-4 if precision == "fp32" else 3e-2)
+    assert rel_l2(x0, ref) < (2e-4 if precision in ("fp32", "fp16x3") else 3e-2)
     # the fused epilogue must agree with the unfused route on the same engine
     from diffpir_b200 import ops
     tabs = orc.diffusion_tables()
@@ -74,7 +76,7 @@ def test_graph_mode_matches_stream_mode():
     assert torch.equal(d, m(x2.cuda(), t2.cuda()))
 
 
-@pytest.mark.parametrize("precision", ["fp32", "fp16", "fp16s"])
+@pytest.mark.parametrize("precision", ["fp32", "fp16x3", "fp16", "fp16s"])
 def test_ffhq_unet_forward_matches_oracle(precision):
     """The real diffusion_ffhq_10m architecture at 256x256, one image."""
     from diffpir_b200 import arch
@@ -117,7 +119,7 @@ def test_imagenet_unet_forward_matches_oracle():
     x, _ = _inputs(1, 256, seed=5)
     t = torch.tensor([77])
     ref = unet_oracle.unet_forward(sd, cfg.as_dict(), x, t)
-    for precision in ("fp16", "fp16s"):
+    for precision in ("fp16", "fp16s", "fp16x3"):
         m = make_model(cfg, precision)
         out = m(x.cuda(), t.cuda())
         err = rel_l2(out, ref)
@@ -126,10 +128,10 @@ def test_imagenet_unet_forward_matches_oracle():
         del m
 
 
-@pytest.mark.parametrize("mode", [1, 2] + ([3] if os.environ.get("DPIR_TEST_EXPERIMENTAL") == "1" else []))
+@pytest.mark.parametrize("mode", [1, 4, 2])
 def test_gn_fusion_equivalence(mode):
     """fp16s: ResBlock GroupNorm+SiLU evaluated inside the convolutions (v4 kernel) vs as separate passes - same network, the
-    only difference is where the activated operand is rounded to fp16 (mode 1: identical arithmetic) -> agreement far inside
+    only difference is where the activated operand is rounded to fp16 (modes 1 and 4: identical arithmetic) -> agreement far inside
     the fp16 tolerance; both against the oracle."""
     cfg = small_config()
     sd = weights(cfg)

@@ -23,7 +23,7 @@ def main():
     ap.add_argument("--json", default="")
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--variant", type=int, default=0, help="dpir_conv_tc_variant: 0 auto (v3), 1 v1, 2 v2")
-    ap.add_argument("--gn-fusion", type=int, default=1, help="0 separate GroupNorm passes, 1 fused into the convs (fp32 math), 2 (half math)")
+    ap.add_argument("--gn-fusion", type=int, default=1, help="0 separate GroupNorm passes, 1 fused into the convs (activate-once producers), 4 round-1 per-tap producers, 2 per-tap half math")
     a = ap.parse_args()
     from diffpir_b200 import _lib
     _lib.check(_lib.load().dpir_conv_tc_variant(a.variant), "dpir_conv_tc_variant")
