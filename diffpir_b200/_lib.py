@@ -21,7 +21,8 @@ class UNetConfigC(ctypes.Structure):
                 ("out_channels", c_int32), ("num_res_blocks", c_int32), ("n_channel_mult", c_int32),
                 ("channel_mult", c_int32 * 8), ("n_attention_ds", c_int32), ("attention_ds", c_int32 * 8),
                 ("num_heads", c_int32), ("num_head_channels", c_int32), ("num_heads_upsample", c_int32),
-                ("use_new_attention_order", c_int32), ("precision", c_int32), ("diffusion_steps", c_int32)]
+                ("use_new_attention_order", c_int32), ("precision", c_int32), ("diffusion_steps", c_int32),
+                ("channel_mult_den", c_int32)]
 
 
 # name -> (restype, argtypes); must list every symbol include/diffpir_b200.h declares (tests check this)
@@ -80,6 +81,7 @@ SIGNATURES = {
                                c_int32, c_int32, c_int32, c_void_p]),
     "dpir_conv_tc_f16io": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
                                      c_int32, c_int32, c_int32, c_void_p]),
+    "dpir_attention": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "dpir_conv_tc_variant": (c_int32, [c_int32]),
     "dpir_gn_coef": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
                                c_void_p, c_void_p]),

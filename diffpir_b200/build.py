@@ -10,8 +10,8 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdiffpir_b200.so")
 STAMP = os.path.join(HERE, "libdiffpir_b200.srchash")     # sha256 of the sources the shipped .so was built from
 LOCK = os.path.join(HERE, ".build.lock")
-SOURCES = ["prox.cu", "unet_kernels.cu", "conv_tc.cu", "engine.cu"]
-HEADERS = ["common.cuh", "unet_kernels.cuh", os.path.join("..", "..", "include", "diffpir_b200.h")]
+SOURCES = ["prox.cu", "unet_kernels.cu", "conv_tc.cu", "attention_tc.cu", "engine.cu"]
+HEADERS = ["common.cuh", "unet_kernels.cuh", "tc_ptx.cuh", os.path.join("..", "..", "include", "diffpir_b200.h")]
 
 
 def _nvcc():

@@ -26,166 +26,13 @@
 //   k_conv3x3_v3<1|2>       the same with the preceding GroupNorm(+FiLM)+SiLU applied to the activation operand by 8 producer
 //                           warps ("v4", default for eligible ResBlocks); <3> is an unvalidated activate-once variant
 #include "unet_kernels.cuh"
+#include "tc_ptx.cuh"
 
 #include <cstdlib>
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
 namespace dpir {
-
-// ------------------------------------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ uint32_t mbar_try_wait(uint64_t *bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.b32 %0, 1, 0, p;\n\t"
-      "}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok;
-}
-// try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes (or ~the hint elapses) instead of
-// returning after the short default time limit.  Without it a waiting warp re-issues the poll every ~70 cycles: ncu counted
-// 141 M of the 255 M epilogue warp-instructions of one 256x256 convolution in this loop - a fifth of the issue slots of
-// sub-partitions that are issue-bound once the operand producers of the fused kernel share them.
-__device__ __forceinline__ uint32_t mbar_try_wait_sleep(uint64_t *bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-      "selp.b32 %0, 1, 0, p;\n\t"
-      "}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity), "r"(200000u)      // nanoseconds
-      : "memory");
-  return ok;
-}
-// bounded wait (latency-critical hand-offs): a broken pipeline traps after ~1-2 s instead of hanging the GPU.  The hardware
-// caps the suspend time of a try_wait at ~130 cycles (measured), so the loop body is kept to a counter: every poll of a
-// waiting warp takes issue slots from the warps that work.
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  uint32_t polls = 0;
-  while (!mbar_try_wait_sleep(bar, parity)) {
-    if (++polls > 20000000u) __trap();
-  }
-}
-// the same for long waits with slack (an epilogue warp waiting for the next accumulator, ~10 us): back off with nanosleep so
-// that the ~140 polls per wait (ncu: 89 M of the 436 M warp-instructions of a fused 256x256 convolution) become a handful
-__device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  uint32_t polls = 0;
-  while (!mbar_try_wait_sleep(bar, parity)) {
-    __nanosleep(256);
-    if (++polls > 4000000u) __trap();
-  }
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *m) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *m, uint64_t *bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
-          smem_u32(dst)),
-      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *m, uint64_t *bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
-          smem_u32(dst)),
-      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-
-// L2 prefetch of a tensor box (no shared-memory destination): warms the lines the operand producers are about to read
-__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap *m, int c0, int c1, int c2, int c3) {
-  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(reinterpret_cast<uint64_t>(m)),
-               "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-               : "memory");
-}
-__device__ __forceinline__ void tma_store_4d(const CUtensorMap *m, const void *src, int c0, int c1, int c2, int c3) {
-  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
-                   reinterpret_cast<uint64_t>(m)),
-               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-               : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-
-template <int COLS> __device__ __forceinline__ void tmem_alloc(uint32_t *slot) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "n"(COLS) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-template <int COLS> __device__ __forceinline__ void tmem_dealloc(uint32_t addr) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "n"(COLS) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem]^T, kind::f16 (fp16 in, fp32 accumulate), issued by ONE thread
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
-__device__ __forceinline__ void umma_commit(uint64_t *bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t *r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t *r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major SWIZZLE_128B shared-memory matrix descriptor (sm_100 format): start address >> 4 in bits [0,14),
-// LBO (ignored for swizzled K-major) = 1 in [16,30), SBO = 1024 B (8 rows x 128 B) >> 4 in [32,46), version 1 in [46,48),
-// layout type SWIZZLE_128B = 2 in [61,64).
-__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
 
 // ------------------------------------------------------------------------------------------------ kernel
 constexpr int TC_BM = 128;
@@ -289,7 +136,22 @@ __device__ __forceinline__ void epi_nhwc_chunk32(const ConvEpi &epi, const ConvT
         if (co + j < g.Cout) *reinterpret_cast<float4 *>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
     }
   }
-  if (epi.qstats) warp_quad_stats(qs, qq, lane, warp_img_ok, epi.qstats, n, g.Cout, co);
+  if (epi.qstats) {
+    if (g.TW * g.TH >= 32) {
+      warp_quad_stats(qs, qq, lane, warp_img_ok, epi.qstats, n, g.Cout, co);      // the 32 rows of a warp lie in one image
+    } else if (valid) {
+      // maps smaller than 32 pixels (4x4, 2x2: the deepest levels of the 512x512 model family, or small inputs): a warp's rows
+      // span several images, so every pixel row adds its own quads (a handful of atomics on tensors of a few KB)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (co + 4 * j < g.Cout) {
+          double *qp = epi.qstats + ((int64_t)n * (g.Cout >> 2) + ((co + 4 * j) >> 2)) * 2;
+          atomicAdd(qp, (double)qs[j]);
+          atomicAdd(qp + 1, (double)qq[j]);
+        }
+      }
+    }
+  }
 }
 
 template <int BN, int STAGES>
@@ -448,7 +310,7 @@ constexpr int V3_A_SLOTS = 3;
 constexpr int V3_W_SLOTS = 4;
 constexpr int V3_W_BYTES = 128 * 128;                 // one tap: 128 couts x 64 fp16
 constexpr int V3_RING_BYTES = V3_A_SLOTS * V2_A_BYTES + V3_W_SLOTS * V3_W_BYTES;     // 176,128 B
-constexpr int V3_SMEM = V3_RING_BYTES + V3_STG_BYTES + 1024 + 512;
+constexpr int V3_SMEM = V3_RING_BYTES + V3_STG_BYTES + 1024 + 1024;    // + alignment slack + barrier block
 
 struct ConvV2Geom {
   int B, H, W, Cin, Cout;
@@ -463,6 +325,8 @@ struct ConvV2Geom {
   int a_slots, w_slots, w_taps;       // v3 rings: activation halo boxes (36 KB each) and weight slots of w_taps taps (16 KB per tap);
                                       // a_slots*36 KB + w_slots*w_taps*16 KB <= V3_RING_BYTES
   int pf_dist;                        // fused kernels: L2 prefetch distance of the raw operand in 64-channel chunks (0 = off)
+  int stg_stride;                     // epilogue staging bytes per warp: 6144 (OUT + two residual boxes) or 2048 (OUT only, convs
+                                      // without a residual: the 32 KB saved buy a deeper weight ring)
 };
 
 __device__ __forceinline__ float tanh_approx_f(float x) {
@@ -793,11 +657,13 @@ __global__ void __launch_bounds__(FUSE ? V4_THREADS : V2_THREADS, 1) k_conv3x3_v
   constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t *a_ring = smem;                                    // [A_SL][V2_A_BYTES]  activation halo boxes
+  // barriers first (fixed offset), then the rings, then the per-epilogue-warp staging (OUT, RES0, RES1: 2 KB each; OUT only when the
+  // convolution has no residual) - ring and staging sizes are launch parameters, their sum never exceeds V3_RING_BYTES + V3_STG_BYTES
+  uint64_t *a_full = reinterpret_cast<uint64_t *>(smem);
   const int A_SL = g.a_slots, W_SL = g.w_slots;              // ring depths (runtime: tuned per kernel flavour)
-  uint8_t *w_ring = smem + A_SL * V2_A_BYTES;                // [W_SL][w_taps * V3_W_BYTES]  weight tap tiles
-  uint8_t *stg_base = smem + V3_RING_BYTES;                  // per epilogue warp: OUT, RES0, RES1 (2 KB each)
-  uint64_t *a_full = reinterpret_cast<uint64_t *>(stg_base + V3_STG_BYTES);
+  uint8_t *a_ring = smem + 1024;                             // [A_SL][V2_A_BYTES]  activation halo boxes
+  uint8_t *w_ring = a_ring + A_SL * V2_A_BYTES;              // [W_SL][w_taps * V3_W_BYTES]  weight tap tiles
+  uint8_t *stg_base = w_ring + W_SL * g.w_taps * V3_W_BYTES;
   uint64_t *a_empty = a_full + 4;              // up to 4 activation slots
   uint64_t *w_full = a_empty + 4;
   uint64_t *w_empty = w_full + 8;              // up to 8 weight slots
@@ -1176,7 +1042,7 @@ __global__ void __launch_bounds__(FUSE ? V4_THREADS : V2_THREADS, 1) k_conv3x3_v
     // ahead) and is read back column-wise (32 x LDS.U16).
     const int q = warp & 3;               // TMEM lane quarter -> channels co0 + q*32 + lane
     const int hv = ew >> 2;               // which half of the tile's 256 pixels (image rows hv*8 .. hv*8+7)
-    __half *outb = reinterpret_cast<__half *>(stg_base + ew * 6144);
+    __half *outb = reinterpret_cast<__half *>(stg_base + ew * g.stg_stride);
     __half *resb0 = outb + 1024, *resb1 = outb + 2048;
     uint64_t *rbar = res_full + ew * 2;
     uint32_t rcount = 0;                  // residual boxes consumed so far by this warp (buffer = rcount & 1, parity = (rcount >> 1) & 1)
@@ -1353,7 +1219,7 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 static int pow2_ge(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
 int conv_tc_plan_create(const void *act_half, const void *w_half, int B, int H, int W, int Cin_real, int CoutPad, int ksize,
-                        ConvTcPlan **out, int split) {
+                        ConvTcPlan **out, int split, int force_bn) {
   DPIR_REQUIRE(Cin_real % TC_BK == 0, "conv_tc: Cin must be a multiple of 64 (got %d)", Cin_real);
   const int Cin = split ? 3 * Cin_real : Cin_real;          // K extent of the weights
   const int Cact = split ? 2 * Cin_real : Cin_real;         // channels per pixel of the activation tensor ([hi | lo] when split)
@@ -1377,6 +1243,7 @@ int conv_tc_plan_create(const void *act_half, const void *w_half, int B, int H, 
   p->v2 = g_force_v1 != 1 && ksize == 3 && H >= 16 && W >= 16 && CoutPad % 128 == 0;
   // one-tile-per-CTA kernel on small maps (8x8, 16x16 1x1): 128-wide cout tiles would leave most of the 148 SMs idle
   if (!p->v2 && CoutPad != 16 && g.tiles_w * g.tiles_h * g.tiles_n * (CoutPad / 128) < 100) p->BN = 64;
+  if (force_bn) p->BN = force_bn;
   p->use_v3 = g_force_v1 == 0;
   if (p->v2) {
     ConvV2Geom &g2 = p->g2;
@@ -1384,7 +1251,7 @@ int conv_tc_plan_create(const void *act_half, const void *w_half, int B, int H, 
     g2.a_wrap = g.a_wrap;
     g2.tiles_w = cdiv(W, 16); g2.tiles_h = cdiv(H, 16); g2.n_tiles = CoutPad / 128;
     g2.total_tiles = B * g2.tiles_w * g2.tiles_h * g2.n_tiles;
-    g2.a_slots = V3_A_SLOTS; g2.w_slots = V3_W_SLOTS; g2.w_taps = 1; g2.pf_dist = 0;
+    g2.a_slots = V3_A_SLOTS; g2.w_slots = V3_W_SLOTS; g2.w_taps = 1; g2.pf_dist = 0; g2.stg_stride = 6144;
   }
   {
     cuuint64_t gdim[4] = {(cuuint64_t)Cact, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
@@ -1569,28 +1436,38 @@ int launch_conv_tc(const ConvTcPlan *p, const ConvEpi &epi, int Cout, cudaStream
       // ring shapes: the TMA-fed plain kernel keeps round 1's two (halo box + 3 taps) stages; the activate-once producers want a
       // whole chunk (3 dx boxes) of activation slots, per-tap weight slots and an L2 prefetch of the raw operand two chunks ahead.
       // DPIR_CONV_RING="a,w,t,af,wf,tf,pf" overrides (plain: a boxes, w slots of t taps; fused likewise; pf = prefetch distance).
-      static int ring[7] = {-1, 0, 0, 0, 0, 0, 0};
+      static int ring[10] = {-1, 0, 0, 0, 0, 0, 0, 0, 0, 0};
       if (ring[0] < 0) {
-        int v[7] = {2, 2, 3, V3_A_SLOTS, V3_W_SLOTS, 1, 1};
+        // plain | fused with a residual | prefetch distance | fused without a residual (OUT-only staging -> 2 x 3-tap weight slots)
+        int v[10] = {2, 2, 3, V3_A_SLOTS, V3_W_SLOTS, 1, 1, 3, 2, 3};
         const char *e = getenv("DPIR_CONV_RING");
         if (e) {
-          int u[7] = {v[0], v[1], v[2], v[3], v[4], v[5], v[6]};
-          const int n = sscanf(e, "%d,%d,%d,%d,%d,%d,%d", &u[0], &u[1], &u[2], &u[3], &u[4], &u[5], &u[6]);
-          auto ok = [](int a, int w, int t) {
-            return a >= 2 && a <= 4 && w >= 2 && w <= 8 && (t == 1 || t == 3) && a * V2_A_BYTES + w * t * V3_W_BYTES <= V3_RING_BYTES;
+          int u[10];
+          for (int i = 0; i < 10; ++i) u[i] = v[i];
+          const int n = sscanf(e, "%d,%d,%d,%d,%d,%d,%d,%d,%d,%d", &u[0], &u[1], &u[2], &u[3], &u[4], &u[5], &u[6], &u[7], &u[8], &u[9]);
+          auto ok = [](int a, int w, int t, int stg) {
+            return a >= 2 && a <= 4 && w >= 2 && w <= 8 && (t == 1 || t == 3) &&
+                   a * V2_A_BYTES + w * t * V3_W_BYTES + 8 * stg <= V3_RING_BYTES + V3_STG_BYTES;
           };
-          if (n >= 3 && ok(u[0], u[1], u[2])) { v[0] = u[0]; v[1] = u[1]; v[2] = u[2]; }
-          if (n >= 6 && ok(u[3], u[4], u[5])) { v[3] = u[3]; v[4] = u[4]; v[5] = u[5]; }
+          if (n >= 3 && ok(u[0], u[1], u[2], 6144)) { v[0] = u[0]; v[1] = u[1]; v[2] = u[2]; }
+          if (n >= 6 && ok(u[3], u[4], u[5], 6144)) { v[3] = u[3]; v[4] = u[4]; v[5] = u[5]; }
           if (n >= 7 && u[6] >= 0 && u[6] <= 8) v[6] = u[6];
+          if (n >= 10 && ok(u[7], u[8], u[9], 2048)) { v[7] = u[7]; v[8] = u[8]; v[9] = u[9]; }
         }
-        for (int i = 1; i < 7; ++i) ring[i] = v[i];
+        for (int i = 1; i < 10; ++i) ring[i] = v[i];
         ring[0] = v[0];
       }
       const bool fused = p->gf.coef != nullptr;
-      g2.a_slots = fused ? ring[3] : ring[0];
-      g2.w_slots = fused ? ring[4] : ring[1];
-      g2.w_taps = fused ? ring[5] : ring[2];
+      const bool nores = fused && !epi.residual;
+      g2.a_slots = nores ? ring[7] : (fused ? ring[3] : ring[0]);
+      g2.w_slots = nores ? ring[8] : (fused ? ring[4] : ring[1]);
+      g2.w_taps = nores ? ring[9] : (fused ? ring[5] : ring[2]);
       g2.pf_dist = fused ? ring[6] : 0;
+      g2.stg_stride = nores ? 2048 : 6144;
+      if (g2.a_slots * V2_A_BYTES + g2.w_slots * g2.w_taps * V3_W_BYTES + 8 * g2.stg_stride > V3_RING_BYTES + V3_STG_BYTES) {
+        set_error("conv_tc: ring configuration exceeds the shared-memory budget");
+        return DPIR_E_STATE;
+      }
     }
     int grid = g2.total_tiles < g_num_sms ? g2.total_tiles : g_num_sms;
     const bool v3_ok = !p->split && p->use_v3 && p->io_half && epi.out_half && epi.out == p->io_out && epi.residual == p->io_res &&

@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <map>
 #include <memory>
 #include <string>
@@ -97,8 +98,13 @@ struct Pool {
   struct Blk { size_t off, size; bool free; };
   std::vector<Blk> blks;
   size_t peak = 0;
+  // Every block is followed by a small odd-sized skew (a multiple of 10 KB that cycles with the allocation count).  The
+  // activation tensors of this network are exact powers of two (B=32: 2^28 / 2^29 bytes), and back-to-back placement put a
+  // convolution's input, output and residual exactly 2^28 bytes apart: measured 3.3x slower on such a layer (0.46 -> 1.5 ms,
+  // profiles/r02_workspace_skew.md) - the streams collide in the same DRAM banks.  The skew breaks the alignment.
+  int n_alloc = 0;
   size_t alloc(size_t n) {
-    n = align_up(n, 1024);
+    n = align_up(n, 1024) + (size_t)((n_alloc++ % 13) + 1) * 10240;
     for (size_t i = 0; i < blks.size(); ++i) {
       if (blks[i].free && blks[i].size >= n) {
         if (blks[i].size > n) {
@@ -199,7 +205,9 @@ int build_structure(dpir_engine *e) {
   int nh_up = c.num_heads_upsample == -1 ? c.num_heads : c.num_heads_upsample;
   auto heads = [&](int ch, int nh) { return c.num_head_channels == -1 ? nh : ch / c.num_head_channels; };
   int mc = c.model_channels;
-  int ch = c.channel_mult[0] * mc;
+  const int den = c.channel_mult_den > 1 ? c.channel_mult_den : 1;
+  auto level_ch = [&](int level) { return (int)((int64_t)c.channel_mult[level] * mc / den); };   // int(mult * model_channels), unet.py:483, 497
+  int ch = level_ch(0);
   e->ch0 = ch;
   e->ted = mc * 4;
   std::vector<int> chans;
@@ -210,12 +218,12 @@ int build_structure(dpir_engine *e) {
   chans.push_back(ch);
   int ds = 1;
   for (int level = 0; level < c.n_channel_mult; ++level) {
-    int mult = c.channel_mult[level];
+    const int lch = level_ch(level);
     for (int r = 0; r < c.num_res_blocks; ++r) {
       int i = (int)e->inputs.size();
       std::vector<LayerDesc> blk;
-      blk.push_back(mk(1, "input_blocks." + std::to_string(i) + ".0.", ch, mult * mc));
-      ch = mult * mc;
+      blk.push_back(mk(1, "input_blocks." + std::to_string(i) + ".0.", ch, lch));
+      ch = lch;
       if (has_att(ds)) blk.push_back(mk(2, "input_blocks." + std::to_string(i) + ".1.", ch, ch, 0, heads(ch, c.num_heads)));
       e->inputs.push_back(blk);
       chans.push_back(ch);
@@ -230,15 +238,15 @@ int build_structure(dpir_engine *e) {
   e->middle.push_back({mk(1, "middle_block.0.", ch, ch), mk(2, "middle_block.1.", ch, ch, 0, heads(ch, c.num_heads)),
                        mk(1, "middle_block.2.", ch, ch)});
   for (int level = c.n_channel_mult - 1; level >= 0; --level) {
-    int mult = c.channel_mult[level];
+    const int lch = level_ch(level);
     for (int i = 0; i <= c.num_res_blocks; ++i) {
       int ich = chans.back();
       chans.pop_back();
       int o = (int)e->outputs.size();
       std::string pre = "output_blocks." + std::to_string(o) + ".";
       std::vector<LayerDesc> blk;
-      blk.push_back(mk(1, pre + "0.", ch + ich, mc * mult));
-      ch = mc * mult;
+      blk.push_back(mk(1, pre + "0.", ch + ich, lch));
+      ch = lch;
       if (has_att(ds)) blk.push_back(mk(2, pre + std::to_string(blk.size()) + ".", ch, ch, 0, heads(ch, nh_up)));
       if (level && i == c.num_res_blocks) {
         blk.push_back(mk(1, pre + std::to_string(blk.size()) + ".", ch, ch, RS_UP));
@@ -579,6 +587,9 @@ struct PlanBuilder {
     int h1;
     conv(a1, rw.c1, -1, &h1, /*want_stats=*/true, /*out_half=*/true);   // h1 feeds only GroupNorm -> conv2
     release(a1);
+    // (Fusing the SECOND norm of the up/down-sampling ResBlocks into conv2 was measured in round 2: the k_gn_apply pass it removes
+    // (0.48 ms per forward) is paid back by the slower fused convolution (+0.59 ms) - profiles/r02_conv_ring_experiments.md - so
+    // these blocks keep the separate pass.)
     int a2, d0, d1;
     gn(h1, -1, rw.n2, rw.film_row, 1, RS_NONE, false, false, &a2, &d0, &d1);
     release(h1);
@@ -1278,6 +1289,15 @@ int dpir_conv_gnfuse_f16io(const void *src1, int32_t C1, const void *src2, int32
   if (!rc) rc = launch_conv_tc(p, epi, Cout, (cudaStream_t)stream);
   conv_tc_plan_destroy(p);
   return rc;
+}
+
+/* QKVAttentionLegacy / QKVAttention (unet.py:337-354, 371-389) on its own: qkv dev fp32 [B][T][3C] (NHWC output of the qkv 1x1
+ * convolution; legacy channel order [head][q,k,v][64], new order [q,k,v][head][64]), out dev [B][T][C] fp16 (out_half: the
+ * tcgen05 kernel) or fp32 (the fp32 CUDA-core kernel).  Any T >= 1. */
+int dpir_attention(const float *qkv, void *out, int32_t out_half, int32_t B, int32_t T, int32_t C, int32_t heads, int32_t new_order,
+                   void *stream) {
+  DPIR_REQUIRE(qkv && out, "dpir_attention: null pointer");
+  return launch_attention(qkv, out, out_half, B, T, C, heads, new_order, (cudaStream_t)stream);
 }
 
 int dpir_conv_tc_variant(int32_t variant) {

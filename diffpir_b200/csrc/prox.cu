@@ -450,7 +450,7 @@ struct dpir_fft_plan {
 extern "C" {
 
 const char *dpir_last_error(void) { return g_err.c_str(); }
-int dpir_version(void) { return 100; }
+int dpir_version(void) { return 200; }
 int64_t dpir_launch_count(void) { return g_launch_count; }
 void dpir_launch_count_reset(void) { g_launch_count = 0; }
 

@@ -11,6 +11,8 @@
 // buffers feed the tcgen05 implicit-GEMM convolution (conv_tc.cu) as K-major operands.
 #include "unet_kernels.cuh"
 #include <mma.h>
+#include <cstdlib>
+#include <string>
 
 namespace dpir {
 
@@ -549,7 +551,8 @@ __global__ void __launch_bounds__(256) k_attention(const float *__restrict__ qkv
     int r = tid >> 2, qd = tid & 3;   // 64 rows x 4 quads of 16 -> loop 4 times over d quads
     for (int it = 0; it < 4; ++it) {
       int d = (qd * 4 + it) * 4;
-      float4 v = *reinterpret_cast<const float4 *>(base + (int64_t)(q0 + r) * C3 + qoff + d);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (q0 + r < Tn) v = *reinterpret_cast<const float4 *>(base + (int64_t)(q0 + r) * C3 + qoff + d);   // rows >= T: zeros, never stored
       Qt[(d + 0) * AT_LD + r] = v.x; Qt[(d + 1) * AT_LD + r] = v.y; Qt[(d + 2) * AT_LD + r] = v.z; Qt[(d + 3) * AT_LD + r] = v.w;
     }
   }
@@ -568,9 +571,10 @@ __global__ void __launch_bounds__(256) k_attention(const float *__restrict__ qkv
       for (int it = 0; it < 4; ++it) {
         int d = (qd * 4 + it) * 4;
         const float *rowp = base + (int64_t)(k0 + r) * C3;
-        float4 kv = *reinterpret_cast<const float4 *>(rowp + koff + d);
+        const bool kin = k0 + r < Tn;                                    // keys >= T: zero operands, masked scores
+        float4 kv = kin ? *reinterpret_cast<const float4 *>(rowp + koff + d) : make_float4(0.f, 0.f, 0.f, 0.f);
         Kt[(d + 0) * AT_LD + r] = kv.x; Kt[(d + 1) * AT_LD + r] = kv.y; Kt[(d + 2) * AT_LD + r] = kv.z; Kt[(d + 3) * AT_LD + r] = kv.w;
-        float4 vv = *reinterpret_cast<const float4 *>(rowp + voff + d);
+        float4 vv = kin ? *reinterpret_cast<const float4 *>(rowp + voff + d) : make_float4(0.f, 0.f, 0.f, 0.f);
         *reinterpret_cast<float4 *>(&Vs[r * AT_LD + d]) = vv;
       }
     }
@@ -595,7 +599,10 @@ __global__ void __launch_bounds__(256) k_attention(const float *__restrict__ qkv
     for (int i = 0; i < 4; ++i) {
       float mx = -INFINITY;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { s[i][j] *= scale2; mx = fmaxf(mx, s[i][j]); }
+      for (int j = 0; j < 4; ++j) {
+        s[i][j] = (k0 + tx * 4 + j < Tn) ? s[i][j] * scale2 : -INFINITY;
+        mx = fmaxf(mx, s[i][j]);
+      }
 #pragma unroll
       for (int off = 1; off < 16; off <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
       float m_new = fmaxf(m_run[i], mx);
@@ -628,7 +635,7 @@ __global__ void __launch_bounds__(256) k_attention(const float *__restrict__ qkv
   for (int i = 0; i < 4; ++i) {
     float inv = 1.f / l_run[i];
     float4 v = make_float4(o[i][0] * inv, o[i][1] * inv, o[i][2] * inv, o[i][3] * inv);
-    Store4<T>::st(out + ((int64_t)b * Tn + q0 + ty * 4 + i) * C + h * AT_D + tx * 4, v);
+    if (q0 + ty * 4 + i < Tn) Store4<T>::st(out + ((int64_t)b * Tn + q0 + ty * 4 + i) * C + h * AT_D + tx * 4, v);
   }
 }
 
@@ -763,25 +770,30 @@ __global__ void __launch_bounds__(128) k_attention_wmma(const float *__restrict_
   }
 }
 
+int launch_attention_tc(const float *qkv, void *out, int out_half, int B, int T, int C, int heads, int new_order, cudaStream_t st);
+
+// out_half (fp16 / fp16s pipelines): the tcgen05 kernel of attention_tc.cu (DPIR_ATTENTION=wmma selects the round-1 HMMA kernel for
+// A/B runs, T % 64 == 0 only); fp32 output (fp32 parity mode, fp16x3 split-precision mode): the fp32 CUDA-core kernel.  Any T.
 int launch_attention(const float *qkv, void *out, int out_half, int B, int T, int C, int heads, int new_order, cudaStream_t st) {
   DPIR_REQUIRE(C == heads * AT_D, "attention: head dim must be 64 (C=%d heads=%d)", C, heads);
-  DPIR_REQUIRE(T % AT_Q == 0, "attention: token count must be a multiple of 64 (got %d)", T);
+  DPIR_REQUIRE(T >= 1, "attention: empty sequence");
+  static int use_wmma = -1;
+  if (use_wmma < 0) { const char *e = getenv("DPIR_ATTENTION"); use_wmma = (e && std::string(e) == "wmma") ? 1 : 0; }
+  if (out_half && !(use_wmma && T % 64 == 0)) return launch_attention_tc(qkv, out, out_half, B, T, C, heads, new_order, st);
   size_t smem = (size_t)4 * AT_D * AT_LD * sizeof(float);
-  dim3 grid(T / AT_Q, heads, B);
-  static bool attr_set = false;
-  if (!attr_set) {
+  dim3 grid(cdiv(T, AT_Q), heads, B);
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+  if (!attr_set[dev]) {
+    constexpr size_t smem_w = (size_t)4 * 64 * ATW_LDH * sizeof(__half) + (size_t)2 * 64 * ATW_LDF * sizeof(float);
     DPIR_CUDA_CHECK(cudaFuncSetAttribute(k_attention<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     DPIR_CUDA_CHECK(cudaFuncSetAttribute(k_attention<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    DPIR_CUDA_CHECK(cudaFuncSetAttribute(k_attention_wmma<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
+    attr_set[dev] = true;
   }
   if (out_half) {
-    // tensor-core pipelines: fp16 operands on HMMA; the fp32 parity mode below keeps the fp32 CUDA-core kernel
     constexpr size_t smem_w = (size_t)4 * 64 * ATW_LDH * sizeof(__half) + (size_t)2 * 64 * ATW_LDF * sizeof(float);
-    static bool attr_w = false;
-    if (!attr_w) {
-      DPIR_CUDA_CHECK(cudaFuncSetAttribute(k_attention_wmma<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
-      attr_w = true;
-    }
     k_attention_wmma<__half><<<grid, 128, smem_w, st>>>(qkv, (__half *)out, T, C, heads, new_order);
   } else {
     k_attention<float><<<grid, 256, smem, st>>>(qkv, (float *)out, T, C, heads, new_order);

@@ -123,7 +123,7 @@ struct ConvTcPlan;  // opaque: tensor maps + geometry
 // split != 0: split-precision operands - act holds [hi | lo] (2*Cin channels per pixel), w is packed [tap][CoutPad][3*Cin] =
 // [w_hi | w_hi | w_lo]; the K loop runs x_hi*w_hi + x_lo*w_hi + x_hi*w_lo in one fp32 accumulation (error ~2^-22)
 int conv_tc_plan_create(const void *act_half, const void *w_half, int B, int H, int W, int Cin, int CoutPad, int ksize,
-                        ConvTcPlan **out, int split = 0);
+                        ConvTcPlan **out, int split = 0, int force_bn = 0);
 void conv_tc_plan_destroy(ConvTcPlan *p);
 bool conv_tc_plan_is_v2(const ConvTcPlan *p);
 int conv_tc_plan_add_skip(ConvTcPlan *p, const void *act2_half, const void *w2_half, int Cin2a, const void *act2b_half = nullptr,

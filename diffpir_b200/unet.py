@@ -44,9 +44,14 @@ class UNetModel:
         c = _lib.UNetConfigC()
         c.image_size, c.in_channels, c.model_channels = cfg.image_size, cfg.in_channels, cfg.model_channels
         c.out_channels, c.num_res_blocks = cfg.out_channels, cfg.num_res_blocks
-        cm = [int(m) for m in cfg.channel_mult]
-        if any(m != mm for m, mm in zip(cm, cfg.channel_mult)):
-            raise ValueError("fractional channel_mult is not supported")
+        # fractional multipliers (the 512x512 model's 0.5, script_util.py:149-150) travel as numerators over a common denominator
+        den = 1
+        while any(abs(m * den - round(m * den)) > 1e-9 for m in cfg.channel_mult) and den < 64:
+            den *= 2
+        cm = [int(round(m * den)) for m in cfg.channel_mult]
+        if any(abs(c_ / den - m) > 1e-9 for c_, m in zip(cm, cfg.channel_mult)):
+            raise ValueError(f"channel_mult {cfg.channel_mult} is not representable")
+        c.channel_mult_den = den
         c.n_channel_mult = len(cm)
         for i, m in enumerate(cm):
             c.channel_mult[i] = m

@@ -77,6 +77,9 @@ typedef struct dpir_unet_config {
   int32_t use_new_attention_order; /* 0: QKVAttentionLegacy unet.py:328-358, 1: QKVAttention :361-393 */
   int32_t precision;           /* DPIR_PRECISION_* */
   int32_t diffusion_steps;     /* 1000: size of the eps->x0 coefficient tables */
+  int32_t channel_mult_den;    /* 0 or 1: channel_mult holds the integer multipliers; d > 1: level channels =
+                                  int(channel_mult[i] * model_channels / d) - the 512x512 model's (0.5, 1, 1, 2, 2, 4, 4)
+                                  (script_util.py:149-150) is passed as (1, 2, 2, 4, 4, 8, 8) with d = 2 */
 } dpir_unet_config;
 
 int dpir_create(const dpir_unet_config *cfg, dpir_engine **out);
@@ -276,6 +279,12 @@ int dpir_conv_gnfuse_f16io(const void *src1, int32_t C1, const void *src2, int32
  * separate k_gn_apply pass.  Per engine (drops the cached plans of `e`); with e == NULL it sets the flavour used by the
  * per-kernel test entry dpir_conv_gnfuse_f16io. */
 int dpir_set_gn_fusion(dpir_engine *e, int32_t enable);
+/* The attention core of AttentionBlock (guided_diffusion/unet.py:299-305 calls QKVAttentionLegacy :337-354 / QKVAttention :371-389)
+ * on its own: qkv dev fp32 [B][T][3C] (NHWC output of the qkv 1x1 convolution; legacy channel order [head][q,k,v][64], new order
+ * [q,k,v][head][64]); out dev [B][T][C] fp16 when out_half (tcgen05 kernel: S = QK^T and O = PV on the tensor cores with TMEM
+ * accumulators, fp32 softmax) or fp32 (fp32 CUDA-core kernel).  Head dim 64, any T >= 1. */
+int dpir_attention(const float *qkv, void *out, int32_t out_half, int32_t B, int32_t T, int32_t C, int32_t heads, int32_t new_order,
+                   void *stream);
 /* A/B switch for tests and benchmarks.  0 (default): 3x3 convs on >=16x16 maps use the persistent swap-AB halo-reuse
  * kernel (k_conv3x3_v3), everything else the one-tile-per-CTA kernel (k_conv_tc); 1: k_conv_tc everywhere;
  * 2: the persistent kernel with pixels on the M side (k_conv3x3_v2).  Affects plans created afterwards. */

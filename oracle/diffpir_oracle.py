@@ -266,7 +266,7 @@ def ibp_step(x0, y, sf, gamma, rho, in_iter=1):
 def diffpir_loop(sd, cfg, task, y, *, k=None, mask=None, sf=1, sigma=0.05, lambda_=7.0, zeta=0.3,
                  eta=0.0, guidance_scale=1.0, iter_num=100, skip_type="quad", T=1000,
                  x_init=None, init_noise=None, zeta_noise=None, eta_noise=None, sr_mode="blur",
-                 gamma=1.0 / 100, in_iter=1, unet=None, trace=None, max_steps=None):
+                 gamma=1.0 / 100, in_iter=1, unet=None, trace=None, max_steps=None, iter_num_U=1, u_noise=None):
     """The batched DiffPIR loop of main_ddpir.py:259-470 (generate_mode='DiffPIR', sub_1_analytic,
     model_output_type='pred_xstart', iter_num_U=1, noise_init_img='max', skip_noise_model_t=False)
     with all noise pre-drawn:
@@ -275,6 +275,9 @@ def diffpir_loop(sd, cfg, task, y, *, k=None, mask=None, sf=1, sigma=0.05, lambd
     task: 'deblur' | 'sr' | 'inpaint'.  y in [0,1] (for inpaint y is the un-masked image, mask applied
     as in :310-312).  `x_init` is the pre-noise x of :295-312 for sr (bicubic upsample); defaults to y / y*mask.
     `unet(x, vec_t)` may override the denoiser (e.g. the reference nn.Module).  Returns x_0 = x/2+0.5 (:470).
+    iter_num_U > 1 (main_ddpir.py:349, 460-467): every non-final step is repeated U times - re-noise to t_{i-1}, then back to
+    t_i with fresh noise u_noise[.]; zeta_noise then holds one tensor per re-noise.  (On the final sequence entry the reference's
+    repeats would index seq[i+1] - IndexError at :451 - so it is evaluated once.)
     """
     sched = driver_schedule(T=T)
     tables = diffusion_tables(T)
@@ -293,29 +296,37 @@ def diffpir_loop(sd, cfg, task, y, *, k=None, mask=None, sf=1, sigma=0.05, lambd
     seq = make_seq(T, iter_num, skip_type)
     red = sched["reduced_alpha_cumprod"].numpy()
     n_steps = len(seq) if max_steps is None else min(max_steps, len(seq))
+    nz = nu = 0
     for i in range(n_steps):
         curr_sigma = sigmas[seq[i]].numpy()
         t_i = find_nearest(red, curr_sigma)
         vec_t = torch.tensor([t_i] * x.shape[0])
-        out = unet(x, vec_t) if unet is not None else unet_oracle.unet_forward(sd, cfg, x, vec_t)
-        x0 = pred_xstart(out, x, vec_t, tables)
-        if trace is not None:
-            trace.append(("x0_unet", i, x0.clone()))
         last = seq[i] == seq[-1]
-        if not last:
-            tau = rhos[t_i].float().reshape(1, 1, 1, 1).to(dt)
-            if task == "inpaint":
-                x0 = inpaint_prox(x0, 2 * y - 1, mask, tau, guidance_scale)
-            elif sr_mode == "blur":
-                x0_p = data_solution(x0 / 2 + 0.5, FB, FBC, F2B, FBFy, tau, sf) * 2 - 1
-                x0 = x0 + guidance_scale * (x0_p - x0)
-            else:
-                x0 = ibp_step(x0, y, sf, gamma, rhos[t_i].to(dt), in_iter)
+        for u in range(1 if last else iter_num_U):
+            out = unet(x, vec_t) if unet is not None else unet_oracle.unet_forward(sd, cfg, x, vec_t)
+            x0 = pred_xstart(out, x, vec_t, tables)
             if trace is not None:
-                trace.append(("x0_prox", i, x0.clone()))
-            t_im1 = find_nearest(red, sigmas[seq[i + 1]].numpy())
-            n_eta = eta_noise[i] if eta_noise is not None else torch.zeros_like(x)
-            x = renoise(x, x0, t_i, t_im1, sched, eta, zeta, n_eta, zeta_noise[i])
-            if trace is not None:
-                trace.append(("x", i, x.clone()))
+                trace.append(("x0_unet", i, x0.clone()))
+            if not last:
+                tau = rhos[t_i].float().reshape(1, 1, 1, 1).to(dt)
+                if task == "inpaint":
+                    x0 = inpaint_prox(x0, 2 * y - 1, mask, tau, guidance_scale)
+                elif sr_mode == "blur":
+                    x0_p = data_solution(x0 / 2 + 0.5, FB, FBC, F2B, FBFy, tau, sf) * 2 - 1
+                    x0 = x0 + guidance_scale * (x0_p - x0)
+                else:
+                    x0 = ibp_step(x0, y, sf, gamma, rhos[t_i].to(dt), in_iter)
+                if trace is not None:
+                    trace.append(("x0_prox", i, x0.clone()))
+                t_im1 = find_nearest(red, sigmas[seq[i + 1]].numpy())
+                n_eta = eta_noise[nz] if eta_noise is not None else torch.zeros_like(x)
+                x = renoise(x, x0, t_i, t_im1, sched, eta, zeta, n_eta, zeta_noise[nz])
+                nz += 1
+                if u < iter_num_U - 1:                   # :460-467 set back to x_t from x_{t-1}
+                    sa, s1 = sched["sqrt_alphas_cumprod"], sched["sqrt_1m_alphas_cumprod"]
+                    a_eff = (sa[t_i] / sa[t_im1]).to(dt)
+                    x = a_eff * x + torch.sqrt(s1[t_i].to(dt) ** 2 - a_eff ** 2 * s1[t_im1].to(dt) ** 2) * u_noise[nu]
+                    nu += 1
+                if trace is not None:
+                    trace.append(("x", i, x.clone()))
     return x / 2 + 0.5

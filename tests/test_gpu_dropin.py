@@ -170,7 +170,8 @@ def test_model_fn_output_types_match_reference(ddim, monkeypatch):
     x = torch.randn(2, 3, 64, 64, generator=torch.Generator().manual_seed(21))
     torch.manual_seed(MODEL_FN_SEED)
     noise = torch.randn_like(x)
-    monkeypatch.setattr(torch, "randn_like", lambda t_, **kw: noise.to(t_.device))
+    noise_dev = noise.cuda()
+    monkeypatch.setattr(torch, "randn_like", lambda t_, **kw: noise_dev if t_.is_cuda else noise)
     model = make_model(small_config(), "fp32")
     betas = torch.from_numpy(np.linspace(0.0001, 0.02, 1000, dtype=np.float32))
     alphas_cumprod = np.cumprod((1.0 - betas).cpu(), axis=0)
@@ -192,11 +193,12 @@ def test_model_fn_output_types_match_reference(ddim, monkeypatch):
                                    diffusion=None, alphas_cumprod=alphas_cumprod)
         assert rel_l2(out, torch.from_numpy(gold["p_vec_t_prev"])) < 2e-5
         # epsilon / score with an explicit vec_t index alphas_cumprod on the device (no .item())
+        ac_dev, vt500 = alphas_cumprod.to(dev), torch.full((2,), 500, device=dev)
         torch.cuda.synchronize()
         torch.cuda.set_sync_debug_mode("error")
         try:
-            e = utils_model.model_fn(xd, noise_level=0, vec_t=torch.full((2,), 500, device=dev), model_out_type="epsilon",
-                                     model_diffusion=model, diffusion=None, alphas_cumprod=alphas_cumprod.to(dev))
+            e = utils_model.model_fn(xd, noise_level=0, vec_t=vt500, model_out_type="epsilon",
+                                     model_diffusion=model, diffusion=None, alphas_cumprod=ac_dev)
         finally:
             torch.cuda.set_sync_debug_mode("default")
         assert torch.isfinite(e).all()
@@ -229,9 +231,20 @@ def test_iter_num_U_matches_reference_golden():
     model = make_model(small_config(), "fp32")
     out = DiffPIRSampler(model, task, iter_num=iters, iter_num_U=2, **hp).run(
         y.cuda(), k=k.cuda(), init_noise=init.cuda(), zeta_noise=[z.cuda() for z in zs], u_noise=[u.cuda() for u in us])
-    err = rel_l2(out, torch.from_numpy(gold["deblur_U2_x0"]))
-    print(f"iter_num_U=2 deblur: rel-L2 vs reference golden {err:.3e}")
-    assert err < 5e-4, err
+    # scored like the other loops: against the fp64 oracle (its fp32 evaluation is pinned to this golden by the CPU suite), with
+    # the bar max(1e-4, 1.5 x the golden's own distance to fp64) - the reference's fp32 FFT prox cancels at small rho
+    from oracle import diffpir_oracle as orc
+    from dpir_testutil import weights
+    cfg = small_config()
+    ref64 = orc.diffpir_loop(weights(cfg), cfg.as_dict(), task, y.double(), k=k.double(), sf=1, iter_num=iters,
+                             init_noise=init.double(), zeta_noise=[z.double() for z in zs], iter_num_U=2,
+                             u_noise=[u.double() for u in us], **hp)
+    golden = torch.from_numpy(gold["deblur_U2_x0"])
+    dev = rel_l2(golden, ref64)
+    err64, err_gold = rel_l2(out, ref64), rel_l2(out, golden)
+    print(f"iter_num_U=2 deblur: rel-L2 vs fp64 oracle {err64:.3e}, vs reference fp32 golden {err_gold:.3e} (golden vs fp64: {dev:.3e})")
+    assert err64 < max(1e-4, 1.5 * dev), (err64, dev)
+    assert err_gold < max(1e-4, 2.5 * dev), (err_gold, dev)
 
 
 def test_sr_default_start_is_the_bicubic_upsample():

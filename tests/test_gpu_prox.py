@@ -194,3 +194,42 @@ def test_measurement_blur_uint8_bit_exact_vs_scipy(ksz):
         assert np.array_equal(u8[b].cpu().numpy(), ref)
         yl = (np.float32(ref / 255.0) * 2 - 1 + noise[b]) / 2 + 0.5
         assert np.abs(y[b].cpu().numpy() - np.transpose(yl, (2, 0, 1))).max() < 1e-6
+
+
+def test_motion_blur_operator_forward_and_kernel():
+    """MotionBlurOperator (utils/utils_deblur.py:683-705 surface; BASELINE config 5 depends on it): get_kernel() is a normalised
+    non-negative (1,1,k,k) PSF that is reproducible per seed, forward = ReflectionPad2d(k//2) + depthwise correlation with it
+    (checked against torch in fp64), transpose returns its input like the reference's."""
+    import torch.nn.functional as F
+    from diffpir_b200.utils_deblur import MotionBlurOperator
+    op = MotionBlurOperator(kernel_size=61, intensity=0.5, device="cuda", seed=1234)
+    k = op.get_kernel()
+    assert tuple(k.shape) == (1, 1, 61, 61) and float(k.min()) >= 0 and abs(float(k.sum()) - 1) < 1e-5
+    assert torch.equal(k, MotionBlurOperator(61, 0.5, "cuda", seed=1234).get_kernel())
+    assert not torch.equal(k, MotionBlurOperator(61, 0.5, "cuda", seed=1235).get_kernel())
+    x = torch.rand(2, 3, 96, 80, generator=torch.Generator().manual_seed(1))
+    out = op.forward(x.cuda())
+    ref = F.conv2d(F.pad(x.double(), (30, 30, 30, 30), mode="reflect"), k.double().repeat(3, 1, 1, 1), groups=3)
+    assert rel_l2(out, ref) < 1e-6
+    assert op.transpose(out) is out
+
+
+def test_weight_arena_clone_computes_identical_results():
+    """A rank that RECEIVES the packed weight arena (the one NCCL broadcast, parallel.broadcast_model) never calls
+    load_state_dict: emulate it on one GPU by copying the arena into a second engine - outputs must be bit-identical (fp16s
+    throughput mode and the fp16x3 split mode, whose accumulator scales also live in the arena)."""
+    from dpir_testutil import make_model, small_config
+    from diffpir_b200.unet import UNetModel
+    cfg = small_config()
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(2, 3, 64, 64, generator=g).cuda()
+    t = torch.tensor([999, 123], device="cuda")
+    for precision in ("fp16s", "fp16x3"):
+        a = make_model(cfg, precision)
+        b = UNetModel(cfg, precision=precision)
+        assert b.missing_weights() > 0
+        b.weight_arena().copy_(a.weight_arena())
+        b.mark_weights_loaded()
+        assert b.missing_weights() == 0
+        assert torch.equal(a.x0(x, t), b.x0(x, t))
+        del a, b

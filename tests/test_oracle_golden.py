@@ -89,3 +89,35 @@ def test_full_loop(task, sf, hp):
     out = orc.diffpir_loop(sd, cfg.as_dict(), task, y, k=k, mask=mask, sf=sf, iter_num=iters, init_noise=init,
                            zeta_noise=zs, x_init=x_init, **hp)
     assert rel_l2(out, torch.from_numpy(g[task + "_x0"])) < 2e-5
+
+
+def test_full_loop_iter_num_U():
+    """The oracle's iter_num_U = 2 branch (main_ddpir.py:349, 460-467) against the golden of the reference loop arithmetic."""
+    g = _load("loop_u2.npz")
+    iters = int(g["iters"])
+    cfg = gen_golden.small_cfg()
+    sd = synth.synthetic_state_dict(cfg, 0)
+    task, sf, hp = gen_golden.LOOP_CASES[0]
+    gt, y, k, mask = gen_golden.loop_inputs(task, sf=sf)
+    init, zs = synth.predrawn_noise((2, 3, 64, 64), 2 * iters, seed=8)
+    _, us = synth.predrawn_noise((2, 3, 64, 64), iters, seed=9)
+    out = orc.diffpir_loop(sd, cfg.as_dict(), task, y, k=k, sf=sf, iter_num=iters, init_noise=init, zeta_noise=zs,
+                           iter_num_U=2, u_noise=us, **hp)
+    assert rel_l2(out, torch.from_numpy(g["deblur_U2_x0"])) < 2e-5
+
+
+def test_model_fn_goldens_present():
+    """model_fn.npz (utils_model.model_fn output types from the reference's p_sample / ddim_sample) feeds the GPU drop-in tests;
+    here: the identities that tie its entries together (utils/utils_model.py:241-256)."""
+    g = _load("model_fn.npz")
+    betas = np.linspace(0.0001, 0.02, 1000, dtype=np.float32)
+    ac = np.cumprod(1.0 - betas, axis=0)
+    red = np.sqrt(1.0 - ac) / np.sqrt(ac)
+    t_step = int(np.abs(red - 37.0 / 255.).argmin())
+    a, b = ac[t_step], 1 - ac[t_step]
+    for tag in ("p", "ddim"):
+        assert np.allclose(g[f"{tag}_score"], -g[f"{tag}_epsilon"] / b ** 0.5, rtol=1e-5, atol=1e-6)
+        assert np.array_equal(g[f"{tag}_both_start"], g[f"{tag}_pred_xstart"])
+        assert np.array_equal(g[f"{tag}_both_prev"], g[f"{tag}_pred_x_prev"])
+    assert np.array_equal(g["p_pred_xstart"], g["ddim_pred_xstart"])
+    assert float(np.abs(g["p_pred_xstart"]).max()) <= 1.0

@@ -49,6 +49,11 @@ def main():
             "dram_bytes_total": tot_r + tot_w, "time_us_total_under_ncu": tot_t,
             "tensor_pipe_pct_time_weighted": sum(float(l["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"][0]) *
                                                  to_us(*l["gpu__time_duration.sum"]) for l in launches) / max(tot_t, 1e-9)}
+    summ["per_launch"] = [{"kernel": l.get("Kernel Name", ("", ""))[0], "dram__bytes_read.sum": to_bytes(*l["dram__bytes_read.sum"]),
+                           "dram__bytes_write.sum": to_bytes(*l["dram__bytes_write.sum"]), "time_us": to_us(*l["gpu__time_duration.sum"]),
+                           "tensor_pipe_pct": float(l["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"][0]),
+                           "lts_hit_pct": float(l["lts__t_sector_hit_rate.pct"][0]) if "lts__t_sector_hit_rate.pct" in l else None}
+                          for l in launches]
     json.dump(summ, open(out + ".json", "w"), indent=1)
     with open(out + ".md", "w") as f:
         f.write(f"# {title}\n\n")
