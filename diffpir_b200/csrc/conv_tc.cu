@@ -718,14 +718,17 @@ __global__ void __launch_bounds__(FUSE ? V4_THREADS : V2_THREADS, 1) k_conv3x3_v
   const int W_SLOT_BYTES = W_TP * V3_W_BYTES;
   auto role_tma = [&]() {
     if (lane == 0) {
-      uint32_t ia = 0, iw = 0;
+      // ring positions are (slot, phase) pairs advanced incrementally: the depths are launch parameters, and a runtime % and /
+      // per stage costs ~20 instructions in every role (ncu source page of the first r02 build)
+      int as = 0, ws_ = 0;
+      uint32_t aph = 0, wph = 0;
       auto load_w = [&](const CUtensorMap *tm, int c0, int co0, int tap0, int ntap, int tap_stride) {
-        const int s = iw % W_SL;
-        mbar_wait(&w_empty[s], ((iw / W_SL) & 1u) ^ 1u);
+        const int s = ws_;
+        mbar_wait(&w_empty[s], wph ^ 1u);
         mbar_expect_tx(&w_full[s], ntap * V3_W_BYTES);
         for (int j = 0; j < ntap; ++j)
           tma_load_3d(w_ring + s * W_SLOT_BYTES + j * V3_W_BYTES, tm, &w_full[s], c0, co0, tap0 + j * tap_stride);
-        ++iw;
+        if (++ws_ == W_SL) { ws_ = 0; wph ^= 1u; }
       };
       // fused kernels: the producers read the raw operand with ordinary global loads whose latency sits on their critical
       // path (load -> activate -> publish); an L2 prefetch of the 18 x 18 halo box `pf_dist` chunks ahead turns it into an
@@ -746,9 +749,10 @@ __global__ void __launch_bounds__(FUSE ? V4_THREADS : V2_THREADS, 1) k_conv3x3_v
       for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++tile_it) {
         int n, h0, w0, co0;
         decode(tile, n, h0, w0, co0);
-        for (int k = 0; k < num_k; ++k, ++ia) {
-          const int s = ia % A_SL;
-          mbar_wait(&a_empty[s], ((ia / A_SL) & 1u) ^ 1u);
+        for (int k = 0; k < num_k; ++k) {
+          const int s = as;
+          mbar_wait(&a_empty[s], aph ^ 1u);
+          if (++as == A_SL) { as = 0; aph ^= 1u; }
           uint8_t *sa = a_ring + s * V2_A_BYTES;
           if (k < num_main) {
             const int ch = k / 3, dx = k - ch * 3;
@@ -773,22 +777,26 @@ __global__ void __launch_bounds__(FUSE ? V4_THREADS : V2_THREADS, 1) k_conv3x3_v
   };
   auto role_mma = [&]() {
     if (lane == 0) {
-      uint32_t ia = 0, iw = 0, tc = 0;
+      uint32_t tc = 0;
+      int as = 0, ws_ = 0;
+      uint32_t rph = 0, wph = 0;
       for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++tc) {
         const uint32_t ab = tc & 1u, aph = (tc >> 1) & 1u;
         mbar_wait(&tmem_empty[ab], aph ^ 1u);
         tc_fence_after();
         const uint32_t d = tmem_base + ab * 256u;
-        for (int k = 0; k < num_k; ++k, ++ia) {
-          const int s = ia % A_SL;
-          mbar_wait(&a_full[s], (ia / A_SL) & 1u);
+        for (int k = 0; k < num_k; ++k) {
+          const int s = as;
+          mbar_wait(&a_full[s], rph);
+          if (++as == A_SL) { as = 0; rph ^= 1u; }
           tc_fence_after();
           const uint32_t sa = smem_u32(a_ring + s * V2_A_BYTES);
           const bool main_stage = k < num_main;
           const int dy_lo = main_stage ? 0 : 1, dy_hi = main_stage ? 3 : 2;
-          for (int dy = dy_lo; dy < dy_hi; ++iw) {
-            const int ws = iw % W_SL;
-            mbar_wait(&w_full[ws], (iw / W_SL) & 1u);
+          for (int dy = dy_lo; dy < dy_hi;) {
+            const int ws = ws_;
+            mbar_wait(&w_full[ws], wph);
+            if (++ws_ == W_SL) { ws_ = 0; wph ^= 1u; }
             tc_fence_after();
             const int nt = main_stage ? W_TP : 1;
             for (int j = 0; j < nt; ++j, ++dy) {
@@ -879,12 +887,14 @@ __global__ void __launch_bounds__(FUSE ? V4_THREADS : V2_THREADS, 1) k_conv3x3_v
       load_tile(tile);
       issue(0);
     }
-    uint32_t it = 0;
+    int rs = 0;
+    uint32_t rph = 0;           // activation-ring position (slot, phase), advanced once per stage
     for (; tile < g.total_tiles; tile += gridDim.x) {
       const int n = ln;                   // image of the tile being transformed (the loader moves on during its last stage)
-      for (int k = 0; k < num_k; ++k, ++it) {
-        const int s = it % A_SL;
-        const uint32_t ph = (it / A_SL) & 1u;
+      for (int k = 0; k < num_k; ++k) {
+        const int s = rs;
+        const uint32_t ph = rph;
+        if (++rs == A_SL) { rs = 0; rph ^= 1u; }
         if (k >= num_main) {               // fused 1x1-skip stage: operand comes by TMA, only keep the barrier count
           mbar_wait(&a_empty[s], ph ^ 1u);
           __syncwarp();
@@ -976,13 +986,15 @@ __global__ void __launch_bounds__(FUSE ? V4_THREADS : V2_THREADS, 1) k_conv3x3_v
       load_tile(tile);
       issue(0);
     }
-    uint32_t it = 0;
+    int rs = 0;
+    uint32_t rph = 0;           // activation-ring position (slot, phase), advanced once per stage
     for (; tile < g.total_tiles; tile += gridDim.x) {
       const int n = ln;
       mask = lmask;
-      for (int k = 0; k < num_k; ++k, ++it) {
-        const int s = it % A_SL;
-        const uint32_t ph = (it / A_SL) & 1u;
+      for (int k = 0; k < num_k; ++k) {
+        const int s = rs;
+        const uint32_t ph = rph;
+        if (++rs == A_SL) { rs = 0; rph ^= 1u; }
         if (k >= num_main) {               // fused 1x1-skip stage: operand comes by TMA, only keep the barrier count
           mbar_wait(&a_empty[s], ph ^ 1u);
           __syncwarp();
@@ -1496,6 +1508,9 @@ int launch_conv_tc(const ConvTcPlan *p, const ConvEpi &epi, int Cout, cudaStream
   ConvTcGeom g = p->g;
   g.Cout = Cout;
   if (p->BN == 16) return launch_tc_impl<16, 4>(p, g, epi, st);
+  // (Small maps - 8x8 / 16x16 - run at ~250 TFLOP/s here.  Deeper rings (9 stages, one CTA per SM) were measured in round 2
+  // and change nothing: with 128 x 64 tiles the arithmetic intensity is 43 FLOP per L2 byte and 128 CTAs pull ~6 TB/s from L2,
+  // i.e. the level is L2-bandwidth bound; the fix is operand multicast across a cluster)
   if (p->BN == 64) return launch_tc_impl<64, 4>(p, g, epi, st);
   return launch_tc_impl<128, 3>(p, g, epi, st);
 }

@@ -76,6 +76,7 @@ struct Op {
   size_t bytes = 0;
   int B = 0, H = 0, W = 0, C1 = 0, C2 = 0, Cin = 0, Cout = 0, ldw = 0, ksize = 0, heads = 0, HW = 0, out_half = 0;
   ConvTcPlan *tc = nullptr;
+  AttnTcPlan *atc = nullptr;                                 // OP_ATTN on the tcgen05 kernel (fp16 qkv)
   bool bind_x = false, bind_t = false, bind_out = false;   // patched with call arguments at launch
 };
 
@@ -83,11 +84,13 @@ struct Plan {
   int B = 0, H = 0, W = 0;
   std::vector<Op> ops;
   std::vector<ConvTcPlan *> tc_plans;
+  std::vector<AttnTcPlan *> attn_plans;
   size_t ws_bytes = 0;
   int final_conv = -1;
   cudaGraphExec_t graph_nchw = nullptr, graph_x0 = nullptr;
   ~Plan() {
     for (auto *p : tc_plans) conv_tc_plan_destroy(p);
+    for (auto *p : attn_plans) attn_tc_plan_destroy(p);
     if (graph_nchw) cudaGraphExecDestroy(graph_nchw);
     if (graph_x0) cudaGraphExecDestroy(graph_x0);
   }
@@ -613,7 +616,7 @@ struct PlanBuilder {
     int xn, d0, d1;
     gn(x, -1, aw.n, -1, 0, RS_NONE, false, false, &xn, &d0, &d1);
     int qkv;
-    conv(xn, aw.qkv, -1, &qkv);
+    conv(xn, aw.qkv, -1, &qkv, /*want_stats=*/false, /*out_half=*/true);   // fp16 in the tensor-core pipelines: the attention's TMA operand
     release(xn);
     const Buf &xb = bufs[x];
     const int aH = xb.H, aW = xb.W;
@@ -622,6 +625,7 @@ struct PlanBuilder {
     op.kind = OP_ATTN;
     op.p0 = bp<float>(qkv); op.q0 = bp<void>(a);
     op.B = B; op.HW = aH * aW; op.Cin = l.cin; op.heads = l.heads; op.out_half = (e->half && !e->split) ? 1 : 0;
+    op.C2 = bufs[qkv].half ? 1 : 0;            // qkv is fp16 -> tcgen05 attention
     plan->ops.push_back(op);
     release(qkv);
     if (e->split) {      // fp32 attention output -> [hi | lo] operand of the proj convolution
@@ -760,6 +764,15 @@ int get_plan(dpir_engine *e, int B, int H, int W, Plan **out) {
     }
     if (op.kind == OP_GN_COEF) { rebase(op.gc.q1, base); rebase(op.gc.q2, base); rebase(op.gc.film, base); rebase(op.gc.coef, base); }
   }
+  for (Op &op : plan->ops) {
+    if (op.kind == OP_ATTN && op.C2) {
+      AttnTcPlan *ap = nullptr;
+      rc = attn_tc_plan_create(op.p0, op.B, op.HW, op.Cin, &ap);
+      if (rc) return rc;
+      op.atc = ap;
+      plan->attn_plans.push_back(ap);
+    }
+  }
   if (e->half) {
     for (Op &op : plan->ops) {
       if (op.kind != OP_CONV) continue;
@@ -854,8 +867,9 @@ int run_plan(dpir_engine *e, Plan *plan, const float *x, const int64_t *t, float
         rc = launch_split_cast((const float *)op.p0, (__half *)op.q0, (int64_t)op.B * op.HW, op.Cin, st);
         break;
       case OP_ATTN:
-        rc = launch_attention((const float *)op.p0, op.q0, op.out_half, op.B, op.HW, op.Cin, op.heads,
-                              e->cfg.use_new_attention_order, st);
+        if (op.atc) rc = launch_attention_tc(op.atc, op.q0, op.out_half, op.heads, e->cfg.use_new_attention_order, st);
+        else rc = launch_attention((const float *)op.p0, op.q0, op.out_half, op.B, op.HW, op.Cin, op.heads,
+                                   e->cfg.use_new_attention_order, st);
         break;
     }
     if (e->profiling) {
@@ -1297,7 +1311,21 @@ int dpir_conv_gnfuse_f16io(const void *src1, int32_t C1, const void *src2, int32
 int dpir_attention(const float *qkv, void *out, int32_t out_half, int32_t B, int32_t T, int32_t C, int32_t heads, int32_t new_order,
                    void *stream) {
   DPIR_REQUIRE(qkv && out, "dpir_attention: null pointer");
-  return launch_attention(qkv, out, out_half, B, T, C, heads, new_order, (cudaStream_t)stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!out_half) return launch_attention(qkv, out, 0, B, T, C, heads, new_order, st);
+  // tensor-core path: the engine's qkv convolution writes fp16; this test entry rounds its fp32 input the same way (stream-ordered
+  // temporary) and runs the tcgen05 kernel on it
+  DPIR_REQUIRE(C == heads * 64 && T >= 1 && B >= 1, "dpir_attention: head dim must be 64");
+  __half *tmp = nullptr;
+  const int64_t n = (int64_t)B * T * 3 * C;
+  DPIR_CUDA_CHECK(cudaMallocAsync(&tmp, (size_t)n * sizeof(__half), st));
+  int rc = launch_cast_half(qkv, tmp, n, st);
+  AttnTcPlan *ap = nullptr;
+  if (!rc) rc = attn_tc_plan_create(tmp, B, T, C, &ap);
+  if (!rc) rc = launch_attention_tc(ap, out, 1, heads, new_order, st);
+  if (ap) attn_tc_plan_destroy(ap);          // the tensor map was copied into the launch parameters
+  cudaFreeAsync(tmp, st);
+  return rc;
 }
 
 int dpir_conv_tc_variant(int32_t variant) {

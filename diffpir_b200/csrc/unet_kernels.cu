@@ -10,7 +10,6 @@
 // Layout: activations NHWC so that channels are the contiguous (coalesced, float4) dimension and so that the same
 // buffers feed the tcgen05 implicit-GEMM convolution (conv_tc.cu) as K-major operands.
 #include "unet_kernels.cuh"
-#include <mma.h>
 #include <cstdlib>
 #include <string>
 
@@ -639,165 +638,37 @@ __global__ void __launch_bounds__(256) k_attention(const float *__restrict__ qkv
   }
 }
 
-// fp16-operand / fp32-accumulate variant for the tensor-core pipelines (legacy warp-level HMMA via nvcuda::wmma: attention
-// is 0.1 % of the UNet FLOPs, so it gets tensor cores the cheap way; q, k, v are rounded to fp16 exactly like every other
-// GEMM operand of this mode, the softmax stays fp32).  One CTA = 64 queries of one (sample, head); 4 warps x 16 query rows.
-// Per 64-key tile: S = Q K^T (16 HMMA per warp) -> smem -> online softmax (fp32, 2 lanes per row) -> P (fp16) -> O += P V
-// with O kept in shared memory so that the per-row rescale needs no knowledge of the fragment layout.
-constexpr int ATW_LDH = 72;    // half row pitch (64 + 8: keeps 16-byte alignment, spreads banks)
-constexpr int ATW_LDF = 68;    // float row pitch
-
-template <typename T>
-__global__ void __launch_bounds__(128) k_attention_wmma(const float *__restrict__ qkv, T *__restrict__ out, int Tn, int C,
-                                                        int heads, int new_order) {
-  using namespace nvcuda;
-  extern __shared__ __align__(32) uint8_t smraw[];
-  __half *Qh = reinterpret_cast<__half *>(smraw);                 // [64][72]
-  __half *Kh = Qh + 64 * ATW_LDH;                                  // [64][72]
-  __half *Vh = Kh + 64 * ATW_LDH;                                  // [64][72]
-  __half *Ph = Vh + 64 * ATW_LDH;                                  // [64][72]
-  float *Sf = reinterpret_cast<float *>(Ph + 64 * ATW_LDH);        // [64][68]  scores of the current key tile
-  float *Of = Sf + 64 * ATW_LDF;                                   // [64][68]  running output
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int q0 = blockIdx.x * 64, h = blockIdx.y, b = blockIdx.z;
-  const int C3 = 3 * C;
-  int qoff, koff, voff;
-  if (new_order) { qoff = h * 64; koff = C + h * 64; voff = 2 * C + h * 64; }
-  else           { qoff = h * 192; koff = qoff + 64; voff = qoff + 128; }
-  const float *base = qkv + (int64_t)b * Tn * C3;
-  // stage Q (scaled by ch^-1/4 like the reference: q * scale, k * scale) and zero O
-  const float sc = 0.35355339059327373f;   // 64^-0.25
-  for (int i = tid; i < 64 * 16; i += 128) {
-    int r = i >> 4, d4 = (i & 15) * 4;
-    float4 v = *reinterpret_cast<const float4 *>(base + (int64_t)(q0 + r) * C3 + qoff + d4);
-    __half2 a = __floats2half2_rn(v.x * sc, v.y * sc), c = __floats2half2_rn(v.z * sc, v.w * sc);
-    *reinterpret_cast<__half2 *>(Qh + r * ATW_LDH + d4) = a;
-    *reinterpret_cast<__half2 *>(Qh + r * ATW_LDH + d4 + 2) = c;
-    *reinterpret_cast<float4 *>(Of + r * ATW_LDF + d4) = make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-  // each row is owned by 2 lanes of its warp: row = warp*16 + lane/2, columns (lane&1)*32 .. +31
-  const int myrow = warp * 16 + (lane >> 1), mycol = (lane & 1) * 32;
-  float m_run = -INFINITY, l_run = 0.f;
-  for (int k0 = 0; k0 < Tn; k0 += 64) {
-    __syncthreads();
-    for (int i = tid; i < 64 * 16; i += 128) {
-      int r = i >> 4, d4 = (i & 15) * 4;
-      const float *rowp = base + (int64_t)(k0 + r) * C3;
-      float4 kv = *reinterpret_cast<const float4 *>(rowp + koff + d4);
-      float4 vv = *reinterpret_cast<const float4 *>(rowp + voff + d4);
-      *reinterpret_cast<__half2 *>(Kh + r * ATW_LDH + d4) = __floats2half2_rn(kv.x * sc, kv.y * sc);
-      *reinterpret_cast<__half2 *>(Kh + r * ATW_LDH + d4 + 2) = __floats2half2_rn(kv.z * sc, kv.w * sc);
-      *reinterpret_cast<__half2 *>(Vh + r * ATW_LDH + d4) = __floats2half2_rn(vv.x, vv.y);
-      *reinterpret_cast<__half2 *>(Vh + r * ATW_LDH + d4 + 2) = __floats2half2_rn(vv.z, vv.w);
-    }
-    __syncthreads();
-    // S[16 x 64] = Q[16 x 64] K^T
-    {
-      wmma::fragment<wmma::accumulator, 16, 16, 16, float> acc[4];
-#pragma unroll
-      for (int n = 0; n < 4; ++n) wmma::fill_fragment(acc[n], 0.f);
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        wmma::fragment<wmma::matrix_a, 16, 16, 16, __half, wmma::row_major> a;
-        wmma::load_matrix_sync(a, Qh + warp * 16 * ATW_LDH + kk * 16, ATW_LDH);
-#pragma unroll
-        for (int n = 0; n < 4; ++n) {
-          wmma::fragment<wmma::matrix_b, 16, 16, 16, __half, wmma::col_major> bf;   // B[k=d][n=key] = Kh[key][d]
-          wmma::load_matrix_sync(bf, Kh + n * 16 * ATW_LDH + kk * 16, ATW_LDH);
-          wmma::mma_sync(acc[n], a, bf, acc[n]);
-        }
-      }
-#pragma unroll
-      for (int n = 0; n < 4; ++n) wmma::store_matrix_sync(Sf + warp * 16 * ATW_LDF + n * 16, acc[n], ATW_LDF, wmma::mem_row_major);
-    }
-    __syncwarp();
-    // online softmax on this warp's 16 rows (2 lanes per row)
-    {
-      float *srow = Sf + myrow * ATW_LDF + mycol;
-      float mx = -INFINITY;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) mx = fmaxf(mx, srow[j]);
-      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-      const float m_new = fmaxf(m_run, mx);
-      const float corr = expf(m_run - m_new);
-      float ps = 0.f;
-      __half *prow = Ph + myrow * ATW_LDH + mycol;
-#pragma unroll
-      for (int j = 0; j < 32; j += 2) {
-        float e0 = expf(srow[j] - m_new), e1 = expf(srow[j + 1] - m_new);
-        __half2 hp = __floats2half2_rn(e0, e1);
-        // sum what is actually multiplied into V (the fp16-rounded probabilities) so that rows stay normalised
-        float2 back = __half22float2(hp);
-        ps += back.x + back.y;
-        *reinterpret_cast<__half2 *>(prow + j) = hp;
-      }
-      ps += __shfl_xor_sync(0xffffffffu, ps, 1);
-      l_run = l_run * corr + ps;
-      m_run = m_new;
-      float *orow = Of + myrow * ATW_LDF + mycol;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) orow[j] *= corr;
-    }
-    __syncwarp();
-    // O[16 x 64] += P[16 x 64] V[64 x 64]
-    {
-      wmma::fragment<wmma::accumulator, 16, 16, 16, float> acc[4];
-#pragma unroll
-      for (int n = 0; n < 4; ++n) wmma::load_matrix_sync(acc[n], Of + warp * 16 * ATW_LDF + n * 16, ATW_LDF, wmma::mem_row_major);
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        wmma::fragment<wmma::matrix_a, 16, 16, 16, __half, wmma::row_major> a;
-        wmma::load_matrix_sync(a, Ph + warp * 16 * ATW_LDH + kk * 16, ATW_LDH);
-#pragma unroll
-        for (int n = 0; n < 4; ++n) {
-          wmma::fragment<wmma::matrix_b, 16, 16, 16, __half, wmma::row_major> bf;   // B[k=key][n=ch] = Vh[key][ch]
-          wmma::load_matrix_sync(bf, Vh + kk * 16 * ATW_LDH + n * 16, ATW_LDH);
-          wmma::mma_sync(acc[n], a, bf, acc[n]);
-        }
-      }
-#pragma unroll
-      for (int n = 0; n < 4; ++n) wmma::store_matrix_sync(Of + warp * 16 * ATW_LDF + n * 16, acc[n], ATW_LDF, wmma::mem_row_major);
-    }
-  }
-  __syncwarp();
-  {
-    const float inv = 1.f / l_run;
-    const float *orow = Of + myrow * ATW_LDF + mycol;
-    T *dst = out + ((int64_t)b * Tn + q0 + myrow) * C + h * 64 + mycol;
-#pragma unroll
-    for (int j = 0; j < 32; j += 4)
-      Store4<T>::st(dst + j, make_float4(orow[j] * inv, orow[j + 1] * inv, orow[j + 2] * inv, orow[j + 3] * inv));
-  }
-}
-
-int launch_attention_tc(const float *qkv, void *out, int out_half, int B, int T, int C, int heads, int new_order, cudaStream_t st);
-
-// out_half (fp16 / fp16s pipelines): the tcgen05 kernel of attention_tc.cu (DPIR_ATTENTION=wmma selects the round-1 HMMA kernel for
-// A/B runs, T % 64 == 0 only); fp32 output (fp32 parity mode, fp16x3 split-precision mode): the fp32 CUDA-core kernel.  Any T.
+// fp32 CUDA-core attention (fp32 parity mode and the fp16x3 split-precision mode): qkv fp32 [B][T][3C] -> out fp32 / fp16 [B][T][C];
+// any T.  The tensor-core pipelines use the tcgen05 kernel of attention_tc.cu on the fp16 qkv tensor (launch_attention_tc).
 int launch_attention(const float *qkv, void *out, int out_half, int B, int T, int C, int heads, int new_order, cudaStream_t st) {
   DPIR_REQUIRE(C == heads * AT_D, "attention: head dim must be 64 (C=%d heads=%d)", C, heads);
   DPIR_REQUIRE(T >= 1, "attention: empty sequence");
-  static int use_wmma = -1;
-  if (use_wmma < 0) { const char *e = getenv("DPIR_ATTENTION"); use_wmma = (e && std::string(e) == "wmma") ? 1 : 0; }
-  if (out_half && !(use_wmma && T % 64 == 0)) return launch_attention_tc(qkv, out, out_half, B, T, C, heads, new_order, st);
   size_t smem = (size_t)4 * AT_D * AT_LD * sizeof(float);
   dim3 grid(cdiv(T, AT_Q), heads, B);
   static bool attr_set[64] = {false};
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
   if (!attr_set[dev]) {
-    constexpr size_t smem_w = (size_t)4 * 64 * ATW_LDH * sizeof(__half) + (size_t)2 * 64 * ATW_LDF * sizeof(float);
     DPIR_CUDA_CHECK(cudaFuncSetAttribute(k_attention<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     DPIR_CUDA_CHECK(cudaFuncSetAttribute(k_attention<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    DPIR_CUDA_CHECK(cudaFuncSetAttribute(k_attention_wmma<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
     attr_set[dev] = true;
   }
-  if (out_half) {
-    constexpr size_t smem_w = (size_t)4 * 64 * ATW_LDH * sizeof(__half) + (size_t)2 * 64 * ATW_LDF * sizeof(float);
-    k_attention_wmma<__half><<<grid, 128, smem_w, st>>>(qkv, (__half *)out, T, C, heads, new_order);
-  } else {
-    k_attention<float><<<grid, 256, smem, st>>>(qkv, (float *)out, T, C, heads, new_order);
-  }
+  if (out_half) k_attention<__half><<<grid, 256, smem, st>>>(qkv, (__half *)out, T, C, heads, new_order);
+  else k_attention<float><<<grid, 256, smem, st>>>(qkv, (float *)out, T, C, heads, new_order);
+  DPIR_LAUNCH_CHECK();
+  return DPIR_OK;
+}
+
+// fp32 -> fp16 elementwise (test entry of the tcgen05 attention: the engine's qkv convolution writes fp16 itself)
+__global__ void k_cast_half(const float *__restrict__ in, __half *__restrict__ out, int64_t n4) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x)
+    Store4<__half>::st(out + 4 * i, *reinterpret_cast<const float4 *>(in + 4 * i));
+}
+int launch_cast_half(const float *in, __half *out, int64_t n, cudaStream_t st) {
+  DPIR_REQUIRE(n % 4 == 0, "cast_half: element count must be a multiple of 4");
+  int64_t blocks = (n / 4 + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  k_cast_half<<<(int)blocks, 256, 0, st>>>(in, out, n / 4);
   DPIR_LAUNCH_CHECK();
   return DPIR_OK;
 }

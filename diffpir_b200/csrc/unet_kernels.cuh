@@ -105,8 +105,14 @@ int launch_gn_stats(const void *src, int src_half, int C, double *qstats, int B,
 int launch_gn_apply(const GnApplyArgs &a, cudaStream_t st);
 int launch_conv_simt(const float *act, const float *w, int ldw, const ConvEpi &epi, int B, int H, int W, int Cin, int Cout,
                      int ksize, cudaStream_t st);
-// qkv fp32 [B,T,3C] -> out [B,T,C] (dtype per out_half); head dim 64
+// fp32 CUDA-core attention: qkv fp32 [B,T,3C] -> out [B,T,C] (dtype per out_half); head dim 64, any T
 int launch_attention(const float *qkv, void *out, int out_half, int B, int T, int C, int heads, int new_order, cudaStream_t st);
+// tcgen05 attention (attention_tc.cu): the plan holds the TMA descriptor over the fp16 qkv tensor [B][T][3C]
+struct AttnTcPlan;
+int attn_tc_plan_create(const void *qkv_half, int B, int T, int C, AttnTcPlan **out);
+void attn_tc_plan_destroy(AttnTcPlan *p);
+int launch_attention_tc(const AttnTcPlan *p, void *out, int out_half, int heads, int new_order, cudaStream_t st);
+int launch_cast_half(const float *in, __half *out, int64_t n, cudaStream_t st);
 // fp32 [npix][C] -> fp16 [npix][hi(C) | lo(C)] (split-precision operand form)
 int launch_split_cast(const float *in, __half *out, int64_t npix, int C, cudaStream_t st);
 // out[i] = clamp(t[i], 0, T-1): the engine's table lookups never leave [0, T)
