@@ -418,10 +418,15 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     dist = None
+    # stdout carries exactly ONE JSON line.  Libraries may write there from C (NCCL prints its version banner when NCCL_DEBUG=VERSION
+    # is set in the environment or in /etc/nccl.conf), so file descriptor 1 points at stderr for the whole run and the line is
+    # written to the saved descriptor at the end.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         import torch.distributed as dist
-        # stdout carries exactly one JSON line: NCCL_DEBUG=VERSION (set on the GPU boxes) makes NCCL print its banner there
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
@@ -681,7 +686,8 @@ def main():
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_prox": prox, "cpu_baseline": cpu,
                 "parity_sample": parity, "strict_mode": strict, "rank_consistency": rank_consistency,
                 "weight_broadcast_ms": t_bcast_ms, "graph": not args.no_graph, "gn_fusion": args.gn_fusion}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

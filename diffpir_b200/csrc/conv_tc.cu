@@ -1231,10 +1231,13 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 static int pow2_ge(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
 int conv_tc_plan_create(const void *act_half, const void *w_half, int B, int H, int W, int Cin_real, int CoutPad, int ksize,
-                        ConvTcPlan **out, int split, int force_bn) {
+                        ConvTcPlan **out, int split, int force_bn, int act_c) {
   DPIR_REQUIRE(Cin_real % TC_BK == 0, "conv_tc: Cin must be a multiple of 64 (got %d)", Cin_real);
   const int Cin = split ? 3 * Cin_real : Cin_real;          // K extent of the weights
-  const int Cact = split ? 2 * Cin_real : Cin_real;         // channels per pixel of the activation tensor ([hi | lo] when split)
+  // channels per pixel of the activation tensor: [hi | lo] when split; act_c > 0: a NARROWER tensor than the K chunk (the stem's
+  // 8-channel operand) - the TMA box still spans 64 channels and the hardware zero-fills the ones that do not exist
+  DPIR_REQUIRE(act_c == 0 || (!split && act_c % 8 == 0 && act_c < Cin_real), "conv_tc: bad narrow-operand width %d", act_c);
+  const int Cact = split ? 2 * Cin_real : (act_c ? act_c : Cin_real);
   DPIR_REQUIRE(ksize == 1 || ksize == 3, "conv_tc: ksize must be 1 or 3");
   DPIR_REQUIRE(CoutPad == 16 || CoutPad % 128 == 0, "conv_tc: padded Cout must be 16 or a multiple of 128 (got %d)", CoutPad);
   DPIR_REQUIRE((((uintptr_t)act_half | (uintptr_t)w_half) & 15) == 0, "conv_tc: operands must be 16-byte aligned");

@@ -58,7 +58,8 @@ struct Buf {   // workspace tensor
   bool has_stats = false;
 };
 
-enum OpKind { OP_MEMSET, OP_TIME_EMBED, OP_FILM, OP_CONV_IN, OP_GN_STATS, OP_GN_APPLY, OP_CONV, OP_ATTN, OP_GN_COEF, OP_SPLIT_CAST };
+enum OpKind { OP_MEMSET, OP_TIME_EMBED, OP_FILM, OP_CONV_IN, OP_GN_STATS, OP_GN_APPLY, OP_CONV, OP_ATTN, OP_GN_COEF, OP_SPLIT_CAST,
+              OP_PACK_STEM };
 struct Op {
   OpKind kind;
   // generic pointers / ints, interpreted per kind
@@ -72,6 +73,8 @@ struct Op {
   const void *w = nullptr;                                   // absolute pointer into the weight arena
   const void *w2 = nullptr;                                  // fused 1x1 skip weights (arena) for the persistent 3x3 kernel
   int Cin2 = 0;                                              // channels of the fused skip operand (p2)
+  int Cin_alg = 0;                                           // algorithmic input channels when the operand is zero-padded (stem: 3 of 64)
+  int act_c = 0;                                             // operand tensor narrower than the K chunk (stem: 8 channels, TMA zero-fills)
   int film_row = -1;                                         // GN apply with FiLM: first row in the FiLM matrix
   size_t bytes = 0;
   int B = 0, H = 0, W = 0, C1 = 0, C2 = 0, Cin = 0, Cout = 0, ldw = 0, ksize = 0, heads = 0, HW = 0, out_half = 0;
@@ -158,6 +161,7 @@ struct dpir_engine {
   std::map<std::string, ResW> resw;
   std::map<std::string, AttnW> attnw;
   ConvW stem, outconv;
+  ConvW stem_tc;              // tensor-core pipelines: the stem as a 3x3 convolution over a 64-channel zero-padded operand
   NormW outnorm;
   size_t te_w0 = 0, te_b0 = 0, te_w2 = 0, te_b2 = 0, film_w = 0, film_b = 0, freqs_off = 0, coef_off = 0;
   int film_rows = 0;
@@ -319,6 +323,11 @@ int build_params(dpir_engine *e) {
       w.w_off = add(p + "weight", PK_CONV_STEM, {l.cout, l.cin, 3, 3}, (size_t)9 * l.cin * l.cout * 4, l.cout).off;
       w.b_off = add_vec(p + "bias", l.cout);
       e->stem = w;
+      if (half && !e->split && l.cout % 128 == 0) {          // fp16 [tap][cout][64] copy, zero beyond the real input channels
+        e->stem_tc = w;
+        e->stem_tc.cin = 64; e->stem_tc.ldw = l.cout;
+        e->stem_tc.w_off = ab.take((size_t)9 * l.cout * 64 * 2);
+      }
     } else if (l.kind == 1) {
       if (l.cin % 128 || l.cout % 128) { set_error("channel counts must be multiples of 128 (%s)", p.c_str()); rc = DPIR_E_ARG; return; }
       ResW r;
@@ -681,11 +690,26 @@ struct PlanBuilder {
     plan->ops.push_back(fl);
 
     std::vector<int> hs;
-    int h = new_buf(B, H, W, e->ch0, e->stream_half, /*want_stats=*/true);
-    Op ci; ci.kind = OP_CONV_IN; ci.bind_x = true; ci.q0 = bp<void>(h); ci.B = B; ci.H = H; ci.W = W;
-    ci.out_half = e->stream_half ? 1 : 0;
-    plan->ops.push_back(ci);
-    emit_stats(h);
+    int h;
+    static int stem_simt = -1;           // DPIR_STEM_SIMT=1: keep the CUDA-core stem in the tensor-core pipelines (A/B timing)
+    if (stem_simt < 0) { const char *ev = getenv("DPIR_STEM_SIMT"); stem_simt = (ev && ev[0] == '1') ? 1 : 0; }
+    if (e->stem_tc.cin && !stem_simt && H >= 16 && W >= 16) {
+      // tensor-core stem: repack x as an 8-channel fp16 NHWC operand (the conv's TMA zero-fills the rest of the 64-channel K chunk),
+      // then the ordinary 3x3 path (bias, store, GroupNorm statistics in the tcgen05 epilogue - no separate statistics pass)
+      int xp = new_buf(B, H, W, 8, true);
+      Op pk; pk.kind = OP_PACK_STEM; pk.bind_x = true; pk.q0 = bp<void>(xp); pk.B = B; pk.H = H; pk.W = W; pk.Cin = e->stem.cin;
+      plan->ops.push_back(pk);
+      conv(xp, e->stem_tc, -1, &h, /*want_stats=*/true, /*out_half=*/e->stream_half);
+      plan->ops.back().Cin_alg = e->stem.cin;
+      plan->ops.back().act_c = 8;
+      release(xp);
+    } else {
+      h = new_buf(B, H, W, e->ch0, e->stream_half, /*want_stats=*/true);
+      Op ci; ci.kind = OP_CONV_IN; ci.bind_x = true; ci.q0 = bp<void>(h); ci.B = B; ci.H = H; ci.W = W;
+      ci.out_half = e->stream_half ? 1 : 0;
+      plan->ops.push_back(ci);
+      emit_stats(h);
+    }
     retain(h); hs.push_back(h);
     for (size_t i = 1; i < e->inputs.size(); ++i) {
       int o;
@@ -777,7 +801,7 @@ int get_plan(dpir_engine *e, int B, int H, int W, Plan **out) {
     for (Op &op : plan->ops) {
       if (op.kind != OP_CONV) continue;
       ConvTcPlan *tp = nullptr;
-      rc = conv_tc_plan_create(op.p0, op.w, op.B, op.H, op.W, op.Cin, op.ldw, op.ksize, &tp, e->split ? 1 : 0);
+      rc = conv_tc_plan_create(op.p0, op.w, op.B, op.H, op.W, op.Cin, op.ldw, op.ksize, &tp, e->split ? 1 : 0, 0, op.act_c);
       if (rc) return rc;
       op.tc = tp;
       plan->tc_plans.push_back(tp);
@@ -830,6 +854,9 @@ int run_plan(dpir_engine *e, Plan *plan, const float *x, const int64_t *t, float
       case OP_CONV_IN:
         rc = launch_conv_in(x, e->ap<float>(e->stem.w_off), e->ap<float>(e->stem.b_off), op.q0, op.out_half, op.B, op.H, op.W,
                             e->stem.cin, e->stem.cout, st);
+        break;
+      case OP_PACK_STEM:
+        rc = launch_pack_stem(x, (__half *)op.q0, op.B, op.Cin, op.H, op.W, st);
         break;
       case OP_GN_STATS:
         rc = launch_gn_stats(op.p0, op.out_half, op.C1, (double *)op.q0, op.B, op.HW, st);
@@ -1074,6 +1101,13 @@ int dpir_load_weight(dpir_engine *e, const char *name, const float *data, const 
       for (int i = 0; i < I; ++i)
         for (int tp = 0; tp < 9; ++tp) pk[((size_t)tp * I + i) * O + o] = data[((size_t)o * I + i) * 9 + tp];
     DPIR_CUDA_CHECK(cudaMemcpy(e->arena + s.off, pk.data(), pk.size() * 4, cudaMemcpyHostToDevice));
+    if (e->stem_tc.cin) {
+      std::vector<__half> ph((size_t)9 * O * 64, __float2half(0.f));
+      for (int o = 0; o < O; ++o)
+        for (int i = 0; i < I; ++i)
+          for (int tp = 0; tp < 9; ++tp) ph[((size_t)tp * O + o) * 64 + i] = __float2half_rn(data[((size_t)o * I + i) * 9 + tp]);
+      DPIR_CUDA_CHECK(cudaMemcpy(e->arena + e->stem_tc.w_off, ph.data(), ph.size() * 2, cudaMemcpyHostToDevice));
+    }
   } else {  // PK_CONV
     int O = (int)s.shape[0], I = (int)s.shape[1];
     int taps = s.shape.size() == 4 ? (int)(s.shape[2] * s.shape[3]) : 1;
@@ -1212,7 +1246,7 @@ int dpir_profile_end(dpir_engine *e, int32_t *kind, int32_t *dims, float *ms, in
   for (int i = 0; i < rows && kind && dims && ms; ++i) {
     const Op &op = e->prof_plan->ops[i];
     kind[i] = (int)op.kind;
-    int H = op.H, W = op.W, Cin = op.Cin, Cout = op.Cout;
+    int H = op.H, W = op.W, Cin = op.Cin_alg ? op.Cin_alg : op.Cin, Cout = op.Cout;
     if (op.kind == OP_GN_APPLY) { H = op.gn.H; W = op.gn.W; Cin = op.gn.C1 + op.gn.C2; Cout = op.gn.resample; }
     if (op.kind == OP_GN_STATS) { H = op.HW; W = 1; Cin = op.C1 + op.C2; Cout = 0; }
     if (op.kind == OP_ATTN || op.kind == OP_SPLIT_CAST) { H = op.HW; W = 1; Cout = op.heads; }

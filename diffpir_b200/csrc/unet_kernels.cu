@@ -133,6 +133,30 @@ int launch_conv_in(const float *x, const float *w, const float *bias, void *out,
   return DPIR_OK;
 }
 
+// Tensor-core pipelines run the stem (input_blocks.0.0, K = 27) on the persistent tcgen05 3x3 kernel like every other convolution:
+// this pass repacks the caller's NCHW fp32 image as NHWC fp16 with 8 channels per pixel (16 bytes, zeros beyond Cin).  The
+// convolution's 4-D TMA box spans a whole 64-channel K chunk of this 8-channel tensor: the hardware zero-fills channels 8..63 like
+// it zero-fills the halo, so the padding costs no memory traffic (the weights are zero-padded to 64 the ordinary way).
+__global__ void k_pack_stem(const float *__restrict__ x, __half *__restrict__ out, int Cin, int64_t HW, int64_t npix) {
+  for (int64_t pix = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; pix < npix; pix += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = pix / HW, p = pix - n * HW;
+    const float *src = x + n * Cin * HW + p;
+    __half h[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) h[c] = __float2half_rn(c < Cin ? __ldg(src + (int64_t)c * HW) : 0.f);
+    *reinterpret_cast<uint4 *>(out + pix * 8) = *reinterpret_cast<const uint4 *>(h);
+  }
+}
+int launch_pack_stem(const float *x_nchw, __half *out, int B, int Cin, int H, int W, cudaStream_t st) {
+  DPIR_REQUIRE(Cin >= 1 && Cin <= 8, "pack_stem: 1..8 input channels");
+  const int64_t npix = (int64_t)B * H * W;
+  int64_t blocks = (npix + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  k_pack_stem<<<(int)blocks, 256, 0, st>>>(x_nchw, out, Cin, (int64_t)H * W, npix);
+  DPIR_LAUNCH_CHECK();
+  return DPIR_OK;
+}
+
 // =========================================================================================== GroupNorm statistics
 // Statistics are attached to the TENSOR, not to the norm: qstats[b][c/4] = (sum, sumsq) over all pixels of channel quad
 // c/4 (fp64).  They are produced where the tensor is produced - the tcgen05 conv epilogue (conv_tc.cu) or this kernel

@@ -101,6 +101,9 @@ __device__ __forceinline__ void conv_epilogue_store(const ConvEpi &e, int n, int
 
 int launch_conv_in(const float *x_nchw, const float *w, const float *bias, void *out, int out_half, int B, int H, int W, int Cin,
                    int Cout, cudaStream_t st);
+// NCHW fp32 (B,Cin<=8,H,W) -> NHWC fp16 [B][H][W][8] (zero-padded to 8 channels = 16 bytes per pixel: the tensor-core stem operand;
+// the convolution's TMA box spans a full 64-channel K chunk and the hardware zero-fills channels 8..63)
+int launch_pack_stem(const float *x_nchw, __half *out, int B, int Cin, int H, int W, cudaStream_t st);
 int launch_gn_stats(const void *src, int src_half, int C, double *qstats, int B, int HW, cudaStream_t st);
 int launch_gn_apply(const GnApplyArgs &a, cudaStream_t st);
 int launch_conv_simt(const float *act, const float *w, int ldw, const ConvEpi &epi, int B, int H, int W, int Cin, int Cout,
@@ -129,7 +132,7 @@ struct ConvTcPlan;  // opaque: tensor maps + geometry
 // split != 0: split-precision operands - act holds [hi | lo] (2*Cin channels per pixel), w is packed [tap][CoutPad][3*Cin] =
 // [w_hi | w_hi | w_lo]; the K loop runs x_hi*w_hi + x_lo*w_hi + x_hi*w_lo in one fp32 accumulation (error ~2^-22)
 int conv_tc_plan_create(const void *act_half, const void *w_half, int B, int H, int W, int Cin, int CoutPad, int ksize,
-                        ConvTcPlan **out, int split = 0, int force_bn = 0);
+                        ConvTcPlan **out, int split = 0, int force_bn = 0, int act_c = 0);
 void conv_tc_plan_destroy(ConvTcPlan *p);
 bool conv_tc_plan_is_v2(const ConvTcPlan *p);
 int conv_tc_plan_add_skip(ConvTcPlan *p, const void *act2_half, const void *w2_half, int Cin2a, const void *act2b_half = nullptr,

@@ -194,7 +194,7 @@ class UNetModel:
         return int(self._lib.dpir_workspace_bytes(self._h))
 
     # ---- per-op device timing (CUDA events inside the engine)
-    OP_KINDS = ("memset", "time_embed", "film", "conv_in", "gn_stats", "gn_apply", "conv", "attention", "gn_coef", "split_cast")
+    OP_KINDS = ("memset", "time_embed", "film", "conv_in", "gn_stats", "gn_apply", "conv", "attention", "gn_coef", "split_cast", "pack_stem")
 
     def set_gn_fusion(self, enable):
         """A/B switch (this model only): 1/True ResBlock GroupNorm+SiLU inside the convolutions (default: producers that activate
