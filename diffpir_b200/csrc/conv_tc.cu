@@ -1473,7 +1473,9 @@ int launch_conv_tc(const ConvTcPlan *p, const ConvEpi &epi, int Cout, cudaStream
         ring[0] = v[0];
       }
       const bool fused = p->gf.coef != nullptr;
-      const bool nores = fused && !epi.residual;
+      static int plain_nores = -1;            // DPIR_CONV_PLAIN_NORES=0: residual-free plain convs keep the 2-box shape (A/B timing)
+      if (plain_nores < 0) { const char *e = getenv("DPIR_CONV_PLAIN_NORES"); plain_nores = (e && e[0] == '0') ? 0 : 1; }
+      const bool nores = !epi.residual && (fused || plain_nores);       // OUT-only staging -> room for 3 boxes + 2 three-tap slots
       g2.a_slots = nores ? ring[7] : (fused ? ring[3] : ring[0]);
       g2.w_slots = nores ? ring[8] : (fused ? ring[4] : ring[1]);
       g2.w_taps = nores ? ring[9] : (fused ? ring[5] : ring[2]);
