@@ -741,7 +741,8 @@ __global__ void __launch_bounds__(FUSE ? V4_THREADS : V2_THREADS, 1) k_conv3x3_v
         int n, h0, w0, co0;
         decode((int)tl, n, h0, w0, co0);
         const int c = (int)ch * TC_BK;
-        if (c < gf.C1) tma_prefetch_4d(&tmA, c, w0 - 1, h0 - 1, n);
+        if (gf.up) tma_prefetch_4d(&tmA, c, (w0 >> 1) - 1, (h0 >> 1) - 1, n);       // the 10 x 10 source box of the 18 x 18 halo
+        else if (c < gf.C1) tma_prefetch_4d(&tmA, c, w0 - 1, h0 - 1, n);
         else tma_prefetch_4d(&tmAb, c - gf.C1, w0 - 1, h0 - 1, n);
       };
       if (FUSE && g.pf_dist > 0)
@@ -967,13 +968,21 @@ __global__ void __launch_bounds__(FUSE ? V4_THREADS : V2_THREADS, 1) k_conv3x3_v
         for (int i = 0; i < 9; ++i) lmask |= ((unsigned)(h0 - 1 + rg + 2 * i) < (unsigned)g.H) ? (1u << i) : 0u;
       }
       if (g.dbg & 32) lmask = 0u;
-      lbase = ((int64_t)ln * g.H + (h0 - 1 + rg)) * g.W + (w0 - 1 + X);
+      if (gf.up) {
+        // nearest-neighbour up-sampling folded into the operand: halo pixel (Y, X) of the OUTPUT grid reads source pixel
+        // (Y >> 1, X >> 1) of the half-resolution tensor; this thread's rows Y = h0 - 1 + rg + 2i map to consecutive source rows
+        // h0/2 - 1 + rg + i (h0 is a multiple of 16), validity stays an output-grid test (the conv pads the UP-SAMPLED tensor)
+        lbase = ((int64_t)ln * (g.H >> 1) + ((h0 >> 1) - 1 + rg)) * (g.W >> 1) + ((w0 - 1 + X) >> 1);
+      } else {
+        lbase = ((int64_t)ln * g.H + (h0 - 1 + rg)) * g.W + (w0 - 1 + X);
+      }
     };
     auto issue = [&](int ch) {             // raw units of chunk ch of the tile described by (lbase, lmask)
       const int c = ch * TC_BK + j * 8;
       const __half *ptr;
       int64_t rs;
-      if (c < gf.C1) { ptr = gf.src1 + lbase * gf.C1 + c; rs = (int64_t)2 * g.W * gf.C1; }
+      if (gf.up) { ptr = gf.src1 + lbase * gf.C1 + c; rs = (int64_t)(g.W >> 1) * gf.C1; }
+      else if (c < gf.C1) { ptr = gf.src1 + lbase * gf.C1 + c; rs = (int64_t)2 * g.W * gf.C1; }
       else { ptr = gf.src2 + lbase * gf.C2 + (c - gf.C1); rs = (int64_t)2 * g.W * gf.C2; }
 #pragma unroll
       for (int i = 0; i < 9; ++i) {
@@ -1070,10 +1079,15 @@ __global__ void __launch_bounds__(FUSE ? V4_THREADS : V2_THREADS, 1) k_conv3x3_v
       float st_s = 0.f, st_q = 0.f;
       const bool full_tile = (h0 + 16 <= g.H) && (w0 + 16 <= g.W);
       const int ybase = h0 + hv * 8;
+      // residual boxes: {32 ch, 16 px, 2 rows} of the output grid, or - res_up - the {32 ch, 8 px, 1 row} source box of the
+      // half-resolution tensor that the two output rows y0, y0 + 1 (y0 even) up-sample
+      const int res_up = epi.res_up;
+      const uint32_t res_bytes = res_up ? 512u : 2048u;
       if (has_res && lane == 0) {          // prefetch the residual box of chunk 0
         uint64_t *bar = &rbar[rcount & 1];
-        mbar_expect_tx(bar, 2048);
-        tma_load_4d((rcount & 1) ? resb1 : resb0, &tmRes, bar, cbase, w0, ybase, n);
+        mbar_expect_tx(bar, res_bytes);
+        if (res_up) tma_load_4d((rcount & 1) ? resb1 : resb0, &tmRes, bar, cbase, w0 >> 1, ybase >> 1, n);
+        else tma_load_4d((rcount & 1) ? resb1 : resb0, &tmRes, bar, cbase, w0, ybase, n);
       }
       mbar_wait_relaxed(&tmem_full[ab], aph);
       tc_fence_after();
@@ -1085,13 +1099,19 @@ __global__ void __launch_bounds__(FUSE ? V4_THREADS : V2_THREADS, 1) k_conv3x3_v
         if (has_res) {
           if (c < 3 && lane == 0) {        // prefetch the next chunk's box into the other buffer (freed one iteration ago)
             uint64_t *bar = &rbar[(rcount + 1) & 1];
-            mbar_expect_tx(bar, 2048);
-            tma_load_4d(((rcount + 1) & 1) ? resb1 : resb0, &tmRes, bar, cbase, w0, y0 + 2, n);
+            mbar_expect_tx(bar, res_bytes);
+            if (res_up) tma_load_4d(((rcount + 1) & 1) ? resb1 : resb0, &tmRes, bar, cbase, w0 >> 1, (y0 + 2) >> 1, n);
+            else tma_load_4d(((rcount + 1) & 1) ? resb1 : resb0, &tmRes, bar, cbase, w0, y0 + 2, n);
           }
           mbar_wait(&rbar[rcount & 1], (rcount >> 1) & 1u);
           const __half *rb = (rcount & 1) ? resb1 : resb0;
+          if (res_up) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __half2float(rb[j * 32 + lane]);
+            for (int j = 0; j < 32; ++j) v[j] = __half2float(rb[((j & 15) >> 1) * 32 + lane]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __half2float(rb[j * 32 + lane]);
+          }
           ++rcount;
         } else {
 #pragma unroll
@@ -1200,6 +1220,7 @@ struct ConvTcPlan {
   CUtensorMap tmOut, tmRes;   // v3: fp16 output / residual tensors for the TMA-store epilogue
   bool io_half = false;       // tmOut (and tmRes when has_res) are valid
   bool has_res = false;
+  bool res_up = false;        // tmRes describes the half-resolution source of an up-sampled residual
   const void *io_out = nullptr, *io_res = nullptr;
 };
 
@@ -1301,16 +1322,18 @@ bool conv_tc_plan_is_v2(const ConvTcPlan *p) { return p->v2; }
 
 // register the (fp16) output / residual tensors of a persistent-kernel plan so that the swap-AB kernel can use its
 // TMA-store epilogue; without it (or with fp32 tensors) the launch falls back to k_conv3x3_v2
-int conv_tc_plan_set_io(ConvTcPlan *p, const void *out, int out_half, const void *residual, int res_half, int Cout) {
+int conv_tc_plan_set_io(ConvTcPlan *p, const void *out, int out_half, const void *residual, int res_half, int Cout, int res_up) {
   p->io_half = false;
+  DPIR_REQUIRE(!res_up || (residual && res_half && p->g.H % 2 == 0 && p->g.W % 2 == 0), "conv_tc: up-sampled residual needs an fp16 tensor and even H, W");
   if (!p->v2 || !out_half || (residual && !res_half) || Cout % 32 != 0) return DPIR_OK;
   auto encode = get_encode_fn();
   if (!encode) { set_error("conv_tc: cuTensorMapEncodeTiled entry point unavailable"); return DPIR_E_CUDA; }
   const ConvTcGeom &g = p->g;
-  auto make = [&](CUtensorMap *tm, const void *ptr) -> int {
-    cuuint64_t gdim[4] = {(cuuint64_t)Cout, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.B};
-    cuuint64_t gstr[3] = {(cuuint64_t)Cout * 2, (cuuint64_t)g.W * Cout * 2, (cuuint64_t)g.H * g.W * Cout * 2};
-    cuuint32_t box[4] = {32, 16, 2, 1};
+  auto make = [&](CUtensorMap *tm, const void *ptr, int up) -> int {
+    const int Ht = up ? g.H / 2 : g.H, Wt = up ? g.W / 2 : g.W;        // the up-sampled residual is read from its half-resolution source
+    cuuint64_t gdim[4] = {(cuuint64_t)Cout, (cuuint64_t)Wt, (cuuint64_t)Ht, (cuuint64_t)g.B};
+    cuuint64_t gstr[3] = {(cuuint64_t)Cout * 2, (cuuint64_t)Wt * Cout * 2, (cuuint64_t)Ht * Wt * Cout * 2};
+    cuuint32_t box[4] = {32, (cuuint32_t)(up ? 8 : 16), (cuuint32_t)(up ? 1 : 2), 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(ptr), gdim, gstr, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
@@ -1318,10 +1341,11 @@ int conv_tc_plan_set_io(ConvTcPlan *p, const void *out, int out_half, const void
     if (r != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled(io) failed: %d", (int)r); return DPIR_E_CUDA; }
     return DPIR_OK;
   };
-  int rc = make(&p->tmOut, out);
+  int rc = make(&p->tmOut, out, 0);
   if (rc) return rc;
   p->tmRes = p->tmOut;
-  if (residual) { rc = make(&p->tmRes, residual); if (rc) return rc; }
+  if (residual) { rc = make(&p->tmRes, residual, res_up); if (rc) return rc; }
+  p->res_up = res_up != 0;
   p->io_half = true;
   p->has_res = residual != nullptr;
   p->io_out = out;
@@ -1375,6 +1399,8 @@ int conv_tc_plan_add_skip(ConvTcPlan *p, const void *act2_half, const void *w2_h
 // per-(image, channel) coefficient table of launch_gn_coef; needs the swap-AB kernel with its fp16 TMA-store epilogue
 int conv_tc_plan_set_gn_fuse(ConvTcPlan *p, const GnFuse &gf, int math) {
   p->gf_math = (math == 1 || math == 2) ? math : (math == 0 ? g_gnfuse_math : 3);
+  DPIR_REQUIRE(!gf.up || (p->gf_math == 3 && gf.C2 == 0 && p->g.H % 2 == 0 && p->g.W % 2 == 0),
+               "conv_tc: the up-sampling index map needs the activate-once producers, one source and even H, W");
   DPIR_REQUIRE(p->v2 && p->use_v3 && !p->split, "conv_tc: GroupNorm fusion needs the persistent swap-AB 3x3 kernel");
   DPIR_REQUIRE(gf.src1 && gf.coef && gf.C1 % TC_BK == 0 && gf.C2 % TC_BK == 0 && gf.C1 + gf.C2 == p->g2.Cin && (gf.C2 == 0 || gf.src2),
                "conv_tc: bad GroupNorm fusion operands (C1 %d, C2 %d, Cin %d)", gf.C1, gf.C2, p->g2.Cin);
@@ -1386,9 +1412,10 @@ int conv_tc_plan_set_gn_fuse(ConvTcPlan *p, const GnFuse &gf, int math) {
   if (!encode) { set_error("conv_tc: cuTensorMapEncodeTiled entry point unavailable"); return DPIR_E_CUDA; }
   const ConvTcGeom &g = p->g;
   auto make = [&](CUtensorMap *tm, const void *ptr, int C) -> int {
-    cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.B};
-    cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)g.W * C * 2, (cuuint64_t)g.H * g.W * C * 2};
-    cuuint32_t box[4] = {(cuuint32_t)TC_BK, 18, 18, 1};
+    const int Hs = gf.up ? g.H / 2 : g.H, Ws = gf.up ? g.W / 2 : g.W;
+    cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)Ws, (cuuint64_t)Hs, (cuuint64_t)g.B};
+    cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)Ws * C * 2, (cuuint64_t)Hs * Ws * C * 2};
+    cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)(gf.up ? 10 : 18), (cuuint32_t)(gf.up ? 10 : 18), 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(ptr), gdim, gstr, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -1487,6 +1514,7 @@ int launch_conv_tc(const ConvTcPlan *p, const ConvEpi &epi, int Cout, cudaStream
       }
     }
     int grid = g2.total_tiles < g_num_sms ? g2.total_tiles : g_num_sms;
+    DPIR_REQUIRE((epi.res_up != 0) == p->res_up, "conv_tc: up-sampled residual not planned for this convolution");
     const bool v3_ok = !p->split && p->use_v3 && p->io_half && epi.out_half && epi.out == p->io_out && epi.residual == p->io_res &&
                        (!epi.residual || epi.res_half);
     DPIR_REQUIRE(v3_ok || (!p->gf.coef && g2.skip_chunks_a == g2.skip_chunks),

@@ -483,8 +483,9 @@ struct PlanBuilder {
   }
 
   int conv(int act, const ConvW &cw, int residual, int *out_id, bool want_stats = false, bool out_half = false,
-           int skip_act = -1, const ConvW *skip_w = nullptr, int skip_act2 = -1) {
-    const Buf a = bufs[act];   // by value: new_buf() below may reallocate `bufs`
+           int skip_act = -1, const ConvW *skip_w = nullptr, int skip_act2 = -1, bool up = false) {
+    Buf a = bufs[act];   // by value: new_buf() below may reallocate `bufs`
+    if (up) { a.H *= 2; a.W *= 2; }                    // `act` is the half-resolution source of an up-sampled (index-mapped) operand
     out_half = out_half && e->half && !e->split;       // split-precision mode keeps every conv output in fp32
     *out_id = new_buf(B, a.H, a.W, cw.cout, out_half, want_stats);
     if (residual >= 0 && bufs[residual].half && !e->half) { set_error("internal: fp16 residual in fp32 mode"); err = DPIR_E_STATE; }
@@ -558,6 +559,36 @@ struct PlanBuilder {
     return true;
   }
 
+  // Up-sampling ResBlock (unet.py:237-244, 256: h = conv1(up(SiLU(GN(x)))), out = up(x) + conv2(...)) without the up-sampled
+  // tensors: conv1's producers read x through the nearest-neighbour index map (GroupNorm statistics of up(x) = those of x), conv2's
+  // epilogue reads its residual up(x) from x the same way.  Saves the k_gn_apply pass that wrote up(SiLU(GN(x))) and up(x) at 4x
+  // the pixels.  fp16 stream + activate-once producers only.
+  bool up_fusable(const LayerDesc &l, int x, int skip, const ResW &rw) const {
+    const Buf &a = bufs[x];
+    static int up_fuse = -1;           // DPIR_UP_FUSE=0 switches it off (A/B timing)
+    if (up_fuse < 0) { const char *ev = getenv("DPIR_UP_FUSE"); up_fuse = (ev && ev[0] == '0') ? 0 : 1; }
+    return up_fuse && e->gn_fuse && e->gn_math == 3 && e->stream_half && conv_tc_swapab_enabled() && l.updown == RS_UP && skip < 0 &&
+           !rw.has_skip && a.half && a.H >= 8 && a.W >= 8 && a.C % 64 == 0 && rw.c1.ksize == 3 && rw.c2.ksize == 3 &&
+           rw.c1.ldw % 128 == 0 && rw.c2.ldw % 128 == 0 && rw.c1.cout % 64 == 0;
+  }
+  int resblock_up_fused(const LayerDesc &l, int x, int *out) {
+    const ResW &rw = e->resw[l.prefix];
+    int c1 = gn_coef(x, -1, rw.n1, -1);
+    int h1;
+    conv(x, rw.c1, -1, &h1, /*want_stats=*/true, /*out_half=*/true, -1, nullptr, -1, /*up=*/true);
+    fuse_last_conv(x, -1, c1);
+    plan->ops.back().gf.up = 1;
+    release(c1);
+    int a2, d0, d1;
+    gn(h1, -1, rw.n2, rw.film_row, 1, RS_NONE, false, false, &a2, &d0, &d1);
+    release(h1);
+    conv(a2, rw.c2, x, out, /*want_stats=*/true, /*out_half=*/true);        // residual = x at half resolution, index-mapped in the epilogue
+    plan->ops.back().epi.res_up = 1;
+    release(a2);
+    release(x);
+    return DPIR_OK;
+  }
+
   int resblock_fused(const LayerDesc &l, int x, int skip, int *out) {
     const ResW &rw = e->resw[l.prefix];
     // in_layers: conv1(SiLU(GN(x | skip)))
@@ -584,6 +615,7 @@ struct PlanBuilder {
   int resblock(const LayerDesc &l, int x, int skip, int *out) {
     const ResW &rw = e->resw[l.prefix];
     if (gn_fusable(l, x, skip, rw)) return resblock_fused(l, x, skip, out);
+    if (up_fusable(l, x, skip, rw)) return resblock_up_fused(l, x, out);
     bool concat = skip >= 0;
     bool need_raw32 = !rw.has_skip && (l.updown != RS_NONE || concat);
     int a1, xr, xraw;
@@ -806,7 +838,7 @@ int get_plan(dpir_engine *e, int B, int H, int W, Plan **out) {
       op.tc = tp;
       plan->tc_plans.push_back(tp);
       if (conv_tc_plan_is_v2(tp) && !op.bind_out) {
-        rc = conv_tc_plan_set_io(tp, op.epi.out, op.epi.out_half, op.epi.residual, op.epi.res_half, op.Cout);
+        rc = conv_tc_plan_set_io(tp, op.epi.out, op.epi.out_half, op.epi.residual, op.epi.res_half, op.Cout, op.epi.res_up);
         if (rc) return rc;
       }
       if (op.p2) {

@@ -33,6 +33,9 @@ struct ConvEpi {
   const float *bias2;       // second bias (fused 1x1 skip convolution) or null; tensor-core NHWC epilogue only
   const float *residual;    // NHWC [B,H,W,Cout] fp32 (or fp16 when res_half) or null (EPI_NHWC only)
   int res_half;             // 1: residual is __half (tensor-core epilogues only)
+  int res_up;               // 1 (swap-AB kernel only): the residual tensor has HALF the resolution (B, H/2, W/2, Cout) and is read through
+                            // the nearest-neighbour index map (y >> 1, x >> 1): the h_upd / x_upd of an up-sampling ResBlock
+                            // (unet.py:237-244) without materialising the up-sampled tensor
   float *out;               // NHWC [B,H,W,Cout] | NCHW [B,Cout,H,W] | x0 NCHW [B,3,H,W]
   int out_half;             // EPI_NHWC on tensor cores: store __half instead of float (out is then a __half*)
   double *qstats;           // EPI_NHWC on tensor cores: accumulate quad statistics [B][Cout/4][2] of the stored tensor, or null
@@ -49,6 +52,9 @@ struct GnFuse {
   const __half *src1 = nullptr, *src2 = nullptr;   // raw NHWC fp16 source(s); src2 = second half of a virtual concat or null
   int C1 = 0, C2 = 0;
   const float *coef = nullptr;                     // [B][2][C1+C2] from launch_gn_coef: 0.5*scale, 0.5*offset; null = no fusion
+  int up = 0;                                      // 1: src1 has HALF the convolution's resolution and is read through the nearest-
+                                                   // neighbour index map (y >> 1, x >> 1): conv(upsample(SiLU(GN(x)))) of an up-sampling
+                                                   // ResBlock (unet.py:237-241) without the up-sampled tensor (activate-once producers only)
 };
 
 // per-(image, channel) affine form of GroupNorm(+FiLM): act = SiLU(scale*x + offset); writes 0.5*scale, 0.5*offset
@@ -139,7 +145,7 @@ int conv_tc_plan_add_skip(ConvTcPlan *p, const void *act2_half, const void *w2_h
                           int Cin2b = 0);
 // math: producer flavour - 3 activate-once (default), 1 per-tap fp32, 2 per-tap packed half, 0 = the process-wide test default
 int conv_tc_plan_set_gn_fuse(ConvTcPlan *p, const GnFuse &gf, int math = 0);
-int conv_tc_plan_set_io(ConvTcPlan *p, const void *out, int out_half, const void *residual, int res_half, int Cout);
+int conv_tc_plan_set_io(ConvTcPlan *p, const void *out, int out_half, const void *residual, int res_half, int Cout, int res_up = 0);
 int launch_conv_tc(const ConvTcPlan *p, const ConvEpi &epi, int Cout, cudaStream_t st);
 bool conv_tc_v2_enabled();
 void conv_tc_set_gnfuse_math(int m);   // producer flavour used by the per-kernel test entry (3 default, 1, 2)
