@@ -1203,6 +1203,216 @@ __global__ void __launch_bounds__(FUSE ? V4_THREADS : V2_THREADS, 1) k_conv3x3_v
   if (warp == MMA_WARP) tmem_dealloc<512>(tmem_base);
 }
 
+// ------------------------------------------------------------------------------------------------ narrow-output 3x3 kernel
+// The UNet's output layer (unet.py:617-621: conv 3x3, model_channels -> 6) has too few output channels for the swap-AB kernel (M =
+// couts) and ran on k_conv_tc<16, 4>, which fetches the 128-pixel activation tile once per tap: 9x the tensor through L2 (ncu/r02:
+// 0.42 ms for a 0.54 GB tensor = 11.6 TB/s of L2->SM traffic, the crossbar's limit).  k_conv3x3_dxn reads every halo box ONCE per
+// 64-channel chunk by moving the horizontal taps into the N dimension of the MMA:
+//   * M = 128 box pixels (8 image rows x the 16 columns of the box), N = 48 = (dx, cout padded to 16), K = 64 channels: for the
+//     vertical tap dy the A operand is the view of the {64 ch, 16 px, 18 rows} halo box starting dy (+ 8 for the lower half-tile)
+//     rows down (2048 B: still SWIZZLE_128B aligned), the B operand the 48 weight rows [dx][16 couts] of that dy - which are
+//     CONTIGUOUS in the packed weight tensor [tap = dy*3 + dx][16][Cin], so a {64, 48, 1} TMA box over the same buffer delivers them;
+//   * D[pixel p][dx*16 + o] then holds tap (dy summed, dx) applied AT box pixel p; the output at box column xb is
+//     D[xb - 1][0*16 + o] + D[xb][1*16 + o] + D[xb + 1][2*16 + o]: two warp shuffles per channel in the epilogue (TMEM lane = box
+//     pixel, 16 consecutive lanes = one image row).  Box columns 0 and 15 are halo only: a tile produces 14 x 16 output pixels;
+//   * all weights (chunks x 3 x 6 KB) stay resident in shared memory; the activation ring holds 3-4 halo boxes; persistent CTAs,
+//     two TMEM accumulator sets so the epilogue of tile i overlaps the loads / MMAs of tile i + 1.
+// L2->SM traffic per output pixel: 36 KB x chunks / 224 px instead of 9 x 16 KB x chunks / 128 px (3.5x less).
+constexpr int DXN_THREADS = 320;                      // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
+constexpr int DXN_W_BYTES = 48 * 128;                 // one (chunk, dy) weight tile: 48 rows x 64 fp16
+constexpr int DXN_MAX_CHUNKS = 6;
+constexpr int DXN_ACT_WARPS = 8;                      // FUSE: warps 10-17 activate the halo boxes in place
+struct ConvDxnGeom {
+  int B, H, W, Cout, chunks, a_wrap;
+  int tiles_w, tiles_h, total_tiles;                 // 14 x 16 output-pixel tiles
+  int a_slots;
+  const float *coef;                                 // FUSE: [B][2][C] GroupNorm(+FiLM) coefficients of launch_gn_coef (C = chunks * 64)
+};
+
+// FUSE: the operand is SiLU(GroupNorm(x)) of the RAW tensor the TMA fetched (the UNet's out.0 / out.1, unet.py:617-619): eight
+// activator warps rewrite every halo box in place (thread = channel octet x box pixel mod 32: 9 x LDS.128 -> 8 x (fma, tanh, fma)
+// -> STS.128 at the same swizzled address), write exact zeros outside the image (the convolution pads the ACTIVATED tensor; the
+// TMA's zero fill would activate to SiLU(offset)), and hand the box to the MMA warp through fence.proxy.async + a second barrier.
+template <bool FUSE>
+__global__ void __launch_bounds__(FUSE ? DXN_THREADS + 32 * DXN_ACT_WARPS : DXN_THREADS, 1)
+    k_conv3x3_dxn(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, ConvDxnGeom g, ConvEpi epi) {
+  // M = 128 (box pixels), N = 48 (dx x 16 couts)
+  constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(48 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t *a_full = reinterpret_cast<uint64_t *>(smem);
+  uint64_t *a_empty = a_full + 4;
+  uint64_t *a_ready = a_empty + 4;             // FUSE: box activated (one arrive per activator warp)
+  uint64_t *w_full = a_ready + 4;
+  uint64_t *tmem_full = w_full + 1;            // [2]
+  uint64_t *tmem_empty = tmem_full + 2;        // [2]
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+  uint8_t *w_sm = smem + 1024;                                   // [chunks][3 dy][48 x 128 B]
+  uint8_t *a_ring = w_sm + g.chunks * 3 * DXN_W_BYTES;           // [a_slots][V2_A_BYTES]
+  const int A_SL = g.a_slots;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmW);
+    for (int s = 0; s < A_SL; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); mbar_init(&a_ready[s], DXN_ACT_WARPS); }
+    mbar_init(w_full, 1);
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 8); }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) tmem_alloc<256>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto decode = [&](int tile, int &n, int &h0, int &w0) {
+    w0 = (tile % g.tiles_w) * 14;
+    h0 = ((tile / g.tiles_w) % g.tiles_h) * 16;
+    n = tile / (g.tiles_w * g.tiles_h);
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(w_full, (uint32_t)(g.chunks * 3 * DXN_W_BYTES));
+      for (int ch = 0; ch < g.chunks; ++ch)
+        for (int dy = 0; dy < 3; ++dy) tma_load_3d(w_sm + (ch * 3 + dy) * DXN_W_BYTES, &tmW, w_full, ch * TC_BK, 0, dy);
+      int as = 0;
+      uint32_t aph = 0;
+      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+        int n, h0, w0;
+        decode(tile, n, h0, w0);
+        for (int ch = 0; ch < g.chunks; ++ch) {
+          const int s = as;
+          mbar_wait(&a_empty[s], aph ^ 1u);
+          if (++as == A_SL) { as = 0; aph ^= 1u; }
+          mbar_expect_tx(&a_full[s], V2_A_BYTES);
+          const int ach = ch >= g.a_wrap ? ch - g.a_wrap : ch;
+          tma_load_4d(a_ring + s * V2_A_BYTES, &tmA, &a_full[s], ach * TC_BK, w0 - 1, h0 - 1, n);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      mbar_wait(w_full, 0);
+      tc_fence_after();
+      uint32_t tc = 0;
+      int as = 0;
+      uint32_t rph = 0;
+      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++tc) {
+        const uint32_t ab = tc & 1u, aph = (tc >> 1) & 1u;
+        mbar_wait(&tmem_empty[ab], aph ^ 1u);
+        tc_fence_after();
+        const uint32_t d = tmem_base + ab * 128u;
+        for (int ch = 0; ch < g.chunks; ++ch) {
+          const int s = as;
+          mbar_wait(FUSE ? &a_ready[s] : &a_full[s], rph);
+          if (++as == A_SL) { as = 0; rph ^= 1u; }
+          tc_fence_after();
+          const uint32_t sa = smem_u32(a_ring + s * V2_A_BYTES);
+#pragma unroll
+          for (int dy = 0; dy < 3; ++dy) {
+            const uint64_t wdesc = make_sw128_desc(smem_u32(w_sm + (ch * 3 + dy) * DXN_W_BYTES));      // B: 48 (dx, cout) rows x 64 k
+#pragma unroll
+            for (int mb = 0; mb < 2; ++mb) {
+              const uint64_t pdesc = make_sw128_desc(sa + (uint32_t)((dy + mb * 8) * 16 * 128));       // A: 128 box pixels x 64 k
+#pragma unroll
+              for (int kk = 0; kk < TC_BK / 16; ++kk)
+                umma_f16(d + (uint32_t)mb * 64u, pdesc + (uint64_t)(2 * kk), wdesc + (uint64_t)(2 * kk), IDESC, (ch | dy | kk) ? 1u : 0u);
+            }
+          }
+          umma_commit(&a_empty[s]);
+        }
+        umma_commit(&tmem_full[ab]);
+      }
+    }
+  } else if (FUSE && warp >= 10) {
+    // ---------------------------------------------------------------- activators: 256 threads, 9 units of 16 B each per box
+    const int t = (int)threadIdx.x - DXN_THREADS;
+    const int j = t & 7, pix = t >> 3;                   // channel octet, box pixel mod 32 (box row 2i + (pix >> 4), column pix & 15)
+    const int xb = pix & 15, yo = pix >> 4;
+    const uint32_t off = (uint32_t)(pix * 128 + ((j ^ (pix & 7)) << 4));
+    const int C = g.chunks * TC_BK;
+    int as = 0;
+    uint32_t rph = 0;
+    for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+      int n, h0, w0;
+      decode(tile, n, h0, w0);
+      uint32_t vmask = 0;                                // validity of this thread's 9 box rows (all-zero when its column is outside)
+      if ((unsigned)(w0 - 1 + xb) < (unsigned)g.W) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) vmask |= ((unsigned)(h0 - 1 + yo + 2 * i) < (unsigned)g.H) ? (1u << i) : 0u;
+      }
+      for (int ch = 0; ch < g.chunks; ++ch) {
+        const int s = as;
+        const uint32_t ph = rph;
+        if (++as == A_SL) { as = 0; rph ^= 1u; }
+        const float *cf = g.coef + (int64_t)n * 2 * C + ch * TC_BK + j * 8;
+        const float4 a0 = __ldg(reinterpret_cast<const float4 *>(cf)), a1 = __ldg(reinterpret_cast<const float4 *>(cf + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4 *>(cf + C)), b1 = __ldg(reinterpret_cast<const float4 *>(cf + C + 4));
+        const float hs[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float ho[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        mbar_wait(&a_full[s], ph);
+        uint8_t *base = a_ring + s * V2_A_BYTES + off;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+          uint4 *up = reinterpret_cast<uint4 *>(base + i * 4096);
+          const uint4 raw = *up;
+          uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&w[q]));
+            const float ha = fmaf(f.x, hs[2 * q], ho[2 * q]), hb = fmaf(f.y, hs[2 * q + 1], ho[2 * q + 1]);
+            const __half2 r = __floats2half2_rn(fmaf(ha, tanh_approx_f(ha), ha), fmaf(hb, tanh_approx_f(hb), hb));
+            w[q] = *reinterpret_cast<const uint32_t *>(&r);
+          }
+          const bool ok = (vmask >> i) & 1u;
+          *up = make_uint4(ok ? w[0] : 0u, ok ? w[1] : 0u, ok ? w[2] : 0u, ok ? w[3] : 0u);
+        }
+        fence_proxy_async();                             // generic-proxy writes -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_ready[s]);
+      }
+    }
+  } else if (warp < 10) {
+    // ---------------------------------------------------------------- epilogue: TMEM lane = box pixel (row yy = lane quarter*2 +
+    // lane/16 of the half-tile mb, column xb = lane % 16)
+    const int q = warp & 3, mb = (warp - 2) >> 2;
+    const int xb = lane & 15, yy = q * 2 + (lane >> 4);
+    const int ncols = g.Cout;
+    uint32_t tc = 0;
+    for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++tc) {
+      const uint32_t ab = tc & 1u, aph = (tc >> 1) & 1u;
+      int n, h0, w0;
+      decode(tile, n, h0, w0);
+      mbar_wait_relaxed(&tmem_full[ab], aph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * 128u + (uint32_t)mb * 64u;
+      uint32_t r0[16], r1[16], r2[16];
+      tmem_ld16(taddr, r0);
+      tmem_ld16(taddr + 16u, r1);
+      tmem_ld16(taddr + 32u, r2);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[ab]);
+      float acc[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float left = __shfl_up_sync(0xffffffffu, __uint_as_float(r0[j]), 1);      // tap dx = 0 evaluated at box column xb - 1
+        const float right = __shfl_down_sync(0xffffffffu, __uint_as_float(r2[j]), 1);   // tap dx = 2 evaluated at box column xb + 1
+        acc[j] = (left + __uint_as_float(r1[j])) + right;
+      }
+      const int x = w0 + xb - 1, y = h0 + mb * 8 + yy;
+      if (xb >= 1 && xb <= 14 && x < g.W && y < g.H) conv_epilogue_store(epi, n, y, x, g.H, g.W, g.Cout, 0, acc, ncols);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<256>(tmem_base);
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 struct ConvTcPlan {
   CUtensorMap tmA, tmB;
@@ -1222,11 +1432,14 @@ struct ConvTcPlan {
   bool has_res = false;
   bool res_up = false;        // tmRes describes the half-resolution source of an up-sampled residual
   const void *io_out = nullptr, *io_res = nullptr;
+  bool dxn = false;           // narrow-output 3x3 kernel (k_conv3x3_dxn): tmA has the halo box, tmW3 the {64, 48, 1} weight box
+  CUtensorMap tmW3;
+  ConvDxnGeom gd{};
 };
 
 static int g_force_v1 = 0;   // dpir_conv_tc_variant: 0 = auto (persistent swap-AB v3), 1 = v1 everywhere, 2 = persistent v2
 // per-device launch state: cudaFuncSetAttribute and the SM count belong to a device, and one process may drive several
-struct DevState { bool attr_v1[3] = {false, false, false}; bool attr_v3 = false; int num_sms = 0; };
+struct DevState { bool attr_v1[3] = {false, false, false}; bool attr_v3 = false; int attr_dxn = 0; int num_sms = 0; };
 static DevState g_dev[64];
 static DevState *dev_state() {
   int dev = 0;
@@ -1281,6 +1494,15 @@ int conv_tc_plan_create(const void *act_half, const void *w_half, int B, int H, 
   if (!p->v2 && CoutPad != 16 && g.tiles_w * g.tiles_h * g.tiles_n * (CoutPad / 128) < 100) p->BN = 64;
   if (force_bn) p->BN = force_bn;
   p->use_v3 = g_force_v1 == 0;
+  p->dxn = !force_bn && ksize == 3 && conv_tc_narrow_eligible(H, W, Cin, CoutPad);
+  if (p->dxn) {
+    ConvDxnGeom &gd = p->gd;
+    gd.B = B; gd.H = H; gd.W = W; gd.Cout = 0; gd.chunks = Cin / TC_BK; gd.a_wrap = g.a_wrap;
+    gd.tiles_w = cdiv(W, 14); gd.tiles_h = cdiv(H, 16);
+    gd.total_tiles = B * gd.tiles_w * gd.tiles_h;
+    const int budget = 227 * 1024 - 2048 - gd.chunks * 3 * DXN_W_BYTES;
+    gd.a_slots = budget / V2_A_BYTES > 4 ? 4 : budget / V2_A_BYTES;
+  }
   if (p->v2) {
     ConvV2Geom &g2 = p->g2;
     g2.B = B; g2.H = H; g2.W = W; g2.Cin = Cin; g2.Cout = 0; g2.skip_chunks = 0; g2.skip_chunks_a = 0; g2.dbg = 0;
@@ -1288,12 +1510,14 @@ int conv_tc_plan_create(const void *act_half, const void *w_half, int B, int H, 
     g2.tiles_w = cdiv(W, 16); g2.tiles_h = cdiv(H, 16); g2.n_tiles = CoutPad / 128;
     g2.total_tiles = B * g2.tiles_w * g2.tiles_h * g2.n_tiles;
     g2.a_slots = V3_A_SLOTS; g2.w_slots = V3_W_SLOTS; g2.w_taps = 1; g2.pf_dist = 0; g2.stg_stride = 6144;
+    // (the stem's 8-channel operand: issuing only the first K = 16 step of its zero-filled chunk was measured in round 2 and changes
+    // nothing - 0.236 vs 0.228 ms - the stem is bound by its epilogue, 4.2 us per tile)
   }
   {
     cuuint64_t gdim[4] = {(cuuint64_t)Cact, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t gstr[3] = {(cuuint64_t)Cact * 2, (cuuint64_t)W * Cact * 2, (cuuint64_t)H * W * Cact * 2};
     cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)g.TW, (cuuint32_t)g.TH, (cuuint32_t)g.TN};
-    if (p->v2) { box[1] = 16; box[2] = 18; box[3] = 1; }
+    if (p->v2 || p->dxn) { box[1] = 16; box[2] = 18; box[3] = 1; }
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = encode(&p->tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(act_half), gdim, gstr, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -1310,6 +1534,18 @@ int conv_tc_plan_create(const void *act_half, const void *w_half, int B, int H, 
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled(B) failed: %d", (int)r); delete p; return DPIR_E_CUDA; }
   }
+  p->tmW3 = p->tmB;
+  if (p->dxn) {
+    // the packed weights [tap = dy*3 + dx][16][Cin] seen as [dy][dx*16 + cout][Cin]: one box = the 48 rows of a vertical tap
+    cuuint64_t gdim[3] = {(cuuint64_t)Cin, 48, 3};
+    cuuint64_t gstr[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)48 * Cin * 2};
+    cuuint32_t box[3] = {(cuuint32_t)TC_BK, 48, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode(&p->tmW3, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void *>(w_half), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled(W3) failed: %d", (int)r); delete p; return DPIR_E_CUDA; }
+  }
   p->tmA2 = p->tmA;
   p->tmA2b = p->tmA;
   p->tmAb = p->tmA;
@@ -1319,6 +1555,14 @@ int conv_tc_plan_create(const void *act_half, const void *w_half, int B, int H, 
 }
 
 bool conv_tc_plan_is_v2(const ConvTcPlan *p) { return p->v2; }
+
+// whether a 3x3 convolution with K extent Cin (3x the channels for split-precision operands) and CoutPad padded weight rows runs on
+// the narrow-output kernel k_conv3x3_dxn
+bool conv_tc_narrow_eligible(int H, int W, int Cin, int CoutPad) {
+  static int dxn_on = -1;                // DPIR_OUT_DXN=0: narrow-output convs stay on k_conv_tc<16, 4> (A/B timing)
+  if (dxn_on < 0) { const char *e = getenv("DPIR_OUT_DXN"); dxn_on = (e && e[0] == '0') ? 0 : 1; }
+  return dxn_on && g_force_v1 == 0 && CoutPad == 16 && H >= 16 && W >= 16 && Cin / TC_BK <= DXN_MAX_CHUNKS;
+}
 
 // register the (fp16) output / residual tensors of a persistent-kernel plan so that the swap-AB kernel can use its
 // TMA-store epilogue; without it (or with fp32 tensors) the launch falls back to k_conv3x3_v2
@@ -1398,6 +1642,13 @@ int conv_tc_plan_add_skip(ConvTcPlan *p, const void *act2_half, const void *w2_h
 // v4: the activation operand is SiLU(GroupNorm(src)) computed inside the kernel from the raw fp16 source(s) and the
 // per-(image, channel) coefficient table of launch_gn_coef; needs the swap-AB kernel with its fp16 TMA-store epilogue
 int conv_tc_plan_set_gn_fuse(ConvTcPlan *p, const GnFuse &gf, int math) {
+  if (p->dxn) {           // narrow-output kernel: the TMA fetches the raw tensor (tmA already describes it), activator warps apply the norm
+    DPIR_REQUIRE(!p->split && gf.src1 && gf.coef && gf.C2 == 0 && !gf.up && gf.C1 == p->gd.chunks * TC_BK,
+                 "conv_tc: the narrow-output kernel fuses the norm of ONE full-resolution source (C1 %d)", gf.C1);
+    DPIR_REQUIRE(((uintptr_t)gf.coef & 15) == 0, "conv_tc: fused operands must be 16-byte aligned");
+    p->gf = gf;
+    return DPIR_OK;
+  }
   p->gf_math = (math == 1 || math == 2) ? math : (math == 0 ? g_gnfuse_math : 3);
   DPIR_REQUIRE(!gf.up || (p->gf_math == 3 && gf.C2 == 0 && p->g.H % 2 == 0 && p->g.W % 2 == 0),
                "conv_tc: the up-sampling index map needs the activate-once producers, one source and even H, W");
@@ -1538,6 +1789,29 @@ int launch_conv_tc(const ConvTcPlan *p, const ConvEpi &epi, int Cout, cudaStream
     return DPIR_OK;
   }
   DPIR_REQUIRE(!p->v2, "conv_tc: the persistent 3x3 kernel only has the NHWC epilogue");
+  if (p->dxn) {
+    DPIR_REQUIRE(!epi.out_half && !epi.res_half && !epi.qstats && !epi.bias2, "conv_tc: the narrow-output kernel stores fp32 and has no statistics / second bias");
+    DevState *ds = dev_state();
+    const int smem = 2048 + p->gd.chunks * 3 * DXN_W_BYTES + p->gd.a_slots * V2_A_BYTES;
+    if (ds->attr_dxn < smem) {
+      DPIR_CUDA_CHECK(cudaFuncSetAttribute(k_conv3x3_dxn<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      DPIR_CUDA_CHECK(cudaFuncSetAttribute(k_conv3x3_dxn<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      ds->attr_dxn = smem;
+    }
+    if (!ds->num_sms) {
+      int dev = 0;
+      DPIR_CUDA_CHECK(cudaGetDevice(&dev));
+      DPIR_CUDA_CHECK(cudaDeviceGetAttribute(&ds->num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    ConvDxnGeom gd = p->gd;
+    gd.Cout = Cout;
+    const int grid = gd.total_tiles < ds->num_sms ? gd.total_tiles : ds->num_sms;
+    gd.coef = p->gf.coef;
+    if (gd.coef) k_conv3x3_dxn<true><<<grid, DXN_THREADS + 32 * DXN_ACT_WARPS, smem, st>>>(p->tmA, p->tmW3, gd, epi);
+    else k_conv3x3_dxn<false><<<grid, DXN_THREADS, smem, st>>>(p->tmA, p->tmW3, gd, epi);
+    DPIR_LAUNCH_CHECK();
+    return DPIR_OK;
+  }
   ConvTcGeom g = p->g;
   g.Cout = Cout;
   if (p->BN == 16) return launch_tc_impl<16, 4>(p, g, epi, st);

@@ -756,12 +756,20 @@ struct PlanBuilder {
       run_block(e->outputs[i], h, skip, &o);
       h = o;
     }
-    int a, d0, d1;
-    gn(h, -1, e->outnorm, -1, 1, RS_NONE, false, false, &a, &d0, &d1);
-    release(h);
+    // out.0-2 (unet.py:617-621): GroupNorm + SiLU + conv3x3 -> 6 channels.  fp16 stream: the norm is applied inside the narrow-output
+    // kernel (k_conv3x3_dxn<true>: the TMA fetches the raw h, activator warps rewrite the halo boxes in place); DPIR_OUT_FUSE=0 keeps
+    // the separate k_gn_apply pass (A/B timing)
+    static int out_fuse = -1;
+    if (out_fuse < 0) { const char *ev = getenv("DPIR_OUT_FUSE"); out_fuse = (ev && ev[0] == '0') ? 0 : 1; }
+    const bool fuse_out = out_fuse && e->gn_fuse && e->stream_half && !e->split && bufs[h].half && conv_tc_swapab_enabled() &&
+                          conv_tc_narrow_eligible(H, W, e->outconv.cin, e->outconv.ldw);
+    int a = -1, d0, d1, cb = -1;
+    if (fuse_out) cb = gn_coef(h, -1, e->outnorm, -1);
+    else { gn(h, -1, e->outnorm, -1, 1, RS_NONE, false, false, &a, &d0, &d1); release(h); }
     Op fc;
     fc.kind = OP_CONV;
-    fc.p0 = bp<void>(a); fc.w = e->arena + e->outconv.w_off;
+    if (fuse_out) { fc.gf.src1 = bp<__half>(h); fc.gf.C1 = bufs[h].C; fc.gf.coef = bp<float>(cb); }
+    fc.p0 = fuse_out ? bp<void>(h) : bp<void>(a); fc.w = e->arena + e->outconv.w_off;
     fc.B = B; fc.H = H; fc.W = W; fc.Cin = e->outconv.cin; fc.Cout = e->outconv.cout; fc.ldw = e->outconv.ldw; fc.ksize = 3;
     fc.epi.mode = EPI_NCHW; fc.epi.bias = e->ap<float>(e->outconv.b_off);
     fc.epi.coef = e->ap<float>(e->coef_off);
@@ -770,7 +778,8 @@ struct PlanBuilder {
     fc.bind_out = true;
     plan->final_conv = (int)plan->ops.size();
     plan->ops.push_back(fc);
-    release(a);
+    if (fuse_out) { release(cb); release(h); }
+    else release(a);
     if (n_norms != total_norms) { set_error("internal: norm count mismatch %d vs %d", n_norms, total_norms); return DPIR_E_STATE; }
     plan->ws_bytes = pool.peak;
     return err;
@@ -1359,6 +1368,16 @@ int dpir_conv_gnfuse_f16io(const void *src1, int32_t C1, const void *src2, int32
   ConvTcPlan *p = nullptr;
   int rc = conv_tc_plan_create(src1, w, B, H, W, C1 + C2, CoutPad, 3, &p);
   if (rc) return rc;
+  if (CoutPad == 16) {      // narrow-output kernel (the UNet's output layer): one source, no residual, fp32 NHWC output
+    ConvEpi epi{};
+    epi.mode = EPI_NHWC; epi.bias = bias; epi.out = reinterpret_cast<float *>(out_half);
+    GnFuse gf;
+    gf.src1 = (const __half *)src1; gf.C1 = C1; gf.src2 = (const __half *)src2; gf.C2 = C2; gf.coef = coef;
+    rc = residual_half ? DPIR_E_ARG : conv_tc_plan_set_gn_fuse(p, gf);
+    if (!rc) rc = launch_conv_tc(p, epi, Cout, (cudaStream_t)stream);
+    conv_tc_plan_destroy(p);
+    return rc;
+  }
   ConvEpi epi{};
   epi.mode = EPI_NHWC; epi.bias = bias; epi.residual = reinterpret_cast<const float *>(residual_half);
   epi.res_half = residual_half ? 1 : 0; epi.out = reinterpret_cast<float *>(out_half); epi.out_half = 1;

@@ -141,6 +141,7 @@ int conv_tc_plan_create(const void *act_half, const void *w_half, int B, int H, 
                         ConvTcPlan **out, int split = 0, int force_bn = 0, int act_c = 0);
 void conv_tc_plan_destroy(ConvTcPlan *p);
 bool conv_tc_plan_is_v2(const ConvTcPlan *p);
+bool conv_tc_narrow_eligible(int H, int W, int Cin, int CoutPad);   // 3x3, <= 16 couts, >= 16x16 map: k_conv3x3_dxn
 int conv_tc_plan_add_skip(ConvTcPlan *p, const void *act2_half, const void *w2_half, int Cin2a, const void *act2b_half = nullptr,
                           int Cin2b = 0);
 // math: producer flavour - 3 activate-once (default), 1 per-tap fp32, 2 per-tap packed half, 0 = the process-wide test default

@@ -266,7 +266,8 @@ int dpir_conv_tc_f16io(const void *act, const void *w, const float *bias, const 
  * (film[b*film_stride + c] = scale, [.. + C + c] = shift) into coef dev fp32 [B][2][C] = (0.5*scale_c, 0.5*offset_c);
  * dpir_conv_gnfuse_f16io computes out = conv3x3(SiLU(scale*x + offset)) + bias (+ residual) with x = (src1 | src2) raw fp16
  * NHWC (C1, C2 multiples of 64; src2 NULL / C2 0 for one source), zero padding applied AFTER the activation, fp16 NHWC
- * residual/output. */
+ * residual/output.  CoutPad == 16 (the UNet's output head out.0-2, unet.py:617-621, <= 16 output channels): one source, no residual,
+ * and `out_half` receives fp32 NHWC [B][H][W][Cout] (the narrow-output kernel k_conv3x3_dxn stores fp32). */
 int dpir_gn_coef(const double *q1, const double *q2, int32_t C1, int32_t C2, const float *gamma, const float *beta, const float *film,
                  int32_t film_stride, int32_t B, int32_t HW, float *coef, void *stream);
 int dpir_conv_gnfuse_f16io(const void *src1, int32_t C1, const void *src2, int32_t C2, const float *coef, const void *w,

@@ -83,18 +83,30 @@ def test_conv_tc_matches_torch(B, H, W, Cin, Cout, k, residual, variant):
     assert rel_l2(got, full) < 1.5e-3
 
 
-def test_conv_tc_small_cout_pad16():
+@pytest.mark.parametrize("B,H,W,Cin,Cout,residual", [
+    (2, 32, 32, 128, 8, False),
+    (1, 256, 256, 128, 8, False),      # the FFHQ output layer's shape: 19 x 16 tiles of 14 x 16 output pixels, the last tile column ragged
+    (3, 24, 40, 256, 4, True),         # ragged on both edges, 4 K chunks, fp32 residual
+    (2, 16, 16, 384, 16, False),       # 6 K chunks (the resident-weight limit), all 16 columns of a tap block in use
+    (40, 16, 16, 128, 12, False),      # more tiles than SMs at the smallest map the kernel takes
+    (2, 8, 8, 128, 8, False),          # below 16 x 16: stays on the one-tile-per-CTA kernel
+])
+def test_conv_tc_small_cout_pad16(B, H, W, Cin, Cout, residual):
+    """3x3 convolutions with <= 16 output channels (the UNet's output layer): k_conv3x3_dxn, horizontal taps in the MMA's N."""
     from diffpir_b200 import _lib
     lib = _lib.load()
-    B, H, W, Cin, Cout = 2, 32, 32, 128, 8
-    x, w, b, _ = _case(B, H, W, Cin, Cout, 3, 1, False)
+    x, w, b, r = _case(B, H, W, Cin, Cout, 3, 1, residual)
     ref = F.conv2d(x.half().double(), w.half().double(), b.double(), padding=1)
+    if r is not None:
+        ref = ref + r.double()
     act = x.permute(0, 2, 3, 1).contiguous().half().cuda()
     wp = _pack_tc(w, 16).cuda()
+    res = r.permute(0, 2, 3, 1).contiguous().cuda() if r is not None else None
     out = torch.full((B, H, W, Cout), float("nan"), device="cuda")
-    _lib.check(lib.dpir_conv_tc(_lib.ptr(act), _lib.ptr(wp), _lib.ptr(b.cuda()), None, _lib.ptr(out), B, H, W, Cin, Cout, 16, 3,
-                                _lib.stream_ptr()), "dpir_conv_tc")
+    _lib.check(lib.dpir_conv_tc(_lib.ptr(act), _lib.ptr(wp), _lib.ptr(b.cuda()), _lib.ptr(res), _lib.ptr(out), B, H, W, Cin, Cout, 16,
+                                3, _lib.stream_ptr()), "dpir_conv_tc")
     torch.cuda.synchronize()
+    assert not torch.isnan(out).any()
     assert rel_l2(out.permute(0, 3, 1, 2), ref) < 2e-6
 
 
@@ -220,3 +232,37 @@ def test_conv_gn_fused_matches_torch(B, H, W, C1, C2, Cout, residual, film, math
     assert not torch.isnan(got).any()
     # fp16 rounding of the activated operand (+ of the stored result); packed-half arithmetic (math 2) rounds twice more
     assert rel_l2(got, ref) < (3e-3 if math == "2" else 1.2e-3)
+
+
+@pytest.mark.parametrize("B,H,W,C,Cout", [
+    (1, 256, 256, 128, 8),      # the FFHQ output head's shape (the NHWC test entry needs Cout % 4 == 0; 6 runs in the UNet tests)
+    (3, 24, 40, 256, 4),        # ragged tiles: exact zeros outside the image AFTER the activation; 4 K chunks
+    (33, 16, 16, 128, 12),
+])
+def test_conv_gn_fused_narrow_output(B, H, W, C, Cout):
+    """k_conv3x3_dxn<true>: out = conv3x3(SiLU(GroupNorm(x))) + bias for <= 16 output channels (out.0-2, unet.py:617-621): the TMA
+    fetches the raw tensor, activator warps rewrite each halo box in place, fp32 NHWC output."""
+    from diffpir_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(B, C, H, W, generator=g) * 1.7 + 0.6 * torch.randn(B, C, 1, 1, generator=g)
+    xh = x.half()
+    w = torch.randn(Cout, C, 3, 3, generator=g) / (C * 9) ** 0.5
+    b = torch.randn(Cout, generator=g) * 0.1
+    gamma = 1 + 0.3 * torch.randn(C, generator=g)
+    beta = 0.2 * torch.randn(C, generator=g)
+    ref = F.conv2d(_gn_reference(xh.float(), gamma, beta, None), w.half().double(), b.double(), padding=1)
+    s1 = xh.permute(0, 2, 3, 1).contiguous().cuda()
+    q1 = _quad_stats(s1.cpu()).cuda()
+    coef = torch.empty(B, 2, C, device="cuda")
+    gd, bd, biasd = gamma.cuda(), beta.cuda(), b.cuda()
+    _lib.check(lib.dpir_gn_coef(_lib.ptr(q1), None, C, 0, _lib.ptr(gd), _lib.ptr(bd), None, 2 * C, B, H * W, _lib.ptr(coef),
+                                _lib.stream_ptr()), "dpir_gn_coef")
+    wp = _pack_tc(w, 16).cuda()
+    out = torch.full((B, H, W, Cout), float("nan"), device="cuda")
+    _lib.check(lib.dpir_conv_gnfuse_f16io(_lib.ptr(s1), C, None, 0, _lib.ptr(coef), _lib.ptr(wp), _lib.ptr(biasd), None, _lib.ptr(out),
+                                          B, H, W, Cout, 16, _lib.stream_ptr()), "dpir_conv_gnfuse_f16io")
+    torch.cuda.synchronize()
+    got = out.permute(0, 3, 1, 2)
+    assert not torch.isnan(got).any()
+    assert rel_l2(got, ref) < 1.2e-3      # fp16 rounding of the activated operand
