@@ -1,5 +1,5 @@
 #!/bin/bash
-# Final validation on one B200: full GPU suite, smoke, default bench, refreshed per-op tables.
+# Final validation + evidence on one B200: full GPU suite, smoke, default bench, per-op tables, ncu launch list and full captures.
 mkdir -p gpurun_out
 timeout 2700 python -m pytest tests -m gpu -x -q -s > gpurun_out/r02_final_gpu.log 2>&1
 echo "pytest rc=$?" >> gpurun_out/r02_final_gpu.log
@@ -19,3 +19,15 @@ python tools/profile_ops.py --precision fp16s --gn-fusion 0 > gpurun_out/r02_ops
 python tools/profile_ops.py --precision fp16x3 > gpurun_out/r02_ops_fp16x3_b32.txt 2>&1
 python tools/profile_ops.py --precision fp16s --model imagenet --batch 8 > gpurun_out/r02_ops_imagenet_b8.txt 2>&1
 grep "total serialised" gpurun_out/r02_ops_fused_b32.txt gpurun_out/r02_ops_unfused_b32.txt gpurun_out/r02_ops_fp16x3_b32.txt gpurun_out/r02_ops_imagenet_b8.txt
+# launch list of the bench command (cold-cache, serialised: shares, not absolutes)
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r02_launches_bench.csv \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-strict-leg > gpurun_out/r02_bench_under_ncu.log 2>&1
+echo "launch list rc=$?"
+# full captures: the first three k_conv3x3_v3 launches of a forward (stem, in[1] conv1 fused, conv2 fused + residual) and the output head
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_conv3x3_v3 -s 0 -c 3 -o gpurun_out/r02_conv_v3 \
+    python tools/profile_ops.py --precision fp16s --gn-fusion 1 --reps 0 --warmup 1 > gpurun_out/r02_ncu_full.log 2>&1
+echo "ncu v3 rc=$?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_conv3x3_dxn -s 0 -c 1 -o gpurun_out/r02_conv_dxn \
+    python tools/profile_ops.py --precision fp16s --gn-fusion 1 --reps 0 --warmup 1 > gpurun_out/r02_ncu_dxn.log 2>&1
+echo "ncu dxn rc=$?"
+ls -la gpurun_out | grep -E "ncu-rep|launches"
