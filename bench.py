@@ -397,6 +397,9 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="images per GPU (default: the workload's)")
     ap.add_argument("--precision", default="fp16s", choices=["fp16", "fp16s", "fp16x3", "fp32"])
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--weight-bcast", default="torch", choices=["torch", "library"],
+                    help="N > 1: who issues the one collective - torch.distributed.broadcast of the arena view (default), or the "
+                         "library's own NCCL communicator (dpir_bcast_weights)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-strict-leg", action="store_true", help="skip the fp16x3 (<= 1e-4 parity mode) leg of config 2 at N = 1")
     ap.add_argument("--profile-steps", type=int, default=3)
@@ -454,12 +457,23 @@ def main():
         torch.cuda.synchronize()
         dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        dist.broadcast(arena, src=0)          # the ONE collective: packed weights over NVLink
-        e1.record()
-        torch.cuda.synchronize()
+        if args.weight_bcast == "library":
+            from diffpir_b200.parallel import WeightComm
+            wcomm = WeightComm()              # the library's own communicator (id shared through the job's process group)
+            torch.cuda.synchronize()
+            dist.barrier()
+            e0.record()
+            wcomm.broadcast(model, src=0)     # ONE ncclBroadcast issued by libdiffpir_b200 on the current stream
+            e1.record()
+            torch.cuda.synchronize()
+            wcomm.close()
+        else:
+            e0.record()
+            dist.broadcast(arena, src=0)          # the ONE collective: packed weights over NVLink
+            e1.record()
+            torch.cuda.synchronize()
+            model.mark_weights_loaded()
         t_bcast_ms = e0.elapsed_time(e1)
-        model.mark_weights_loaded()
     model.set_gn_fusion(args.gn_fusion)
     if not args.no_graph:
         model.set_graph_mode(True)
@@ -685,7 +699,7 @@ def main():
                         "d2h_bytes_per_step": img_bytes, "ms_per_step": ms_e2e},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_prox": prox, "cpu_baseline": cpu,
                 "parity_sample": parity, "strict_mode": strict, "rank_consistency": rank_consistency,
-                "weight_broadcast_ms": t_bcast_ms, "graph": not args.no_graph, "gn_fusion": args.gn_fusion}
+                "weight_broadcast_ms": t_bcast_ms, "weight_broadcast_by": args.weight_bcast if world > 1 else None, "graph": not args.no_graph, "gn_fusion": args.gn_fusion}
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     if dist is not None:

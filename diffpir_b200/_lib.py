@@ -37,6 +37,11 @@ SIGNATURES = {
     "dpir_missing_weights": (c_int32, [c_void_p]),
     "dpir_weight_arena": (c_int32, [c_void_p, POINTER(c_void_p), POINTER(c_size_t)]),
     "dpir_mark_weights_loaded": (c_int32, [c_void_p]),
+    "dpir_nccl_version": (c_int32, [POINTER(c_int32)]),
+    "dpir_comm_unique_id": (c_int32, [c_void_p, c_size_t]),
+    "dpir_comm_create": (c_int32, [c_void_p, c_int32, c_int32, POINTER(c_void_p)]),
+    "dpir_comm_destroy": (c_int32, [c_void_p]),
+    "dpir_bcast_weights": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p]),
     "dpir_set_tables": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_int32]),
     "dpir_unet_forward": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),
     "dpir_unet_x0": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),

@@ -10,7 +10,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdiffpir_b200.so")
 STAMP = os.path.join(HERE, "libdiffpir_b200.srchash")     # sha256 of the sources the shipped .so was built from
 LOCK = os.path.join(HERE, ".build.lock")
-SOURCES = ["prox.cu", "unet_kernels.cu", "conv_tc.cu", "attention_tc.cu", "engine.cu"]
+SOURCES = ["prox.cu", "unet_kernels.cu", "conv_tc.cu", "attention_tc.cu", "engine.cu", "comm.cu"]
 HEADERS = ["common.cuh", "unet_kernels.cuh", "tc_ptx.cuh", os.path.join("..", "..", "include", "diffpir_b200.h")]
 
 
@@ -82,7 +82,7 @@ def build(force=False, verbose=False):
                     if p.returncode:
                         raise RuntimeError(f"nvcc failed on {s}")
                 out_lib = os.path.join(tmp, "libdiffpir_b200.so")
-                cmd = [_nvcc(), "-shared", "-o", out_lib] + objs + ["-lcufft", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
+                cmd = [_nvcc(), "-shared", "-o", out_lib] + objs + ["-lcufft", "-ldl", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
                 r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
                 if r.returncode:
                     sys.stderr.write(r.stdout)

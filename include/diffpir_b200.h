@@ -97,6 +97,28 @@ int dpir_missing_weights(dpir_engine *e);
 int dpir_weight_arena(dpir_engine *e, void **dev_ptr, size_t *bytes);
 int dpir_mark_weights_loaded(dpir_engine *e);
 
+/* The path's ONE collective, inside the library.  The reference is a single process that loads the
+ * checkpoint on its only GPU (main_ddpir.py:214-236); with one process per GPU, rank `root` repacks the checkpoint once
+ * (dpir_load_weight) and dpir_bcast_weights ships the packed arena to its peers with one ncclBroadcast over NVLink - the other
+ * ranks never read the checkpoint.  NCCL is bound at run time (the libnccl.so.2 the process already carries, e.g. PyTorch's, else
+ * the system one); without it these calls fail with DPIR_E_STATE - there is no host-staged fallback.
+ *   dpir_comm_unique_id : rank 0 fills `id` (DPIR_COMM_ID_BYTES bytes) and the host program hands it to the other ranks over any
+ *                         channel it has (a file, a TCP store, MPI, torch.distributed.broadcast_object_list).
+ *   dpir_comm_create    : collective - every rank calls it with the same id, its rank and the job's world size, with its GPU as the
+ *                         current CUDA device (ncclCommInitRank).
+ *   dpir_bcast_weights  : collective, stream-ordered on `stream`: on return the broadcast is enqueued; the non-root engines are
+ *                         marked loaded (their derived FiLM table is rebuilt by the next forward, which must run on the same stream
+ *                         or after a synchronisation).  Every rank must have created its engine from the same dpir_unet_config and
+ *                         precision (identical arena layout); the root's checkpoint must be complete.
+ */
+#define DPIR_COMM_ID_BYTES 128
+typedef struct dpir_comm dpir_comm;
+int dpir_nccl_version(int32_t *version);                       /* e.g. 22809; DPIR_E_STATE when no NCCL library can be bound */
+int dpir_comm_unique_id(void *id, size_t cap);
+int dpir_comm_create(const void *id, int32_t world, int32_t rank, dpir_comm **out);
+int dpir_comm_destroy(dpir_comm *c);
+int dpir_bcast_weights(dpir_engine *e, dpir_comm *c, int32_t root, void *stream);
+
 /* Optional: override the built-in tables with host-computed ones (so they are bit-identical to the reference's numpy /
  * torch evaluation): freqs[model_channels/2] of nn.py:112-114, coef[T][2] = (sqrt_recip_alphas_cumprod,
  * sqrt_recipm1_alphas_cumprod) of gaussian_diffusion.py:150-151 cast to float (:905).  Either pointer may be NULL. */

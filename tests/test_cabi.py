@@ -70,3 +70,23 @@ def test_shipped_library_matches_sources():
     assert os.path.exists(build.LIB) and os.path.exists(build.STAMP)
     assert not build.needs_build()
     assert open(build.STAMP).read().strip() == build._source_hash()
+
+
+def test_weight_comm_binding_and_argument_checks():
+    """The in-library weight broadcast (dpir_comm_*, dpir_bcast_weights): NCCL binds at run time to the copy the process already
+    carries (PyTorch's here), the id is NCCL's 128 bytes, and bad arguments fail loudly without touching a GPU."""
+    import ctypes
+    import torch  # noqa: F401  (loads PyTorch's libnccl.so.2 first: the library binds to the loaded copy)
+    from diffpir_b200 import _lib
+    lib = _lib.load()
+    v = ctypes.c_int32()
+    assert lib.dpir_nccl_version(ctypes.byref(v)) == 0 and v.value >= 21800
+    a, b = ctypes.create_string_buffer(128), ctypes.create_string_buffer(128)
+    assert lib.dpir_comm_unique_id(a, 128) == 0 and lib.dpir_comm_unique_id(b, 128) == 0
+    assert a.raw != b.raw and any(a.raw)
+    assert lib.dpir_comm_unique_id(a, 64) == -1                      # DPIR_E_ARG: buffer too small
+    h = ctypes.c_void_p()
+    assert lib.dpir_comm_create(a, 2, 2, ctypes.byref(h)) == -1      # rank outside the world
+    assert lib.dpir_comm_create(None, 1, 0, ctypes.byref(h)) == -1
+    assert lib.dpir_bcast_weights(None, None, 0, None) == -1
+    assert lib.dpir_comm_destroy(None) == 0
