@@ -45,6 +45,8 @@ struct ConvTcGeom {
   int a_wrap;                 // split-precision: K chunk ch reads activation chunk (ch >= a_wrap ? ch - a_wrap : ch); else INT_MAX
   int TW, TH, TN;             // M-tile box (TW*TH*TN == 128)
   int tiles_w, tiles_h, tiles_n;
+  int stagger;                // 1: every CTA starts its K loop at a different (tap, chunk) - the order of the fp32 accumulation is
+                              // free, and CTAs that march through K in lockstep request the same L2 lines at the same time
 };
 
 // Per-quad (4-channel) sums over the 32 pixel rows held by a warp: reduce-scatter butterfly (8 -> 4 -> 2 -> 1 values per
@@ -196,11 +198,13 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(const __grid_constant__ 
   if (warp == 0) {
     if (lane == 0) {
       const int pad = g.ksize / 2;
+      const int k0 = g.stagger ? (int)((blockIdx.x * 7u + blockIdx.y * 3u) % (unsigned)num_k) : 0;
       for (int k = 0; k < num_k; ++k) {
         const int s = k % STAGES;
         const uint32_t ph = (uint32_t)(k / STAGES) & 1u;
         mbar_wait(&empty[s], ph ^ 1u);
-        const int tap = k / chunks, ch = k - tap * chunks;
+        const int kq = k + k0 < num_k ? k + k0 : k + k0 - num_k;
+        const int tap = kq / chunks, ch = kq - tap * chunks;
         const int dy = tap / g.ksize - pad, dx = tap % g.ksize - pad;
         uint8_t *sa = smem + s * STAGE_BYTES;
         mbar_expect_tx(&full[s], STAGE_BYTES);
@@ -317,6 +321,10 @@ struct ConvV2Geom {
   int a_wrap;                         // split-precision K-chunk -> activation-chunk wrap (see ConvTcGeom), INT_MAX otherwise
   int skip_chunks;                    // extra K chunks of a fused 1x1 convolution on a second operand (ResBlock skip), or 0
   int skip_chunks_a;                  // of which the first skip_chunks_a come from tmA2, the rest from tmA2b (concat skip input)
+  int skip_il;                        // v3: 1 = the fused-skip stages are spread over the tile's K loop (after main chunk c come skip
+                                      // chunks [c*S/chunks, (c+1)*S/chunks)) instead of all at its end: a skip stage moves a 36 KB box +
+                                      // 16 KB of weights for 4 MMAs (3x the TMA bytes per MMA of a main stage), and 4-8 of them back to
+                                      // back leave the tensor core waiting for TMA; spread out, their loads hide behind the main stages
   int dbg;                            // timing diagnostics only (env DPIR_CONV_DEBUG): 1 = no epilogue memory traffic,
                                       // 2 = no MMA issue, 4 = no TMA loads; v4 producers: 32 = no global loads, 64 = no
                                       // arithmetic, 128 = no proxy fence; results are garbage when non-zero
@@ -716,6 +724,11 @@ __global__ void __launch_bounds__(FUSE ? V4_THREADS : V2_THREADS, 1) k_conv3x3_v
   // the same static tile list in the same order.
   const int W_TP = g.w_taps;
   const int W_SLOT_BYTES = W_TP * V3_W_BYTES;
+  // stage order of a tile, walked identically by every role: for each main chunk its three (chunk, dx) stages, then the fused-skip
+  // chunks [sk, skip_hi(chunk)) - all of them after the last main chunk (skip_il == 0), or spread evenly over the chunks
+  auto skip_hi = [&](const int ch) -> int {
+    return g.skip_il ? ((ch + 1) * g.skip_chunks) / chunks : (ch == chunks - 1 ? g.skip_chunks : 0);
+  };
   auto role_tma = [&]() {
     if (lane == 0) {
       // ring positions are (slot, phase) pairs advanced incrementally: the depths are launch parameters, and a runtime % and /
@@ -750,13 +763,13 @@ __global__ void __launch_bounds__(FUSE ? V4_THREADS : V2_THREADS, 1) k_conv3x3_v
       for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++tile_it) {
         int n, h0, w0, co0;
         decode(tile, n, h0, w0, co0);
-        for (int k = 0; k < num_k; ++k) {
-          const int s = as;
-          mbar_wait(&a_empty[s], aph ^ 1u);
-          if (++as == A_SL) { as = 0; aph ^= 1u; }
-          uint8_t *sa = a_ring + s * V2_A_BYTES;
-          if (k < num_main) {
-            const int ch = k / 3, dx = k - ch * 3;
+        int sk = 0;                            // next fused-skip chunk
+        for (int ch = 0; ch < chunks; ++ch) {
+          for (int dx = 0; dx < 3; ++dx) {
+            const int s = as;
+            mbar_wait(&a_empty[s], aph ^ 1u);
+            if (++as == A_SL) { as = 0; aph ^= 1u; }
+            uint8_t *sa = a_ring + s * V2_A_BYTES;
             if (FUSE) {
               mbar_arrive(&a_full[s]);           // the operand is written by the producer warps
               if (dx == 0 && g.pf_dist > 0) prefetch_raw(tile_it * (uint32_t)chunks + (uint32_t)ch + (uint32_t)g.pf_dist);
@@ -765,12 +778,16 @@ __global__ void __launch_bounds__(FUSE ? V4_THREADS : V2_THREADS, 1) k_conv3x3_v
               tma_load_4d(sa, &tmA, &a_full[s], ch * TC_BK, w0 + dx - 1, h0 - 1, n);
             }
             for (int dy = 0; dy < 3; dy += W_TP) load_w(&tmB, ch * TC_BK, co0, dy * 3 + dx, W_TP, 3);
-          } else {
-            const int ch = k - num_main;
+          }
+          for (const int sk_hi = skip_hi(ch); sk < sk_hi; ++sk) {
+            const int s = as;
+            mbar_wait(&a_empty[s], aph ^ 1u);
+            if (++as == A_SL) { as = 0; aph ^= 1u; }
+            uint8_t *sa = a_ring + s * V2_A_BYTES;
             mbar_expect_tx(&a_full[s], V2_A_BYTES);
-            if (ch < g.skip_chunks_a) tma_load_4d(sa, &tmA2, &a_full[s], ch * TC_BK, w0, h0 - 1, n);
-            else tma_load_4d(sa, &tmA2b, &a_full[s], (ch - g.skip_chunks_a) * TC_BK, w0, h0 - 1, n);
-            load_w(&tmB2, ch * TC_BK, co0, 0, 1, 0);
+            if (sk < g.skip_chunks_a) tma_load_4d(sa, &tmA2, &a_full[s], sk * TC_BK, w0, h0 - 1, n);
+            else tma_load_4d(sa, &tmA2b, &a_full[s], (sk - g.skip_chunks_a) * TC_BK, w0, h0 - 1, n);
+            load_w(&tmB2, sk * TC_BK, co0, 0, 1, 0);
           }
         }
       }
@@ -786,13 +803,15 @@ __global__ void __launch_bounds__(FUSE ? V4_THREADS : V2_THREADS, 1) k_conv3x3_v
         mbar_wait(&tmem_empty[ab], aph ^ 1u);
         tc_fence_after();
         const uint32_t d = tmem_base + ab * 256u;
-        for (int k = 0; k < num_k; ++k) {
+        uint32_t acc = 0;                       // 0 for the tile's very first MMA (overwrite), 1 afterwards
+        // one (chunk, dx) main stage: the three dy views of the halo box against 3 / W_TP weight slots; one fused-skip stage: the
+        // dy = 1 view against one 1x1 weight tile
+        auto stage = [&](const bool main_stage) {
           const int s = as;
           mbar_wait(&a_full[s], rph);
           if (++as == A_SL) { as = 0; rph ^= 1u; }
           tc_fence_after();
           const uint32_t sa = smem_u32(a_ring + s * V2_A_BYTES);
-          const bool main_stage = k < num_main;
           const int dy_lo = main_stage ? 0 : 1, dy_hi = main_stage ? 3 : 2;
           for (int dy = dy_lo; dy < dy_hi;) {
             const int ws = ws_;
@@ -805,12 +824,19 @@ __global__ void __launch_bounds__(FUSE ? V4_THREADS : V2_THREADS, 1) k_conv3x3_v
               const uint64_t wdesc = make_sw128_desc(smem_u32(w_ring + ws * W_SLOT_BYTES + j * V3_W_BYTES));   // A: 128 couts x 64 k
               const uint64_t pdesc = make_sw128_desc(sa + (uint32_t)(dy * 16 * 128));                          // B: 256 pixels x 64 k
 #pragma unroll
-              for (int kk = 0; kk < TC_BK / 16; ++kk)
-                umma_f16(d, wdesc + (uint64_t)(2 * kk), pdesc + (uint64_t)(2 * kk), IDESC, (k | (dy - dy_lo) | kk) ? 1u : 0u);
+              for (int kk = 0; kk < TC_BK / 16; ++kk) {
+                umma_f16(d, wdesc + (uint64_t)(2 * kk), pdesc + (uint64_t)(2 * kk), IDESC, acc);
+                acc = 1u;
+              }
             }
             umma_commit(&w_empty[ws]);
           }
           umma_commit(&a_empty[s]);
+        };
+        int sk = 0;
+        for (int ch = 0; ch < chunks; ++ch) {
+          for (int dx = 0; dx < 3; ++dx) stage(true);
+          for (const int sk_hi = skip_hi(ch); sk < sk_hi; ++sk) stage(false);
         }
         umma_commit(&tmem_full[ab]);
       }
@@ -941,7 +967,7 @@ __global__ void __launch_bounds__(FUSE ? V4_THREADS : V2_THREADS, 1) k_conv3x3_v
   };
   auto role_producer_once = [&]() {
     // ---------------------------------------------------------------- v5 operand producers (FUSE == 3; 9 warps, 288 threads)
-    // EXPERIMENTAL - compiles, not yet validated on hardware, not selected by default (dpir_set_gn_fusion(3)).
+    // The default since round 2 (dpir_set_gn_fusion 1 / 3).
     // k_conv3x3_v3<1> activates every input element once per horizontal tap box: 3 x 18/16 = 3.4 times.  Here a thread owns a
     // column X of the 18-wide halo (instead of a column of one 16-wide box), a channel octet j and every second row (rg):
     // 18 x 8 x 2 = 288 threads x 9 units.  The 9 raw units of a 64-channel chunk are loaded once, activated once in place,
@@ -1000,18 +1026,9 @@ __global__ void __launch_bounds__(FUSE ? V4_THREADS : V2_THREADS, 1) k_conv3x3_v
     for (; tile < g.total_tiles; tile += gridDim.x) {
       const int n = ln;
       mask = lmask;
-      for (int k = 0; k < num_k; ++k) {
-        const int s = rs;
-        const uint32_t ph = rph;
-        if (++rs == A_SL) { rs = 0; rph ^= 1u; }
-        if (k >= num_main) {               // fused 1x1-skip stage: operand comes by TMA, only keep the barrier count
-          mbar_wait(&a_empty[s], ph ^ 1u);
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&a_full[s]);
-          continue;
-        }
-        const int ch = k / 3, dx = k - ch * 3;
-        if (dx == 0 && !(g.dbg & 64)) {    // new chunk: activate the 9 units in place (needs no pipeline slot)
+      int sk = 0;
+      for (int ch = 0; ch < chunks; ++ch) {
+        if (!(g.dbg & 64)) {    // new chunk: activate the 9 units in place (needs no pipeline slot)
           const float *cf = gf.coef + (int64_t)n * 2 * Ctot + ch * TC_BK + j * 8;
           const float4 a0 = __ldg(reinterpret_cast<const float4 *>(cf)), a1 = __ldg(reinterpret_cast<const float4 *>(cf + 4));
           const float4 b0 = __ldg(reinterpret_cast<const float4 *>(cf + Ctot)), b1 = __ldg(reinterpret_cast<const float4 *>(cf + Ctot + 4));
@@ -1031,23 +1048,36 @@ __global__ void __launch_bounds__(FUSE ? V4_THREADS : V2_THREADS, 1) k_conv3x3_v
             buf[i] = make_uint4(ok ? w[0] : 0u, ok ? w[1] : 0u, ok ? w[2] : 0u, ok ? w[3] : 0u);
           }
         }
-        mbar_wait(&a_empty[s], ph ^ 1u);
-        const int xx = X - dx;
-        if ((unsigned)xx < 16u) {
-          uint8_t *dst = a_ring + s * V2_A_BYTES + (rg * 2048 + xx * 128 + ((j ^ (xx & 7)) << 4));
+#pragma unroll 1
+        for (int dx = 0; dx < 3; ++dx) {
+          const int s = rs;
+          const uint32_t ph = rph;
+          if (++rs == A_SL) { rs = 0; rph ^= 1u; }
+          mbar_wait(&a_empty[s], ph ^ 1u);
+          const int xx = X - dx;
+          if ((unsigned)xx < 16u) {
+            uint8_t *dst = a_ring + s * V2_A_BYTES + (rg * 2048 + xx * 128 + ((j ^ (xx & 7)) << 4));
 #pragma unroll
-          for (int i = 0; i < 9; ++i) *reinterpret_cast<uint4 *>(dst + i * 4096) = buf[i];
-        }
-        if (!(g.dbg & 128)) fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&a_full[s]);
-        if (dx == 2) {                     // the chunk is published three times: fetch the next one into the same registers
-          if (ch + 1 < chunks) {
-            issue(ch + 1);
-          } else if (tile + (int)gridDim.x < g.total_tiles) {
-            load_tile(tile + (int)gridDim.x);
-            issue(0);
+            for (int i = 0; i < 9; ++i) *reinterpret_cast<uint4 *>(dst + i * 4096) = buf[i];
           }
+          if (!(g.dbg & 128)) fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&a_full[s]);
+        }
+        // the chunk is published three times: fetch the next one into the same registers (never in flight at a proxy fence)
+        if (ch + 1 < chunks) {
+          issue(ch + 1);
+        } else if (tile + (int)gridDim.x < g.total_tiles) {
+          load_tile(tile + (int)gridDim.x);
+          issue(0);
+        }
+        for (const int sk_hi = skip_hi(ch); sk < sk_hi; ++sk) {   // fused 1x1-skip stages: operand comes by TMA, only keep the barrier count
+          const int s = rs;
+          const uint32_t ph = rph;
+          if (++rs == A_SL) { rs = 0; rph ^= 1u; }
+          mbar_wait(&a_empty[s], ph ^ 1u);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&a_full[s]);
         }
       }
     }
@@ -1481,6 +1511,7 @@ int conv_tc_plan_create(const void *act_half, const void *w_half, int B, int H, 
   ConvTcGeom &g = p->g;
   g.B = B; g.H = H; g.W = W; g.Cin = Cin; g.Cout = 0; g.ksize = ksize; g.taps = ksize * ksize;
   g.a_wrap = split ? Cact / TC_BK : 0x7fffffff;
+  g.stagger = 0;
   p->split = split != 0;
   g.TW = W >= 128 ? 128 : pow2_ge(W);
   int th = 128 / g.TW;
@@ -1505,7 +1536,7 @@ int conv_tc_plan_create(const void *act_half, const void *w_half, int B, int H, 
   }
   if (p->v2) {
     ConvV2Geom &g2 = p->g2;
-    g2.B = B; g2.H = H; g2.W = W; g2.Cin = Cin; g2.Cout = 0; g2.skip_chunks = 0; g2.skip_chunks_a = 0; g2.dbg = 0;
+    g2.B = B; g2.H = H; g2.W = W; g2.Cin = Cin; g2.Cout = 0; g2.skip_chunks = 0; g2.skip_chunks_a = 0; g2.skip_il = 0; g2.dbg = 0;
     g2.a_wrap = g.a_wrap;
     g2.tiles_w = cdiv(W, 16); g2.tiles_h = cdiv(H, 16); g2.n_tiles = CoutPad / 128;
     g2.total_tiles = B * g2.tiles_w * g2.tiles_h * g2.n_tiles;
@@ -1759,6 +1790,9 @@ int launch_conv_tc(const ConvTcPlan *p, const ConvEpi &epi, int Cout, cudaStream
       g2.w_taps = nores ? ring[9] : (fused ? ring[5] : ring[2]);
       g2.pf_dist = fused ? ring[6] : 0;
       g2.stg_stride = nores ? 2048 : 6144;
+      static int skip_il = -1;                // DPIR_SKIP_INTERLEAVE=0: all fused-skip stages at the end of the tile's K loop (A/B timing)
+      if (skip_il < 0) { const char *e = getenv("DPIR_SKIP_INTERLEAVE"); skip_il = (e && e[0] == '0') ? 0 : 1; }
+      g2.skip_il = (skip_il && (!fused || p->gf_math == 3)) ? 1 : 0;      // the per-tap-box producers walk the round-1 order
       if (g2.a_slots * V2_A_BYTES + g2.w_slots * g2.w_taps * V3_W_BYTES + 8 * g2.stg_stride > V3_RING_BYTES + V3_STG_BYTES) {
         set_error("conv_tc: ring configuration exceeds the shared-memory budget");
         return DPIR_E_STATE;
@@ -1814,6 +1848,11 @@ int launch_conv_tc(const ConvTcPlan *p, const ConvEpi &epi, int Cout, cudaStream
   }
   ConvTcGeom g = p->g;
   g.Cout = Cout;
+  {
+    static int stagger = -1;               // DPIR_TC_STAGGER=1: staggered K order in the one-tile-per-CTA kernel (A/B timing)
+    if (stagger < 0) { const char *e = getenv("DPIR_TC_STAGGER"); stagger = (e && e[0] == '1') ? 1 : 0; }
+    g.stagger = stagger;
+  }
   if (p->BN == 16) return launch_tc_impl<16, 4>(p, g, epi, st);
   // (Small maps - 8x8 / 16x16 - run at ~250 TFLOP/s here.  Deeper rings (9 stages, one CTA per SM) were measured in round 2
   // and change nothing: with 128 x 64 tiles the arithmetic intensity is 43 FLOP per L2 byte and 128 CTAs pull ~6 TB/s from L2,
