@@ -45,8 +45,6 @@ struct ConvTcGeom {
   int a_wrap;                 // split-precision: K chunk ch reads activation chunk (ch >= a_wrap ? ch - a_wrap : ch); else INT_MAX
   int TW, TH, TN;             // M-tile box (TW*TH*TN == 128)
   int tiles_w, tiles_h, tiles_n;
-  int stagger;                // 1: every CTA starts its K loop at a different (tap, chunk) - the order of the fp32 accumulation is
-                              // free, and CTAs that march through K in lockstep request the same L2 lines at the same time
 };
 
 // Per-quad (4-channel) sums over the 32 pixel rows held by a warp: reduce-scatter butterfly (8 -> 4 -> 2 -> 1 values per
@@ -198,13 +196,11 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(const __grid_constant__ 
   if (warp == 0) {
     if (lane == 0) {
       const int pad = g.ksize / 2;
-      const int k0 = g.stagger ? (int)((blockIdx.x * 7u + blockIdx.y * 3u) % (unsigned)num_k) : 0;
       for (int k = 0; k < num_k; ++k) {
         const int s = k % STAGES;
         const uint32_t ph = (uint32_t)(k / STAGES) & 1u;
         mbar_wait(&empty[s], ph ^ 1u);
-        const int kq = k + k0 < num_k ? k + k0 : k + k0 - num_k;
-        const int tap = kq / chunks, ch = kq - tap * chunks;
+        const int tap = k / chunks, ch = k - tap * chunks;
         const int dy = tap / g.ksize - pad, dx = tap % g.ksize - pad;
         uint8_t *sa = smem + s * STAGE_BYTES;
         mbar_expect_tx(&full[s], STAGE_BYTES);
@@ -321,10 +317,6 @@ struct ConvV2Geom {
   int a_wrap;                         // split-precision K-chunk -> activation-chunk wrap (see ConvTcGeom), INT_MAX otherwise
   int skip_chunks;                    // extra K chunks of a fused 1x1 convolution on a second operand (ResBlock skip), or 0
   int skip_chunks_a;                  // of which the first skip_chunks_a come from tmA2, the rest from tmA2b (concat skip input)
-  int skip_il;                        // v3: 1 = the fused-skip stages are spread over the tile's K loop (after main chunk c come skip
-                                      // chunks [c*S/chunks, (c+1)*S/chunks)) instead of all at its end: a skip stage moves a 36 KB box +
-                                      // 16 KB of weights for 4 MMAs (3x the TMA bytes per MMA of a main stage), and 4-8 of them back to
-                                      // back leave the tensor core waiting for TMA; spread out, their loads hide behind the main stages
   int dbg;                            // timing diagnostics only (env DPIR_CONV_DEBUG): 1 = no epilogue memory traffic,
                                       // 2 = no MMA issue, 4 = no TMA loads; v4 producers: 32 = no global loads, 64 = no
                                       // arithmetic, 128 = no proxy fence; results are garbage when non-zero
@@ -725,10 +717,10 @@ __global__ void __launch_bounds__(FUSE ? V4_THREADS : V2_THREADS, 1) k_conv3x3_v
   const int W_TP = g.w_taps;
   const int W_SLOT_BYTES = W_TP * V3_W_BYTES;
   // stage order of a tile, walked identically by every role: for each main chunk its three (chunk, dx) stages, then the fused-skip
-  // chunks [sk, skip_hi(chunk)) - all of them after the last main chunk (skip_il == 0), or spread evenly over the chunks
-  auto skip_hi = [&](const int ch) -> int {
-    return g.skip_il ? ((ch + 1) * g.skip_chunks) / chunks : (ch == chunks - 1 ? g.skip_chunks : 0);
-  };
+  // chunks [sk, skip_hi(chunk)): all of them after the last main chunk.  (Spreading them evenly over the chunks - skip_hi(ch) =
+  // (ch + 1) * skip_chunks / chunks, so that a skip stage's 36 KB box + 16 KB of weights for only 4 MMAs loads behind main stages -
+  // was measured in round 2: the convolutions with a fused 1x1 skip did not change, profiles/r02_conv_ring_experiments.md 2f.)
+  auto skip_hi = [&](const int ch) -> int { return ch == chunks - 1 ? g.skip_chunks : 0; };
   auto role_tma = [&]() {
     if (lane == 0) {
       // ring positions are (slot, phase) pairs advanced incrementally: the depths are launch parameters, and a runtime % and /
@@ -1511,7 +1503,6 @@ int conv_tc_plan_create(const void *act_half, const void *w_half, int B, int H, 
   ConvTcGeom &g = p->g;
   g.B = B; g.H = H; g.W = W; g.Cin = Cin; g.Cout = 0; g.ksize = ksize; g.taps = ksize * ksize;
   g.a_wrap = split ? Cact / TC_BK : 0x7fffffff;
-  g.stagger = 0;
   p->split = split != 0;
   g.TW = W >= 128 ? 128 : pow2_ge(W);
   int th = 128 / g.TW;
@@ -1536,7 +1527,7 @@ int conv_tc_plan_create(const void *act_half, const void *w_half, int B, int H, 
   }
   if (p->v2) {
     ConvV2Geom &g2 = p->g2;
-    g2.B = B; g2.H = H; g2.W = W; g2.Cin = Cin; g2.Cout = 0; g2.skip_chunks = 0; g2.skip_chunks_a = 0; g2.skip_il = 0; g2.dbg = 0;
+    g2.B = B; g2.H = H; g2.W = W; g2.Cin = Cin; g2.Cout = 0; g2.skip_chunks = 0; g2.skip_chunks_a = 0; g2.dbg = 0;
     g2.a_wrap = g.a_wrap;
     g2.tiles_w = cdiv(W, 16); g2.tiles_h = cdiv(H, 16); g2.n_tiles = CoutPad / 128;
     g2.total_tiles = B * g2.tiles_w * g2.tiles_h * g2.n_tiles;
@@ -1790,9 +1781,6 @@ int launch_conv_tc(const ConvTcPlan *p, const ConvEpi &epi, int Cout, cudaStream
       g2.w_taps = nores ? ring[9] : (fused ? ring[5] : ring[2]);
       g2.pf_dist = fused ? ring[6] : 0;
       g2.stg_stride = nores ? 2048 : 6144;
-      static int skip_il = -1;                // DPIR_SKIP_INTERLEAVE=0: all fused-skip stages at the end of the tile's K loop (A/B timing)
-      if (skip_il < 0) { const char *e = getenv("DPIR_SKIP_INTERLEAVE"); skip_il = (e && e[0] == '0') ? 0 : 1; }
-      g2.skip_il = (skip_il && (!fused || p->gf_math == 3)) ? 1 : 0;      // the per-tap-box producers walk the round-1 order
       if (g2.a_slots * V2_A_BYTES + g2.w_slots * g2.w_taps * V3_W_BYTES + 8 * g2.stg_stride > V3_RING_BYTES + V3_STG_BYTES) {
         set_error("conv_tc: ring configuration exceeds the shared-memory budget");
         return DPIR_E_STATE;
@@ -1848,11 +1836,8 @@ int launch_conv_tc(const ConvTcPlan *p, const ConvEpi &epi, int Cout, cudaStream
   }
   ConvTcGeom g = p->g;
   g.Cout = Cout;
-  {
-    static int stagger = -1;               // DPIR_TC_STAGGER=1: staggered K order in the one-tile-per-CTA kernel (A/B timing)
-    if (stagger < 0) { const char *e = getenv("DPIR_TC_STAGGER"); stagger = (e && e[0] == '1') ? 1 : 0; }
-    g.stagger = stagger;
-  }
+  // (Measured in round 2, no effect: starting every CTA's K loop at a different (tap, chunk) so that the CTAs do not request the same
+  // L2 lines in lockstep - 8x8 / 1x1 layers unchanged within noise, profiles/r02_conv_ring_experiments.md section 2f.)
   if (p->BN == 16) return launch_tc_impl<16, 4>(p, g, epi, st);
   // (Small maps - 8x8 / 16x16 - run at ~250 TFLOP/s here.  Deeper rings (9 stages, one CTA per SM) were measured in round 2
   // and change nothing: with 128 x 64 tiles the arithmetic intensity is 43 FLOP per L2 byte and 128 CTAs pull ~6 TB/s from L2,
