@@ -1373,7 +1373,8 @@ int dpir_conv_gnfuse_f16io(const void *src1, int32_t C1, const void *src2, int32
     epi.mode = EPI_NHWC; epi.bias = bias; epi.out = reinterpret_cast<float *>(out_half);
     GnFuse gf;
     gf.src1 = (const __half *)src1; gf.C1 = C1; gf.src2 = (const __half *)src2; gf.C2 = C2; gf.coef = coef;
-    rc = residual_half ? DPIR_E_ARG : conv_tc_plan_set_gn_fuse(p, gf);
+    if (residual_half) { set_error("dpir_conv_gnfuse_f16io: the narrow-output form (CoutPad 16) takes no residual"); rc = DPIR_E_ARG; }
+    else rc = conv_tc_plan_set_gn_fuse(p, gf);
     if (!rc) rc = launch_conv_tc(p, epi, Cout, (cudaStream_t)stream);
     conv_tc_plan_destroy(p);
     return rc;
