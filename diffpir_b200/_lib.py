@@ -40,6 +40,7 @@ SIGNATURES = {
     "dpir_nccl_version": (c_int32, [POINTER(c_int32)]),
     "dpir_comm_unique_id": (c_int32, [c_void_p, c_size_t]),
     "dpir_comm_create": (c_int32, [c_void_p, c_int32, c_int32, POINTER(c_void_p)]),
+    "dpir_comm_adopt": (c_int32, [c_void_p, c_int32, c_int32, POINTER(c_void_p)]),
     "dpir_comm_destroy": (c_int32, [c_void_p]),
     "dpir_bcast_weights": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p]),
     "dpir_set_tables": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_int32]),

@@ -60,6 +60,7 @@ NcclApi *nccl_api() {
 struct dpir_comm {
   NcclComm comm = nullptr;
   int world = 0, rank = 0, device = 0;
+  bool owned = true;          // false: adopted from the host program (dpir_comm_adopt), never destroyed here
 };
 
 #define DPIR_NCCL_API(api)                                                                      \
@@ -117,10 +118,23 @@ int dpir_comm_create(const void *id, int32_t world, int32_t rank, dpir_comm **ou
   return DPIR_OK;
 }
 
+int dpir_comm_adopt(void *nccl_comm, int32_t world, int32_t rank, dpir_comm **out) {
+  DPIR_REQUIRE(nccl_comm && out, "dpir_comm_adopt: null pointer");
+  DPIR_REQUIRE(world >= 1 && rank >= 0 && rank < world, "dpir_comm_adopt: rank %d outside [0, %d)", rank, world);
+  DPIR_NCCL_API(api);
+  (void)api;
+  dpir_comm *c = new dpir_comm();
+  c->comm = reinterpret_cast<NcclComm>(nccl_comm);
+  c->world = world; c->rank = rank; c->owned = false;
+  if (cudaGetDevice(&c->device) != cudaSuccess) { delete c; dpir::set_error("dpir_comm_adopt: no CUDA device"); return DPIR_E_CUDA; }
+  *out = c;
+  return DPIR_OK;
+}
+
 int dpir_comm_destroy(dpir_comm *c) {
   if (!c) return DPIR_OK;
   NcclApi *api = nccl_api();
-  if (api->handle && c->comm) api->CommDestroy(c->comm);
+  if (c->owned && api->handle && c->comm) api->CommDestroy(c->comm);
   delete c;
   return DPIR_OK;
 }

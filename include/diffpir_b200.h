@@ -116,6 +116,9 @@ typedef struct dpir_comm dpir_comm;
 int dpir_nccl_version(int32_t *version);                       /* e.g. 22809; DPIR_E_STATE when no NCCL library can be bound */
 int dpir_comm_unique_id(void *id, size_t cap);
 int dpir_comm_create(const void *id, int32_t world, int32_t rank, dpir_comm **out);
+/* a host program that already owns an ncclComm_t (of the SAME libnccl the process carries) hands it over instead: `world` / `rank`
+ * as it was initialised with, its GPU current; the communicator is borrowed - dpir_comm_destroy does not destroy it */
+int dpir_comm_adopt(void *nccl_comm, int32_t world, int32_t rank, dpir_comm **out);
 int dpir_comm_destroy(dpir_comm *c);
 int dpir_bcast_weights(dpir_engine *e, dpir_comm *c, int32_t root, void *stream);
 

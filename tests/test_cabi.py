@@ -89,4 +89,6 @@ def test_weight_comm_binding_and_argument_checks():
     assert lib.dpir_comm_create(a, 2, 2, ctypes.byref(h)) == -1      # rank outside the world
     assert lib.dpir_comm_create(None, 1, 0, ctypes.byref(h)) == -1
     assert lib.dpir_bcast_weights(None, None, 0, None) == -1
+    assert lib.dpir_comm_adopt(None, 1, 0, ctypes.byref(h)) == -1    # no communicator to adopt
+    assert lib.dpir_comm_adopt(ctypes.c_void_p(1), 2, 5, ctypes.byref(h)) == -1
     assert lib.dpir_comm_destroy(None) == 0
