@@ -153,3 +153,16 @@ def test_imresize_tables_reproduce_reference_goldens():
     w, f = imresize_tables(256, 64, 0.25)
     assert w.dtype == np.float32 and f.dtype == np.int32 and f.min() >= 0 and f.max() < 256
     assert np.allclose(w.sum(0), 1, atol=1e-6)
+
+
+def test_kernel_design_checks():
+    """The numpy replays of the kernels' index arithmetic (no GPU): operand-producer thread mappings of k_conv3x3_v3 and the tiling /
+    horizontal-taps-in-N formulation of the narrow-output kernel k_conv3x3_dxn against a direct convolution."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for name in ("check_dxn_formulation", "check_producer_mapping"):
+        spec = importlib.util.spec_from_file_location(name, os.path.join(root, "tools", name + ".py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        mod.main()
