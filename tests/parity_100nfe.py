@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Full 100-NFE parity of the headline configuration against the fp64 evaluation of the reference formulae (evidence run, not
-part of the test-suite: the fp64 CPU oracle needs minutes).
+collected by pytest: the fp64 CPU oracle needs minutes; it lives under tests/ because it executes oracle/, which is test infrastructure).
 
 BASELINE config-2 shape - FFHQ architecture, 256x256, a Levin-size kernel, sigma 12.75/255, lambda 7, zeta 0.3, the full 100-entry
 quad schedule, one image, identical pre-drawn noise on every side:
@@ -8,7 +8,7 @@ quad schedule, one image, identical pre-drawn noise on every side:
     ref32 = CPU oracle in fp32          (pinned to the unmodified reference's goldens; `dev` = its own distance to ref64)
     GPU   = fp16s (throughput mode), fp16x3 (split-precision tensor-core mode), fp32 (CUDA cores), through the C-ABI
 Prints rel-L2 of the iterate x at steps 1 / 25 / 50 / 75 / 99 and of the final image, PSNR differences vs ground truth.
-Usage: python tools/parity_100nfe.py > profiles/rNN_parity_100nfe.txt
+Usage: python tests/parity_100nfe.py > profiles/rNN_parity_100nfe.txt
 """
 import os
 import sys
